@@ -1,0 +1,129 @@
+// api.cu — the extern "C" boundary declared in include/sylph_b200.h (context + seeding entry
+// points; the sketch / containment entry points live next to their kernels).
+#include <mutex>
+#include <new>
+
+#include "common.cuh"
+
+namespace syl {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off,
+                uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
+                uint64_t cap, uint64_t *n_out);
+
+// Stage caller memory on the device if needed. For SYL_MEM_DEVICE the pointer is used as is.
+template <typename T>
+struct Staged {
+    const T *p = nullptr;
+    DevBuf<T> buf;
+    int init(syl_ctx *ctx, int mem, const T *src, size_t n) {
+        if (mem == SYL_MEM_DEVICE) { p = src; return SYL_OK; }
+        if (mem != SYL_MEM_HOST) { set_error("bad mem"); return SYL_ERR_ARG; }
+        SYL_TRY(buf.alloc(n + 16 / sizeof(T) + 1, ctx->stream));
+        if (n) SYL_CUDA(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        p = buf.p;
+        return SYL_OK;
+    }
+};
+
+}  // namespace syl
+
+using namespace syl;
+
+extern "C" {
+
+const char *syl_last_error(void) { return g_last_error.c_str(); }
+int syl_abi_version(void) { return SYL_ABI_VERSION; }
+
+int syl_ctx_create(int device, void *stream, syl_ctx **out) {
+    if (!out) { set_error("out is NULL"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+        return SYL_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("bad device index"); return SYL_ERR_ARG; }
+    SYL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SYL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor) + "; this library only carries sm_100a code");
+        return SYL_ERR_CUDA;
+    }
+    syl_ctx *ctx = new (std::nothrow) syl_ctx();
+    if (!ctx) return SYL_ERR_OOM;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->own_stream = false;
+    } else {
+        cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete ctx; set_error(cudaGetErrorString(se)); return SYL_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    // keep freed scratch in the pool instead of returning it to the driver on every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    if (cudaMalloc((void **)&ctx->d_counters, 16 * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMallocHost((void **)&ctx->h_counters, 16 * sizeof(uint64_t)) != cudaSuccess) {
+        set_error("ctx scratch allocation failed");
+        syl_ctx_destroy(ctx);
+        return SYL_ERR_OOM;
+    }
+    *out = ctx;
+    return SYL_OK;
+}
+
+void syl_ctx_destroy(syl_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int syl_ctx_sync(syl_ctx *ctx) {
+    if (!ctx) { set_error("ctx is NULL"); return SYL_ERR_ARG; }
+    SYL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SYL_OK;
+}
+
+uint64_t syl_ctx_launch_count(const syl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
+                   const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
+                   syl_survivor *out, uint64_t cap, uint64_t *n_out) {
+    if (!ctx || !n_out || (!bases && n_bases) || !rec_off || (!out && cap)) {
+        set_error("NULL argument");
+        return SYL_ERR_ARG;
+    }
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    Staged<uint8_t> sb;
+    Staged<uint64_t> so;
+    SYL_TRY(sb.init(ctx, mem, bases, n_bases));
+    SYL_TRY(so.init(ctx, mem, rec_off, n_rec + 1));
+    if (mem == SYL_MEM_DEVICE) return seed_device(ctx, sb.p, n_bases, so.p, n_rec, k, c, sem, with_pos, out, cap, n_out);
+    DevBuf<syl_survivor> d_out;
+    SYL_TRY(d_out.alloc(cap, ctx->stream));
+    int rc = seed_device(ctx, sb.p, n_bases, so.p, n_rec, k, c, sem, with_pos, d_out.p, cap, n_out);
+    if (rc != SYL_OK) return rc;
+    if (*n_out) {
+        SYL_CUDA(cudaMemcpyAsync(out, d_out.p, *n_out * sizeof(syl_survivor), cudaMemcpyDeviceToHost, ctx->stream));
+        SYL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return SYL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// common.cuh — shared device/host helpers for the sylph_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/sylph_b200.h"
+
+namespace syl {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const std::string &msg);
+
+struct Status {
+    int code;
+    Status(int c = SYL_OK) : code(c) {}
+    bool ok() const { return code == SYL_OK; }
+};
+
+#define SYL_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ::syl::set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + " (" +       \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                   \
+            return (_e == cudaErrorMemoryAllocation) ? SYL_ERR_OOM : SYL_ERR_CUDA;               \
+        }                                                                                        \
+    } while (0)
+
+#define SYL_TRY(expr)                                                                            \
+    do {                                                                                         \
+        int _s = (expr);                                                                         \
+        if (_s != SYL_OK) return _s;                                                             \
+    } while (0)
+
+// ---- context --------------------------------------------------------------------------------
+}  // namespace syl
+
+struct syl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    uint64_t launches = 0;
+    // small persistent scratch: device counters + pinned host mirror
+    uint64_t *d_counters = nullptr;  // 16 x u64
+    uint64_t *h_counters = nullptr;  // pinned
+};
+
+namespace syl {
+
+// stream-ordered temporary device buffer (cudaMallocAsync from the device's default pool)
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream;
+        n = count;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error(std::string("cudaMallocAsync(") + std::to_string(count * sizeof(T)) +
+                      " B): " + cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? SYL_ERR_OOM : SYL_ERR_CUDA;
+        }
+        return SYL_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    T *take() {
+        T *q = p;
+        p = nullptr;
+        n = 0;
+        return q;
+    }
+};
+
+// ---- the reference's arithmetic, device side ------------------------------------------------
+
+// src/types.rs:50-59 BYTE_TO_SEQ, as arithmetic (used off the hot path; the seeding kernel uses
+// a shared-memory copy of the same 256-entry table, built from this function).
+__host__ __device__ __forceinline__ uint32_t byte_to_seq(uint32_t b) {
+    switch (b) {
+        case 1: case 'C': case 'c': return 1u;
+        case 2: case 'G': case 'g': return 2u;
+        case 3: case 'T': case 't': case 'U': case 'u': return 3u;
+        default: return 0u;
+    }
+}
+
+// src/seeding.rs:4-15 — the shipped hash; line 7 negates the SUM key + (key << 21).
+// Written with multiplies (k + (k<<21) == k * 0x200001 etc.) so that ptxas maps the four
+// multiply steps to the FMA pipe (IMAD) and the three xor-shifts to the ALU pipe.
+__host__ __device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
+    key = ~(key * 0x200001ull);
+    key ^= key >> 24;
+    key *= 265ull;
+    key ^= key >> 14;
+    key *= 21ull;
+    key ^= key >> 28;
+    key *= 0x80000001ull;
+    return key;
+}
+
+__host__ __device__ __forceinline__ uint64_t fmh_threshold(uint64_t c) {
+    return 0xFFFFFFFFFFFFFFFFull / c;  // src/seeding.rs:108
+}
+
+// number of window START positions the reference visits in a record of length L
+// (SURVEY §0 R2).  with_pos selects the positions-variant short-sequence rule.
+__host__ __device__ __forceinline__ uint64_t valid_windows(uint64_t L, uint32_t k, int sem,
+                                                           int with_pos) {
+    if (L < k) return 0;
+    if (sem == SYL_SEM_SCALAR) return L - k + 1;
+    uint64_t min_len = with_pos ? 2ull * k : (uint64_t)k + 1;
+    if (L < min_len) return 0;
+    return 4ull * ((L - k + 1) / 4);
+}
+
+}  // namespace syl

@@ -1,0 +1,332 @@
+// seed.cu — FracMinHash seeding on sm_100a.
+//
+// Replaces, for a whole batch of records at once, the reference's per-record
+//   extract_markers            (src/sketch.rs:53-69  -> src/avx2_seeding.rs:33-148 / src/seeding.rs:86-146)
+//   extract_markers_positions  (src/sketch.rs:71-93  -> src/avx2_seeding.rs:151-266 / src/seeding.rs:148-209)
+//
+// Formulation (nothing here mirrors the AVX2 traversal; only its window *set* is kept):
+//   * the batch is one flat ASCII buffer; a CTA owns a tile of SEED_TILE window-start positions
+//   * the tile (+halo) is staged HBM -> shared memory with one TMA bulk copy (cp.async.bulk +
+//     mbarrier complete_tx), then packed ONCE into two 2-bit streams:
+//        fw: forward codes, MSB-first     -> forward k-mer of any window = one 64-bit funnel extract
+//        cw: complement codes, LSB-first  -> reverse-complement k-mer  = one 64-bit funnel extract
+//     so windows are independent (no serial roll, no per-window byte loads)
+//   * the records overlapping the tile are cut into runs of <= SEED_W consecutive VALID window
+//     starts (the AVX2 lane rule is just "start < 4*((L-k+1)/4)"), one run per thread, so no
+//     issue slots are spent on windows that straddle a record boundary (20 % of all windows
+//     for 150 bp reads)
+//   * per window: 2+2 funnel shifts, 64-bit min, the 64-bit hash (4 IMAD-pipe multiplies +
+//     3 ALU-pipe xor-shifts), one compare of the high word against the threshold
+//   * survivors (1/c of windows) are staged in shared memory and flushed with one global
+//     atomic per CTA
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace syl {
+
+constexpr int SEED_THREADS = 256;
+constexpr int SEED_TILE = 32768;   // window-start positions (== bases) per CTA
+constexpr int SEED_W = 32;         // windows per thread-run
+constexpr int SEED_HALO = 48;      // bytes staged past the tile (>= k-1, multiple of 16)
+constexpr int SEED_STAGE = 512;    // survivors staged per CTA before falling back to global atomics
+constexpr int SEED_ASC_BYTES = SEED_TILE + SEED_HALO;  // 32816, multiple of 16
+constexpr int SEED_NCHUNK16 = SEED_ASC_BYTES / 16;     // 2051 16-base words per stream
+constexpr int SEED_FW_WORDS = SEED_NCHUNK16 + 1 + 8;   // +1 leading pad word, +8 slack for run loads
+constexpr int SEED_CW_WORDS = SEED_NCHUNK16 + 8;
+
+struct SeedSmem {
+    // region A: ASCII staging; after packing it is reused for the per-chunk record table and
+    // the survivor staging buffer (see offsets below)
+    alignas(128) uint8_t asc[SEED_ASC_BYTES + 16];
+    alignas(16) uint32_t fw[SEED_FW_WORDS];
+    alignas(16) uint32_t cw[SEED_CW_WORDS];
+    alignas(16) uint8_t lut[256];
+    alignas(8) unsigned long long mbar;
+};
+// views into region A once the ASCII bytes are dead
+struct SeedMeta {
+    long long rel[SEED_THREADS];      // rec_off[r] - tile_start (may be very negative)
+    int s0[SEED_THREADS];             // first valid window start inside the tile (tile-relative)
+    int cnt[SEED_THREADS];            // number of valid window starts inside the tile
+    int rbase[SEED_THREADS + 1];      // exclusive scan of ceil(cnt / SEED_W)
+    int warp_tot[SEED_THREADS / 32];
+    unsigned int stage_count;
+    unsigned long long flush_base;
+    alignas(16) syl_survivor stage[SEED_STAGE];
+};
+static_assert(sizeof(SeedMeta) <= SEED_ASC_BYTES, "meta must fit in the dead ASCII region");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// tile t -> index of the record that contains flat position t*SEED_TILE
+__global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t n_rec,
+                                 uint64_t n_tiles, uint32_t *__restrict__ tile_rec) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    if (t == n_tiles) {
+        tile_rec[t] = (uint32_t)(n_rec - 1);
+        return;
+    }
+    uint64_t pos = t * (uint64_t)SEED_TILE;
+    // upper_bound over rec_off[0..n_rec]: first i with rec_off[i] > pos
+    uint64_t lo = 0, hi = n_rec + 1;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (rec_off[mid] > pos) hi = mid; else lo = mid + 1;
+    }
+    uint64_t r = lo == 0 ? 0 : lo - 1;
+    if (r >= n_rec) r = n_rec - 1;
+    tile_rec[t] = (uint32_t)r;
+}
+
+template <int K>
+__global__ void __launch_bounds__(SEED_THREADS, 4)
+k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__restrict__ rec_off,
+       const uint32_t *__restrict__ tile_rec, uint64_t thr, int sem, int with_pos,
+       syl_survivor *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SeedSmem &S = *reinterpret_cast<SeedSmem *>(smem_raw);
+    SeedMeta &M = *reinterpret_cast<SeedMeta *>(S.asc);
+
+    constexpr uint32_t PAD = 64 - 2 * K;                     // unused high bits of a k-mer word
+    constexpr uint32_t HI_MASK = (1u << (32 - PAD)) - 1u;    // K=31: 0x3FFFFFFF, K=21: 0x3FF
+    const int tid = threadIdx.x;
+    const uint64_t T0 = (uint64_t)blockIdx.x * SEED_TILE;
+    const uint64_t T1 = T0 + SEED_TILE;
+    const uint32_t thr_hi = (uint32_t)(thr >> 32);
+
+    // ---- stage the tile: TMA bulk copy for the 16-byte-aligned body, plain loads for the tail
+    const uint64_t remain = n_bases - T0;
+    const uint32_t avail = remain < (uint64_t)SEED_ASC_BYTES ? (uint32_t)remain : (uint32_t)SEED_ASC_BYTES;
+    const uint32_t nbulk = avail & ~15u;
+    const uint32_t mbar = smem_u32(&S.mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && nbulk) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(nbulk)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(S.asc)),
+            "l"(bases + T0), "r"(nbulk), "r"(mbar)
+            : "memory");
+    }
+    // tail (< 16 bytes) and zero fill of everything past the end of the buffer
+    for (uint32_t i = nbulk + tid; i < (uint32_t)SEED_ASC_BYTES + 16; i += SEED_THREADS)
+        S.asc[i] = (i < avail) ? bases[T0 + i] : (uint8_t)0;
+    S.lut[tid] = (uint8_t)byte_to_seq((uint32_t)tid);
+    if (tid < 8) {
+        S.fw[SEED_NCHUNK16 + 1 + tid] = 0u;
+        S.cw[SEED_NCHUNK16 + tid] = 0u;
+    }
+    if (tid == 0) S.fw[0] = 0u;
+    if (nbulk) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(mbar)
+                : "memory");
+        }
+    }
+    __syncthreads();
+
+    // ---- pack: 16 ASCII bytes -> one forward word (MSB-first) + one complement word (LSB-first)
+    for (int ch = tid; ch < SEED_NCHUNK16; ch += SEED_THREADS) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(S.asc + 16 * ch);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t f = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t byte = (w[q] >> (8 * b)) & 0xFFu;
+                f = (f << 2) | (uint32_t)S.lut[byte];
+            }
+        }
+        // complement stream: base j's (3 - code) at bits [2j, 2j+2): reverse the 16 fields of f
+        uint32_t x = __brev(f);                                        // fields reversed, bits swapped in each
+        x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);       // swap bits back inside each field
+        S.fw[1 + ch] = f;
+        S.cw[ch] = ~x;
+    }
+    __syncthreads();  // ASCII bytes are dead from here on; region A becomes SeedMeta
+
+    if (tid == 0) M.stage_count = 0u;
+
+    const uint32_t r_lo = tile_rec[blockIdx.x];
+    const uint32_t r_hi = tile_rec[blockIdx.x + 1];  // inclusive
+    const int lane = tid & 31, wid = tid >> 5;
+
+    for (uint64_t rc = r_lo; rc <= (uint64_t)r_hi; rc += SEED_THREADS) {
+        // -- per-record table for this chunk of (up to) SEED_THREADS records
+        int runs = 0;
+        const uint64_t r = rc + tid;
+        if (r <= (uint64_t)r_hi) {
+            const uint64_t a = rec_off[r], b = rec_off[r + 1];
+            const uint64_t L = b - a;
+            const uint64_t nv = valid_windows(L, (uint32_t)K, sem, with_pos);
+            const uint64_t lo = a > T0 ? a : T0;
+            uint64_t hi = a + nv;
+            if (hi > T1) hi = T1;
+            const int cnt = hi > lo ? (int)(hi - lo) : 0;
+            M.rel[tid] = (long long)a - (long long)T0;
+            M.s0[tid] = (int)(lo - T0);
+            M.cnt[tid] = cnt;
+            runs = (cnt + SEED_W - 1) / SEED_W;
+        }
+        // block-wide exclusive scan of runs
+        int incl = runs;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) M.warp_tot[wid] = incl;
+        __syncthreads();
+        int wbase = 0;
+#pragma unroll
+        for (int w = 0; w < SEED_THREADS / 32; w++) wbase += (w < wid) ? M.warp_tot[w] : 0;
+        M.rbase[tid] = wbase + incl - runs;
+        if (tid == SEED_THREADS - 1) M.rbase[SEED_THREADS] = wbase + incl;
+        __syncthreads();
+        const int total = M.rbase[SEED_THREADS];
+        const uint64_t nrec_left = (uint64_t)r_hi - rc + 1;
+        const int nrec = nrec_left < (uint64_t)SEED_THREADS ? (int)nrec_left : SEED_THREADS;
+
+        // -- one run of <= SEED_W windows per thread per pass
+        for (int q = tid; q < total; q += SEED_THREADS) {
+            // largest j in [0,nrec) with rbase[j] <= q
+            int jlo = 0, jhi = nrec;
+            while (jhi - jlo > 1) {
+                int mid = (jlo + jhi) >> 1;
+                if (M.rbase[mid] <= q) jlo = mid; else jhi = mid;
+            }
+            const int j = jlo;
+            const int ridx = q - M.rbase[j];
+            const int p = M.s0[j] + ridx * SEED_W;            // tile-relative first window start
+            const int n = min(SEED_W, M.cnt[j] - ridx * SEED_W);
+            const uint32_t rec = (uint32_t)(rc + j);
+            const uint32_t pos0 = (uint32_t)((long long)p - M.rel[j] + (K - 1));
+
+            // realign the two streams so that window i of this run starts at bit 2i
+            uint32_t F[4], G[4];
+            {
+                const uint32_t bitpos = 32u + 2u * (uint32_t)p - PAD;
+                const uint32_t q0 = bitpos >> 5, sh = bitpos & 31u;
+                uint32_t w0 = S.fw[q0], w1 = S.fw[q0 + 1], w2 = S.fw[q0 + 2], w3 = S.fw[q0 + 3],
+                         w4 = S.fw[q0 + 4];
+                F[0] = __funnelshift_l(w1, w0, sh);
+                F[1] = __funnelshift_l(w2, w1, sh);
+                F[2] = __funnelshift_l(w3, w2, sh);
+                F[3] = __funnelshift_l(w4, w3, sh);
+                const uint32_t cq = (uint32_t)p >> 4, csh = ((uint32_t)p & 15u) * 2u;
+                uint32_t c0 = S.cw[cq], c1 = S.cw[cq + 1], c2 = S.cw[cq + 2], c3 = S.cw[cq + 3],
+                         c4 = S.cw[cq + 4];
+                G[0] = __funnelshift_r(c0, c1, csh);
+                G[1] = __funnelshift_r(c1, c2, csh);
+                G[2] = __funnelshift_r(c2, c3, csh);
+                G[3] = __funnelshift_r(c3, c4, csh);
+            }
+#pragma unroll
+            for (int i = 0; i < SEED_W; i++) {
+                const int jb = (2 * i) >> 5;
+                const uint32_t s = (uint32_t)((2 * i) & 31);
+                const uint32_t f_hi = __funnelshift_l(F[jb + 1], F[jb], s) & HI_MASK;
+                const uint32_t f_lo = __funnelshift_l(F[jb + 2], F[jb + 1], s);
+                const uint32_t r_lo32 = __funnelshift_r(G[jb], G[jb + 1], s);
+                const uint32_t r_hi32 = __funnelshift_r(G[jb + 1], G[jb + 2], s) & HI_MASK;
+                const uint64_t f = ((uint64_t)f_hi << 32) | f_lo;
+                const uint64_t rr = ((uint64_t)r_hi32 << 32) | r_lo32;
+                const uint64_t canon = f < rr ? f : rr;  // src/seeding.rs:131-136
+                const uint64_t h = mm_hash64(canon);
+                if ((uint32_t)(h >> 32) <= thr_hi) {      // cheap pre-test on the high word
+                    if (h < thr && i < n) {               // src/seeding.rs:139
+                        syl_survivor sv;
+                        sv.hash = h;
+                        sv.rec = rec;
+                        sv.pos = pos0 + (uint32_t)i;
+                        const unsigned int idx = atomicAdd(&M.stage_count, 1u);
+                        if (idx < (unsigned)SEED_STAGE) {
+                            M.stage[idx] = sv;
+                        } else {
+                            const unsigned long long g = atomicAdd(g_count, 1ull);
+                            if (g < cap) out[g] = sv;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // table is rewritten by the next chunk
+    }
+
+    // ---- flush staged survivors: one global atomic per CTA, coalesced 16-byte stores
+    __syncthreads();
+    const unsigned int staged = min(M.stage_count, (unsigned)SEED_STAGE);
+    if (tid == 0 && staged) M.flush_base = atomicAdd(g_count, (unsigned long long)staged);
+    __syncthreads();
+    if (staged) {
+        const unsigned long long base = M.flush_base;
+        for (unsigned int i = tid; i < staged; i += SEED_THREADS)
+            if (base + i < cap) out[base + i] = M.stage[i];
+    }
+}
+
+// Host launcher: device-resident inputs, survivors to a device buffer. *n_out is the true
+// number of survivors even when it exceeds cap (then SYL_ERR_CAPACITY).
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off,
+                uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
+                uint64_t cap, uint64_t *n_out) {
+    *n_out = 0;
+    if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
+    if (!(k == 21 || k == 31)) {
+        set_error("k must be 21 or 31 (the reference panics otherwise, src/avx2_seeding.rs:46-52)");
+        return SYL_ERR_UNSUPPORTED;
+    }
+    if (sem != SYL_SEM_SCALAR && sem != SYL_SEM_AVX2) { set_error("bad sem"); return SYL_ERR_ARG; }
+    if (n_rec == 0 || n_bases == 0) return SYL_OK;
+    if (n_rec >= 0xFFFFFFFFull) { set_error("more than 2^32-2 records in one batch"); return SYL_ERR_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) != 0) {
+        set_error("device base buffer must be 16-byte aligned (TMA bulk copy)");
+        return SYL_ERR_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_tiles = (n_bases + SEED_TILE - 1) / SEED_TILE;
+    DevBuf<uint32_t> tile_rec;
+    SYL_TRY(tile_rec.alloc(n_tiles + 1, st));
+    {
+        const int bs = 256;
+        const uint64_t nb = (n_tiles + 1 + bs - 1) / bs;
+        k_tile_first_rec<<<(unsigned)nb, bs, 0, st>>>(d_rec_off, n_rec, n_tiles, tile_rec.p);
+        ctx->launches++;
+    }
+    SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint64_t), st));
+    const uint64_t thr = fmh_threshold(c);
+    const size_t smem = sizeof(SeedSmem);
+    auto kern = (k == 31) ? k_seed<31> : k_seed<21>;
+    SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
+        d_bases, n_bases, d_rec_off, tile_rec.p, thr, sem, with_pos, d_out, cap,
+        reinterpret_cast<unsigned long long *>(ctx->d_counters));
+    ctx->launches++;
+    SYL_CUDA(cudaGetLastError());
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    *n_out = ctx->h_counters[0];
+    if (*n_out > cap) {
+        set_error("survivor buffer too small");
+        return SYL_ERR_CAPACITY;
+    }
+    return SYL_OK;
+}
+
+}  // namespace syl

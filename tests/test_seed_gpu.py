@@ -1,0 +1,110 @@
+"""GPU parity: batched seeding (syl_seed_batch) vs the CPU oracle, bit-exact survivor sets."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import DATA, flatten, read_fastx
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_survivors(buf, off, k, c, sem, with_pos):
+    from oracle import oracle as O
+    rows = []
+    for r in range(len(off) - 1):
+        s = buf[int(off[r]):int(off[r + 1])]
+        if with_pos:
+            pos, h = O.extract_markers_positions(s, k, c, sem)
+        else:
+            # the hash-only variant reports no positions; recover them from the positions variant
+            # under the hash-only length rule by brute force: same windows, so compare hashes only
+            h = O.extract_markers(s, k, c, sem)
+            pos = np.zeros(len(h), dtype=np.uint64)
+        for p, x in zip(pos, h):
+            rows.append((r, int(p), int(x)))
+    return rows
+
+
+def check(ctx, buf, off, k, c, sem, with_pos):
+    sv = ctx.extract_markers_batch(buf, off, k=k, c=c, sem=sem, with_pos=with_pos)
+    exp = oracle_survivors(buf, off, k, c, sem, with_pos)
+    if with_pos:
+        got = sorted((int(a), int(b), int(h)) for h, a, b in zip(sv["hash"], sv["rec"], sv["pos"]))
+        assert got == sorted(exp)
+    else:
+        got = sorted((int(a), int(h)) for h, a in zip(sv["hash"], sv["rec"]))
+        assert got == sorted((r, h) for r, _, h in exp)
+    return len(exp)
+
+
+def random_records(rng, lengths, alphabet=b"ACGT"):
+    seqs = [bytes(rng.choice(list(alphabet), size=int(n)).astype(np.uint8)) for n in lengths]
+    return flatten(seqs)
+
+
+@pytest.mark.parametrize("k", [31, 21])
+@pytest.mark.parametrize("sem", [1, 0])
+@pytest.mark.parametrize("with_pos", [False, True])
+def test_ragged_edge_lengths(ctx, k, sem, with_pos):
+    rng = np.random.default_rng(7 + k + sem)
+    lengths = [0, 1, 7, k - 1, k, k + 1, k + 2, k + 3, k + 4, 2 * k - 1, 2 * k, 2 * k + 1, 66, 70, 100, 149, 150, 151,
+               250, 399, 400, 401, 1000, 4097, 0, 0, 33000, 12, 65536 + 17, 150, 150, 150]
+    lengths += list(rng.integers(0, 600, size=700))
+    buf, off = random_records(rng, lengths, alphabet=b"ACGTNacgtnRYU\x00\x01\x02\x03*")
+    n = check(ctx, buf, off, k, 5, sem, with_pos)
+    assert n > 1000
+
+
+@pytest.mark.parametrize("c", [1, 3, 200, 1000])
+def test_c_values(ctx, c):
+    rng = np.random.default_rng(11)
+    buf, off = random_records(rng, list(rng.integers(100, 300, size=300)) + [40000])
+    check(ctx, buf, off, 31, c, 1, True)
+
+
+def test_single_long_contig_tile_boundaries(ctx):
+    rng = np.random.default_rng(5)
+    for L in (32768, 32768 + 30, 32768 + 31, 2 * 32768 - 1, 3 * 32768 + 123):
+        buf, off = random_records(rng, [L])
+        check(ctx, buf, off, 31, 50, 1, True)
+        check(ctx, buf, off, 31, 50, 0, True)
+
+
+def test_many_tiny_records(ctx):
+    rng = np.random.default_rng(9)
+    lengths = list(rng.integers(0, 40, size=20000))
+    buf, off = random_records(rng, lengths)
+    check(ctx, buf, off, 31, 2, 1, False)
+    check(ctx, buf, off, 21, 2, 0, True)
+
+
+def test_ecoli_genome_positions(ctx):
+    recs = read_fastx(os.path.join(DATA, "e.coli-o157.fasta.gz"))
+    buf, off = flatten([s for _, s in recs])
+    n = check(ctx, buf, off, 31, 200, 1, True)
+    assert 20000 < n < 35000
+
+
+def test_o157_reads(ctx):
+    recs = read_fastx(os.path.join(DATA, "o157_reads.fastq.gz"))
+    buf, off = flatten([s for _, s in recs])
+    check(ctx, buf, off, 31, 200, 1, False)
+
+
+def test_device_resident_inputs(ctx):
+    import torch
+    rng = np.random.default_rng(3)
+    buf, off = random_records(rng, list(rng.integers(50, 500, size=2000)))
+    tb = torch.from_numpy(buf).cuda()
+    to = torch.from_numpy(off.astype(np.int64)).cuda()
+    sv_d = ctx.extract_markers_batch(tb, to, k=31, c=20, with_pos=True)
+    sv_h = ctx.extract_markers_batch(buf, off, k=31, c=20, with_pos=True)
+    assert sorted(sv_d.tolist()) == sorted(sv_h.tolist())
+
+
+def test_unsupported_k(ctx):
+    from sylph_b200 import SylphError
+    buf, off = flatten([b"ACGT" * 50])
+    with pytest.raises(SylphError):
+        ctx.extract_markers_batch(buf, off, k=25)
