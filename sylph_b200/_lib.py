@@ -92,9 +92,7 @@ def lib():
         so = _build.build()
     L = C.CDLL(so)  # raises OSError if missing: no fallback
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(L, name, None)
-        if fn is None:  # tests/test_abi.py asserts that every declared symbol is exported
-            continue
+        fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
     _LIB = L

@@ -112,3 +112,189 @@ class Context:
             if mem_b == _lib.MEM_DEVICE:
                 return dbuf[: 2 * n].cpu().numpy().view(SURVIVOR_DTYPE).copy()
             return hbuf[:n].copy()
+
+    # ---- (2) sample sketch -------------------------------------------------------------------
+    def sketch_sequences(self, bases, rec_off, k=31, c=200, no_dedup=False, sem=SEM_AVX2):
+        """Batched body of sketch_sequences_needle (src/sketch.rs:897-959) -> Sample."""
+        L = _lib.lib()
+        mem_b, pb, nb, kb = _arg(bases, np.uint8)
+        mem_o, po, no, ko = _arg(rec_off, np.uint64)
+        if mem_b != mem_o:
+            raise ValueError("bases and rec_off must live in the same memory space")
+        h = C.c_void_p()
+        _lib.check(L.syl_sketch_reads(self._h, mem_b, pb, nb, po, no - 1, k, c, int(no_dedup), sem, C.byref(h)))
+        return Sample(self, h)
+
+    def upload_sample(self, hashes, counts, k=31, c=200):
+        L = _lib.lib()
+        mem_h, ph, nh, kh = _arg(hashes, np.uint64)
+        mem_c, pc, nc, kc = _arg(counts, np.uint32)
+        assert mem_h == mem_c and nh == nc
+        h = C.c_void_p()
+        _lib.check(L.syl_sample_upload(self._h, mem_h, ph, pc, nh, k, c, C.byref(h)))
+        return Sample(self, h)
+
+    # ---- (3) genome sketches -----------------------------------------------------------------
+    def sketch_genomes(self, bases, contig_off, genome_off=None, k=31, c=200, min_spacing=30, pseudotax=True,
+                       individual=False, sem=SEM_AVX2):
+        """Batched sketch_genome / sketch_genome_individual (src/sketch.rs:550-622, 481-548)."""
+        L = _lib.lib()
+        mem_b, pb, nb, kb = _arg(bases, np.uint8)
+        mem_o, po, no, ko = _arg(contig_off, np.uint64)
+        n_genomes = 0
+        pg = None
+        if not individual:
+            mem_g, pg, ng, kg = _arg(genome_off, np.uint64)
+            assert mem_g == mem_b
+            n_genomes = ng - 1
+        h = C.c_void_p()
+        _lib.check(L.syl_sketch_genomes(self._h, mem_b, pb, nb, po, no - 1, pg, n_genomes, k, c, min_spacing,
+                                        int(pseudotax), int(individual), sem, C.byref(h)))
+        return Genomes(self, h)
+
+    def upload_genomes(self, kmers, kmer_off, tracked=None, tracked_off=None, gn_size=None, k=31, c=200):
+        L = _lib.lib()
+        mem, pk, nk, k1 = _arg(kmers, np.uint64)
+        _, pko, nko, k2 = _arg(kmer_off, np.uint64)
+        _, pt, nt, k3 = _arg(tracked, np.uint64)
+        _, pto, nto, k4 = _arg(tracked_off, np.uint64)
+        _, pg, ngs, k5 = _arg(gn_size, np.uint64)
+        h = C.c_void_p()
+        _lib.check(L.syl_genomes_upload(self._h, mem, pk, pko, pt, pto, pg, nko - 1, k, c, C.byref(h)))
+        return Genomes(self, h)
+
+    # ---- (4) containment ---------------------------------------------------------------------
+    def build_db(self, genomes, genome_base=0):
+        """Index a batch of genome sketches for probing (syl_db_build)."""
+        h = C.c_void_p()
+        _lib.check(_lib.lib().syl_db_build(self._h, genomes._h, int(genome_base), C.byref(h)))
+        return Db(self, h)
+
+    def _pairs(self, fn, db, samples, params, cap):
+        L = _lib.lib()
+        n = len(samples)
+        arr = (C.c_void_p * max(n, 1))(*[s._h for s in samples])
+        if cap is None:
+            cap = max(1024, min(len(db) * max(n, 1), 1 << 20))
+        while True:
+            rows = np.zeros(cap, dtype=ANI_ROW_DTYPE)
+            n_rows = C.c_uint64(0)
+            rc = fn(self._h, db._h, arr, n, C.byref(params), rows.ctypes.data_as(C.c_void_p), cap, C.byref(n_rows))
+            if rc == _lib.SYL_ERR_CAPACITY:
+                cap = n_rows.value
+                continue
+            _lib.check(rc)
+            return rows[: n_rows.value].copy()
+
+    def query(self, db, samples, params=None, cap=None):
+        """Pass-1 get_stats over samples x db (`sylph query`); rows ordered by (sample, genome)."""
+        params = params or contain_params(pseudotax=False)
+        return self._pairs(_lib.lib().syl_query, db, samples, params, cap)
+
+    def profile(self, db, samples, params=None, cap=None):
+        """`sylph profile`: pass 1, winner table, pass 2, derep, abundances; per sample sorted by rel_abund."""
+        params = params or contain_params(pseudotax=True)
+        return self._pairs(_lib.lib().syl_profile, db, samples, params, cap)
+
+
+def contain_params(k=31, pseudotax=False, **kw):
+    p = ContainParams()
+    _lib.lib().syl_contain_params_default(C.byref(p), k, int(pseudotax))
+    for a, b in kw.items():
+        setattr(p, a, b)
+    return p
+
+
+class Db:
+    """Probe index over a batch of genome sketches (syl_db)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    def __len__(self):
+        return int(_lib.lib().syl_db_num_genomes(self._h))
+
+    def free(self):
+        if self._h:
+            _lib.lib().syl_db_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Sample:
+    """Device-resident SequencesSketch.kmer_counts (src/types.rs:145-155), sorted by hash."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    def __len__(self):
+        return int(_lib.lib().syl_sample_size(self._h))
+
+    @property
+    def mean_read_length(self):
+        return float(_lib.lib().syl_sample_mean_read_length(self._h))
+
+    @property
+    def num_dup_removed(self):
+        return int(_lib.lib().syl_sample_num_dup_removed(self._h))
+
+    def download(self):
+        n = len(self)
+        h = np.empty(n, dtype=np.uint64)
+        c = np.empty(n, dtype=np.uint32)
+        _lib.check(_lib.lib().syl_sample_download(self.ctx._h, self._h, h.ctypes.data_as(C.c_void_p),
+                                                  c.ctypes.data_as(C.c_void_p)))
+        return h, c
+
+    def free(self):
+        if self._h:
+            _lib.lib().syl_sample_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Genomes:
+    """Device-resident batch of GenomeSketch (src/types.rs:163-173) in CSR form."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    def __len__(self):
+        return int(_lib.lib().syl_genomes_count(self._h))
+
+    @property
+    def has_tracked(self):
+        return bool(_lib.lib().syl_genomes_has_tracked(self._h))
+
+    def download(self):
+        """-> dict(kmers, kmer_off, tracked, tracked_off, gn_size)"""
+        L = _lib.lib()
+        n = len(self)
+        nk, nt = int(L.syl_genomes_total_kmers(self._h)), int(L.syl_genomes_total_tracked(self._h))
+        d = dict(kmers=np.empty(nk, np.uint64), kmer_off=np.empty(n + 1, np.uint64), tracked=np.empty(nt, np.uint64),
+                 tracked_off=np.empty(n + 1, np.uint64), gn_size=np.empty(n, np.uint64))
+        _lib.check(L.syl_genomes_download(self.ctx._h, self._h, *[d[x].ctypes.data_as(C.c_void_p) for x in
+                                                                   ("kmers", "kmer_off", "tracked", "tracked_off",
+                                                                    "gn_size")]))
+        return d
+
+    def free(self):
+        if self._h:
+            _lib.lib().syl_genomes_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,20 +1,24 @@
 """Build the sm_100a shared library in-tree (sylph_b200/libsylph_b200.so).
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the
-gpurun snapshot.  `python -m sylph_b200.build` rebuilds unconditionally.
+gpurun snapshot.  Each .cu is compiled to build/<name>.o (in parallel, only when stale) and the
+objects are linked into the .so.  `python -m sylph_b200.build [-v] [-f]`.
 """
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libsylph_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "sylph_b200.h")
 SOURCES = ["api.cu", "seed.cu", "sample.cu", "genome.cu", "contain.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
 
 
@@ -25,20 +29,27 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _headers_mtime():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [HEADER]
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _stale(src, obj, hm):
+    return (not os.path.exists(obj)) or os.path.getmtime(obj) < max(os.path.getmtime(src), hm)
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(HERE, "..", "include", "sylph_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return _headers_mtime() > t or any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in _sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return SO
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + srcs
+def _run(cmd, verbose):
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -46,10 +57,27 @@ def build(force=False, verbose=False):
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed")
+        raise RuntimeError("command failed: " + " ".join(cmd))
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    hm = _headers_mtime()
+    jobs, objs = [], []
+    for s in _sources():
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(src, obj, hm):
+            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        list(ex.map(lambda c: _run(c, verbose), jobs))
+    _run([nvcc, "-shared", "-o", SO] + objs, verbose)
     return SO
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
+    build(force="-f" in sys.argv, verbose="-v" in sys.argv)
     print(SO)

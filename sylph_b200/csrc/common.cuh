@@ -50,6 +50,31 @@ struct syl_ctx {
     uint64_t *h_counters = nullptr;  // pinned
 };
 
+// Device-resident SequencesSketch.kmer_counts (src/types.rs:145-155): parallel arrays sorted by hash
+struct syl_sample {
+    int device = 0;
+    uint64_t *hash = nullptr;  // ascending, distinct
+    uint32_t *count = nullptr;
+    uint64_t n = 0;
+    int k = 31;
+    uint64_t c = 200;
+    double mean_read_length = 0.;
+    uint64_t num_dup_removed = 0;
+};
+
+// Device-resident batch of GenomeSketch (src/types.rs:163-173) in CSR form
+struct syl_genomes {
+    int device = 0;
+    uint64_t n = 0;                                       // genomes
+    uint64_t *kmers = nullptr, *kmer_off = nullptr;       // genome_kmers, position order
+    uint64_t *tracked = nullptr, *tracked_off = nullptr;  // pseudotax_tracked_nonused_kmers
+    uint64_t *gn_size = nullptr;
+    uint64_t total_kmers = 0, total_tracked = 0;
+    int has_tracked = 0;
+    int k = 31;
+    uint64_t c = 200;
+};
+
 namespace syl {
 
 // stream-ordered temporary device buffer (cudaMallocAsync from the device's default pool)

@@ -1,0 +1,796 @@
+// contain.cu — containment query / profile on sm_100a.
+//
+// Replaces, for every (sample, genome) pair at once, the get_stats loops of contain()
+// (src/contain.rs:284-292 pass 1, :297-327 pass 2) including
+//   probe loop                      src/contain.rs:632-652
+//   median / Poisson cut / means    :657-690   (statrs Poisson CDF -> 29-entry cutoff table)
+//   ratio_lambda                    src/inference.rs:207-242
+//   ani_from_lambda                 src/contain.rs:817-847
+//   bootstrap_interval              :849-898   (fastrand WyRand, counter-based here)
+//   winner_table + pass-2 lost rule :410-430, :641-646
+//   derep_if_reassign_threshold     :353-375 and abundances :319-326 (host side of syl_profile)
+//
+// Formulation.  The reference probes the sample's hash map with every k-mer of every genome
+// (|DB| probes per sample).  |sample| (~10^6) << |DB| (~10^8..10^9), so the join is turned
+// around: all database k-mers (genome_kmers and tracked) are sorted ONCE into a global index
+// (key -> genome); each sample key then looks itself up through a bucket directory
+// (keys are uniform hashes, so bucket = mulhi(key, M) is a perfect interpolation) and walks
+// the equal range.  Work per sample = |sample| short probes + #hits, independent of how many
+// genomes the database holds, and the database is never streamed.  The per-genome statistics
+// are functions of the multiset of hit counts, computed by one warp per genome (exact radix
+// select for the median, no histogram range limit).  In pass 2 the winner of a k-mer is the
+// best pass-1 ANI inside that k-mer's equal range — a purely local decision, so no global
+// k-mer -> winner map is ever materialised.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+struct syl_db {
+    int device = 0;
+    uint64_t n_genomes = 0;
+    uint32_t genome_base = 0;
+    uint64_t N = 0;             // index entries (genome_kmers + tracked)
+    uint64_t *keys = nullptr;   // sorted ascending
+    uint32_t *gid = nullptr;    // (genome << 1) | is_tracked
+    uint32_t *bstart = nullptr; // NB + 1 bucket starts
+    uint64_t NB = 0, M = 0, maxkey = 0;
+    uint32_t *glen = nullptr;   // |genome_kmers| per genome (device)
+    std::vector<uint64_t> h_gn_size;
+    int has_tracked = 0;
+    int k = 31;
+    uint64_t c = 200;
+};
+
+namespace syl {
+
+static inline unsigned nblk(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// src/contain.rs:664-675 with src/constants.rs:3: largest cov with PoissonCDF(cov; m) < 0.9999999999
+// for integer medians m = 1..29 (statrs 0.16.1 cdf = Q(cov+1, m)); index 0 unused.
+__constant__ uint32_t c_pois_cut[30] = {0,  11, 15, 18, 21, 24, 26, 28, 31, 33, 35, 37, 39, 41, 43,
+                                        45, 46, 48, 50, 52, 53, 55, 57, 58, 60, 62, 63, 65, 67, 68};
+
+struct StatParams {
+    int k;
+    int no_ci, no_adj, mean_coverage;
+    double min_number_kmers, min_count_correct, min_ani;
+};
+
+// ---- index build ----------------------------------------------------------------------------
+
+__global__ void k_db_entries(const uint64_t *__restrict__ kmers, const uint64_t *__restrict__ kmer_off,
+                             const uint64_t *__restrict__ tracked, const uint64_t *__restrict__ tracked_off,
+                             uint64_t n_genomes, uint64_t nk, uint64_t nt, uint64_t *__restrict__ keys,
+                             uint32_t *__restrict__ gid) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nk + nt) return;
+    const bool is_tr = i >= nk;
+    const uint64_t j = is_tr ? i - nk : i;
+    const uint64_t *off = is_tr ? tracked_off : kmer_off;
+    uint64_t lo = 0, hi = n_genomes + 1;  // upper_bound(off, j) - 1
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (off[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    keys[i] = is_tr ? tracked[j] : kmers[j];
+    gid[i] = (uint32_t)(((lo - 1) << 1) | (is_tr ? 1u : 0u));
+}
+
+__global__ void k_glen(const uint64_t *__restrict__ kmer_off, uint64_t n_genomes, uint32_t *__restrict__ glen) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_genomes) glen[g] = (uint32_t)(kmer_off[g + 1] - kmer_off[g]);
+}
+
+__device__ __forceinline__ uint64_t bucket_of(uint64_t key, uint64_t M, uint64_t NB) {
+    uint64_t b = __umul64hi(key, M);
+    return b < NB ? b : NB - 1;
+}
+
+__global__ void k_bucket_starts(const uint64_t *__restrict__ keys, uint64_t N, uint64_t M, uint64_t NB,
+                                uint32_t *__restrict__ bstart) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > N) return;
+    const uint64_t b_prev = i == 0 ? 0 : bucket_of(keys[i - 1], M, NB) + 1;  // first bucket not yet started
+    const uint64_t b_end = i == N ? NB + 1 : bucket_of(keys[i], M, NB) + 1;
+    for (uint64_t b = b_prev; b < b_end; b++) bstart[b] = (uint32_t)i;
+}
+
+// ---- the join -------------------------------------------------------------------------------
+// PASS2 == false: count / fill hits of genome_kmers entries (pass 1).
+// PASS2 == true : only entries of pass-1 survivors take part; the winner of a k-mer is the
+//                 survivor with the best pass-1 ANI in the equal range (lowest genome on ties);
+//                 a genome_kmers hit whose genome is not the winner is "lost" (:641-646).
+// FILL == false : per-genome hit counters only;  FILL == true: scatter the counts into CSR.
+template <bool PASS2, bool FILL>
+__global__ void k_join(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ scount, uint64_t ns,
+                       const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gid,
+                       const uint32_t *__restrict__ bstart, uint64_t M, uint64_t NB, uint64_t maxkey,
+                       const uint8_t *__restrict__ survivor, const double *__restrict__ ani1,
+                       uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, uint32_t *__restrict__ cursor,
+                       uint32_t *__restrict__ covs, uint32_t *__restrict__ lost) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const uint64_t key = skey[i];
+    const uint32_t c = scount[i];
+    if (key > maxkey || c == 0) return;  // count 0: src/contain.rs:634-636
+    const uint64_t b = bucket_of(key, M, NB);
+    uint32_t lo = bstart[b];
+    const uint32_t hi = bstart[b + 1];
+    while (lo < hi && keys[lo] < key) lo++;
+    if (lo >= hi || keys[lo] != key) return;
+    // the equal range may run past the bucket end only if keys are equal, which maps to the same bucket
+    uint32_t e = lo;
+    uint32_t winner = 0xFFFFFFFFu;
+    if (PASS2) {
+        double best = -1.0;
+        for (uint32_t j = lo; j < hi && keys[j] == key; j++) {
+            const uint32_t g = gid[j] >> 1;
+            if (!survivor[g]) continue;
+            const double a = ani1[g];
+            if (a > best || (a == best && g < winner)) { best = a; winner = g; }
+        }
+    }
+    for (; e < hi && keys[e] == key; e++) {
+        const uint32_t gv = gid[e];
+        if (gv & 1u) continue;  // tracked k-mers only take part in the winner decision
+        const uint32_t g = gv >> 1;
+        if (PASS2) {
+            if (!survivor[g]) continue;
+            if (g != winner) {
+                if (!FILL) atomicAdd(&lost[g], 1u);
+                continue;
+            }
+        }
+        if (!FILL) {
+            atomicAdd(&cnt[g], 1u);
+        } else {
+            const uint32_t p = atomicAdd(&cursor[g], 1u);
+            covs[off[g] + p] = c;
+        }
+    }
+}
+
+// ---- per-genome statistics: one warp per genome ---------------------------------------------
+
+struct RatioOut { bool ok; double lambda; };
+
+// src/inference.rs:207-242 on a histogram H[1..16] of the non-zero values (H[v] = #values == v),
+// nz = number of non-zero values in full_covs.
+__device__ __forceinline__ RatioOut ratio_lambda_hist(const uint32_t *H, uint32_t nz, double min_count_correct) {
+    RatioOut r = {false, 0.0};
+    uint32_t distinct = 0, mode = 0, best = 0;
+    for (uint32_t v = 1; v <= 16; v++) {
+        if (H[v]) distinct++;
+        if (H[v] && H[v] >= best) { best = H[v]; mode = v; }  // ties -> larger value (:226-230)
+    }
+    if (distinct == 1) return r;                  // :221-223
+    if (nz < 25u) return r;                       // SAMPLE_SIZE_CUTOFF
+    if (mode == 0 || mode >= 16 || H[mode + 1] == 0) return r;
+    const double cp1 = (double)H[mode + 1], cm = (double)H[mode];
+    if (cp1 < min_count_correct || cm < min_count_correct) return r;
+    r.ok = true;
+    r.lambda = cp1 / cm * (double)(mode + 1);
+    return r;
+}
+
+// src/contain.rs:817-847
+__device__ __forceinline__ bool ani_from_lambda_dev(double lambda, double k, uint64_t nz, uint64_t nfull, double *out) {
+    const double adj = (double)nz / (1. - exp(-lambda)) / (double)nfull;
+    const double ani = pow(adj, 1. / k);
+    if (ani < 0. || isnan(ani)) return false;
+    *out = ani;
+    return true;
+}
+
+constexpr int STAT_WARPS = 4;
+
+__global__ void __launch_bounds__(STAT_WARPS * 32)
+k_stats(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, const uint32_t *__restrict__ covs,
+        const uint32_t *__restrict__ glen, const uint32_t *__restrict__ lost, uint64_t n_genomes,
+        uint32_t genome_base, uint32_t sample_idx, StatParams P, int pass2, syl_ani_row *__restrict__ rows,
+        uint8_t *__restrict__ valid, uint8_t *__restrict__ need_boot, uint32_t *__restrict__ hist_out) {
+    __shared__ uint32_t s_hist[STAT_WARPS][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t g = (uint64_t)blockIdx.x * STAT_WARPS + w;
+    if (g >= n_genomes) return;
+    uint32_t *hist = s_hist[w];
+    if (lane == 0) { valid[g] = 0; need_boot[g] = 0; }
+    const uint32_t n = cnt[g];
+    const uint32_t gl = glen[g];
+    if (n == 0) return;                                   // covs.is_empty() :654
+    if ((double)gl < P.min_number_kmers) return;          // :627
+    const uint32_t *cv = covs + off[g];
+
+    // exact median = element of rank n/2 (0-based) by MSB-first radix select
+    uint32_t prefix = 0, kth = n / 2;
+    for (int pass = 3; pass >= 0; pass--) {
+        for (int b = lane; b < 256; b += 32) hist[b] = 0;
+        __syncwarp();
+        const uint32_t hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t v = cv[i];
+            if ((v & hi_mask) == prefix) atomicAdd(&hist[(v >> (8 * pass)) & 255u], 1u);
+        }
+        __syncwarp();
+        // lane l owns bins [8l, 8l+8)
+        uint32_t local[8], tot = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { local[q] = hist[8 * lane + q]; tot += local[q]; }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t excl = incl - tot;
+        const bool mine = kth >= excl && kth < incl;
+        uint32_t digit = 0, newk = 0;
+        if (mine) {
+            uint32_t acc = excl;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (kth >= acc && kth < acc + local[q]) { digit = 8 * lane + q; newk = kth - acc; }
+                acc += local[q];
+            }
+        }
+        const uint32_t src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+        digit = __shfl_sync(0xffffffffu, digit, src);
+        kth = __shfl_sync(0xffffffffu, newk, src);
+        prefix |= digit << (8 * pass);
+        __syncwarp();
+    }
+    const uint32_t median = prefix;
+    const uint32_t max_cov = median < 30u ? c_pois_cut[median] : 0xFFFFFFFFu;  // f64::MAX
+
+    // sums over full_covs = zeros ++ {cov <= max_cov}; small histogram for ratio_lambda
+    for (int b = lane; b < 32; b += 32) hist[b] = 0;
+    __syncwarp();
+    uint32_t sum = 0, nz = 0;  // u32 sum wraps like iter().sum::<u32>() in a release build
+    const bool want_hist = median <= 2u;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t v = cv[i];
+        if (v <= max_cov) {
+            sum += v;
+            nz++;
+            if (want_hist && v <= 16u) atomicAdd(&hist[v], 1u);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        nz += __shfl_xor_sync(0xffffffffu, nz, d);
+    }
+    __syncwarp();
+    if (lane != 0) return;
+
+    const double k = (double)P.k;
+    const uint64_t nfull = (uint64_t)(gl - n) + nz;
+    const double naive_ani = pow((double)n / (double)gl, 1. / k);
+    const double geq1_mean = (double)sum / (double)n;  // :690 divides by covs.len()
+    uint32_t status;
+    double lam = 0.;
+    if ((double)median > 2.) {
+        status = SYL_LAMBDA_HIGH;
+    } else {
+        RatioOut r = ratio_lambda_hist(hist, nz, P.min_count_correct);
+        status = r.ok ? SYL_LAMBDA_VALUE : SYL_LAMBDA_LOW;
+        lam = r.lambda;
+    }
+    double final_cov;
+    if (status == SYL_LAMBDA_VALUE) final_cov = lam;
+    else if ((double)median < 15.) final_cov = geq1_mean;
+    else final_cov = P.mean_coverage ? geq1_mean : (double)median;
+    double est = 0.;
+    const bool has_lambda = status == SYL_LAMBDA_VALUE;
+    const bool has_est = has_lambda && ani_from_lambda_dev(final_cov, k, nz, nfull, &est);
+    const double final_ani = (!has_lambda || !has_est || P.no_adj) ? naive_ani : est;
+    if (final_ani < P.min_ani) return;  // :746-764
+
+    syl_ani_row r;
+    r.sample = sample_idx;
+    r.genome = genome_base + (uint32_t)g;
+    r.lambda_status = status;
+    r.ci_valid = 0;
+    r.contain = n;
+    r.glen = gl;
+    r.kmers_lost = pass2 ? (int64_t)lost[g] : -1;
+    r.naive_ani = naive_ani;
+    r.final_est_ani = final_ani;
+    r.final_est_cov = final_cov;
+    r.mean_cov = geq1_mean;
+    r.median_cov = (double)median;
+    r.lambda = has_lambda ? lam : 0.;
+    r.ci[0] = r.ci[1] = r.ci[2] = r.ci[3] = 0.;
+    r.rel_abund = 0.;
+    r.seq_abund = 0.;
+    r.reserved = 0.;
+    rows[g] = r;
+    valid[g] = 1;
+    if (!P.no_ci && has_lambda) {
+        need_boot[g] = 1;
+        for (int v = 0; v < 17; v++) hist_out[g * 17 + v] = v == 0 ? (uint32_t)(gl - n) : hist[v];
+    }
+}
+
+// ---- bootstrap (src/contain.rs:849-898) -------------------------------------------------------
+// fastrand 2.1.1 WyRand: state after d draws = seed + d*C0, so draw d is random access.
+__device__ __forceinline__ uint64_t wyrand_at(uint64_t seed, uint64_t d) {
+    const uint64_t s = seed + d * 0x2d358dccaa6c78a5ull;
+    const uint64_t t = s ^ 0x8bb84b93962eacc9ull;
+    return (s * t) ^ __umul64hi(s, t);
+}
+
+constexpr int BOOT_ITERS = 100;
+constexpr int BOOT_THREADS = 256;
+
+// grid (BOOT_ITERS, n_boot): one CTA resamples |full| values for one iteration of one row.
+// H layout per genome: [0] = number of zeros, [v] = #values == v (v = 1..16; all values of a
+// bootstrapped row are <= 15 because its median is <= 2).
+__global__ void __launch_bounds__(BOOT_THREADS)
+k_boot_iter(const uint32_t *__restrict__ boot_rows, const uint32_t *__restrict__ hist_in, StatParams P,
+            double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
+            uint32_t *__restrict__ reject_flag) {
+    __shared__ uint32_t Hb[17];
+    __shared__ uint64_t cum[17];
+    const uint32_t row = blockIdx.y, it = blockIdx.x;
+    const uint32_t g = boot_rows[row];
+    const uint32_t *H = hist_in + (uint64_t)g * 17;
+    if (threadIdx.x < 17) Hb[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        uint64_t acc = 0;
+        for (int v = 0; v < 17; v++) { acc += H[v]; cum[v] = acc; }  // cum[v] = #values <= v
+    }
+    __syncthreads();
+    const uint64_t n = cum[16];
+    uint32_t local[17];
+#pragma unroll
+    for (int v = 0; v < 17; v++) local[v] = 0;
+    const uint64_t t = (0ull - n) % n;  // Lemire rejection threshold (fastrand gen_mod_u64)
+    for (uint64_t j = threadIdx.x; j < n; j += BOOT_THREADS) {
+        const uint64_t x = wyrand_at(7ull, (uint64_t)it * n + j + 1);
+        const uint64_t hi = __umul64hi(x, n), lo = x * n;
+        if (lo < n && lo < t) atomicExch(reject_flag + row, 1u);  // probability ~ n / 2^64 per draw
+        uint32_t v = 0;
+#pragma unroll
+        for (int q = 0; q < 16; q++) v += (hi >= cum[q]) ? 1u : 0u;  // value of full_covs[hi]
+#pragma unroll
+        for (int q = 0; q < 17; q++) local[q] += (v == (uint32_t)q) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int v = 0; v < 17; v++) {
+        uint32_t x = local[v];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&Hb[v], x);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    uint32_t nz = 0;
+    for (int v = 1; v <= 16; v++) nz += Hb[v];
+    RatioOut r = ratio_lambda_hist(Hb, nz, P.min_count_correct);
+    double ani = 0.;
+    bool ok = r.ok && ani_from_lambda_dev(r.lambda, (double)P.k, nz, n, &ani);
+    ok = ok && !isnan(ani) && !isnan(r.lambda);
+    const uint64_t o = (uint64_t)row * BOOT_ITERS + it;
+    res_ani[o] = ani;
+    res_lambda[o] = r.lambda;
+    res_ok[o] = ok ? 1 : 0;
+}
+
+// Exact sequential replay for a row whose counter-based draws hit Lemire's rejection branch
+// (the redraw shifts the RNG stream). One thread per flagged row; practically never runs.
+__global__ void k_boot_seq(const uint32_t *__restrict__ boot_rows, const uint32_t *__restrict__ hist_in, uint32_t n_boot,
+                           StatParams P, const uint32_t *__restrict__ reject_flag, double *__restrict__ res_ani,
+                           double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_boot || !reject_flag[row]) return;
+    const uint32_t *H = hist_in + (uint64_t)boot_rows[row] * 17;
+    uint64_t cum[17], acc = 0;
+    for (int v = 0; v < 17; v++) { acc += H[v]; cum[v] = acc; }
+    const uint64_t n = acc;
+    uint64_t state = 7ull;
+    for (int it = 0; it < BOOT_ITERS; it++) {
+        uint32_t Hb[17];
+        for (int v = 0; v < 17; v++) Hb[v] = 0;
+        for (uint64_t j = 0; j < n; j++) {
+            uint64_t hi, lo;
+            for (;;) {
+                state += 0x2d358dccaa6c78a5ull;
+                const uint64_t tt = state ^ 0x8bb84b93962eacc9ull;
+                const uint64_t x = (state * tt) ^ __umul64hi(state, tt);
+                hi = __umul64hi(x, n);
+                lo = x * n;
+                if (lo < n) {
+                    const uint64_t t = (0ull - n) % n;
+                    if (lo < t) continue;
+                }
+                break;
+            }
+            uint32_t v = 0;
+            for (int q = 0; q < 16; q++) v += (hi >= cum[q]) ? 1u : 0u;
+            Hb[v]++;
+        }
+        uint32_t nz = 0;
+        for (int v = 1; v <= 16; v++) nz += Hb[v];
+        RatioOut r = ratio_lambda_hist(Hb, nz, P.min_count_correct);
+        double ani = 0.;
+        bool ok = r.ok && ani_from_lambda_dev(r.lambda, (double)P.k, nz, n, &ani);
+        ok = ok && !isnan(ani) && !isnan(r.lambda);
+        const uint64_t o = (uint64_t)row * BOOT_ITERS + it;
+        res_ani[o] = ani;
+        res_lambda[o] = r.lambda;
+        res_ok[o] = ok ? 1 : 0;
+    }
+}
+
+// percentile pick: sort the successful iterations, take suc*5/100-1 and suc*95/100-1 (:885-896)
+__global__ void k_boot_final(const uint32_t *__restrict__ boot_rows, uint32_t n_boot, const double *__restrict__ res_ani,
+                             const double *__restrict__ res_lambda, const uint8_t *__restrict__ res_ok,
+                             syl_ani_row *__restrict__ rows) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_boot) return;
+    double a[BOOT_ITERS], l[BOOT_ITERS];
+    int suc = 0;
+    for (int it = 0; it < BOOT_ITERS; it++) {
+        const uint64_t o = (uint64_t)row * BOOT_ITERS + it;
+        if (!res_ok[o]) continue;
+        // insertion sort, ascending, each list on its own
+        double x = res_ani[o], y = res_lambda[o];
+        int p = suc;
+        while (p > 0 && a[p - 1] > x) { a[p] = a[p - 1]; p--; }
+        a[p] = x;
+        p = suc;
+        while (p > 0 && l[p - 1] > y) { l[p] = l[p - 1]; p--; }
+        l[p] = y;
+        suc++;
+    }
+    syl_ani_row &r = rows[boot_rows[row]];
+    if (suc < 50) { r.ci_valid = 0; return; }
+    r.ci[0] = a[suc * 5 / 100 - 1];
+    r.ci[1] = a[suc * 95 / 100 - 1];
+    r.ci[2] = l[suc * 5 / 100 - 1];
+    r.ci[3] = l[suc * 95 / 100 - 1];
+    r.ci_valid = 1;
+}
+
+__global__ void k_gather_rows(const syl_ani_row *__restrict__ rows, const uint32_t *__restrict__ sel, uint32_t n,
+                              syl_ani_row *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rows[sel[i]];
+}
+
+__global__ void k_mark_survivors(const syl_ani_row *__restrict__ rows, const uint8_t *__restrict__ valid, uint64_t n,
+                                 uint8_t *__restrict__ survivor, double *__restrict__ ani1) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    survivor[g] = valid[g];
+    ani1[g] = valid[g] ? rows[g].final_est_ani : 0.;
+}
+
+// Everything the containment passes need per context call (scratch sized by the db)
+struct ContainScratch {
+    DevBuf<uint32_t> cnt, cursor, lost, sel, boot_sel, hist, covs, reject;
+    DevBuf<uint64_t> off;
+    DevBuf<uint8_t> valid, need_boot, survivor, tmp, res_ok;
+    DevBuf<double> ani1, res_ani, res_lambda;
+    DevBuf<syl_ani_row> rows, out_rows;
+    size_t tmp_bytes = 0;
+};
+
+static StatParams make_params(const syl_contain_params *p) {
+    StatParams P;
+    P.k = p->k;
+    P.no_ci = p->no_ci;
+    P.no_adj = p->no_adj;
+    P.mean_coverage = p->mean_coverage;
+    P.min_number_kmers = p->min_number_kmers;
+    P.min_count_correct = p->min_count_correct;
+    P.min_ani = p->minimum_ani >= 0. ? p->minimum_ani / 100. : (p->pseudotax ? 0.95 : 0.90);  // :746-748
+    return P;
+}
+
+// One get_stats pass of one sample over the whole db.  pass2: survivor/ani1 must be filled.
+// Appends the valid rows (genome order) to `rows_out`.
+static int contain_pass(syl_ctx *ctx, const syl_db *db, const syl_sample *s, uint32_t sample_idx, const StatParams &P,
+                        bool pass2, ContainScratch &S, std::vector<syl_ani_row> &rows_out, bool keep_device_rows) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t G = db->n_genomes;
+    (void)keep_device_rows;
+    SYL_CUDA(cudaMemsetAsync(S.cnt.p, 0, G * 4, st));
+    SYL_CUDA(cudaMemsetAsync(S.cursor.p, 0, G * 4, st));
+    if (pass2) SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, G * 4, st));
+    const unsigned jb = nblk(s->n, 128);
+    if (s->n && db->N) {
+        if (!pass2)
+            k_join<false, false><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
+                                                     db->maxkey, nullptr, nullptr, S.cnt.p, nullptr, nullptr, nullptr, nullptr);
+        else
+            k_join<true, false><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
+                                                    db->maxkey, S.survivor.p, S.ani1.p, S.cnt.p, nullptr, nullptr, nullptr,
+                                                    S.lost.p);
+        ctx->launches++;
+    }
+    // CSR offsets of the per-genome hit lists
+    size_t tb = S.tmp_bytes;
+    SYL_CUDA(cub::DeviceScan::ExclusiveSum(S.tmp.p, tb, S.cnt.p, S.off.p, G, st));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 10, S.off.p + (G - 1), 8, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 11, S.cnt.p + (G - 1), 4, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    const uint64_t H = ctx->h_counters[10] + (uint32_t)ctx->h_counters[11];
+    if (H > S.covs.n) SYL_TRY(S.covs.alloc(H + H / 2 + 1024, st));
+    if (H) {
+        if (!pass2)
+            k_join<false, true><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
+                                                    db->maxkey, nullptr, nullptr, nullptr, S.off.p, S.cursor.p, S.covs.p,
+                                                    nullptr);
+        else
+            k_join<true, true><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
+                                                   db->maxkey, S.survivor.p, S.ani1.p, nullptr, S.off.p, S.cursor.p,
+                                                   S.covs.p, nullptr);
+        ctx->launches++;
+    }
+    k_stats<<<nblk(G, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.cnt.p, S.off.p, S.covs.p, db->glen, S.lost.p, G,
+                                                             db->genome_base, sample_idx, P, pass2 ? 1 : 0, S.rows.p,
+                                                             S.valid.p, S.need_boot.p, S.hist.p);
+    ctx->launches++;
+    SYL_CUDA(cudaGetLastError());
+    // select valid rows and rows that need a bootstrap (both in genome order)
+    uint64_t *d_nsel = ctx->d_counters + 12;
+    tb = S.tmp_bytes;
+    SYL_CUDA(cub::DeviceSelect::Flagged(S.tmp.p, tb, cub::CountingInputIterator<uint32_t>(0), S.valid.p, S.sel.p,
+                                        reinterpret_cast<uint32_t *>(d_nsel), (int)G, st));
+    tb = S.tmp_bytes;
+    SYL_CUDA(cub::DeviceSelect::Flagged(S.tmp.p, tb, cub::CountingInputIterator<uint32_t>(0), S.need_boot.p, S.boot_sel.p,
+                                        reinterpret_cast<uint32_t *>(d_nsel + 1), (int)G, st));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 12, d_nsel, 16, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_valid = (uint32_t)ctx->h_counters[12], n_boot = (uint32_t)ctx->h_counters[13];
+    if (n_boot) {
+        const uint64_t nb = (uint64_t)n_boot * BOOT_ITERS;
+        if (nb > S.res_ani.n) {
+            SYL_TRY(S.res_ani.alloc(nb, st));
+            SYL_TRY(S.res_lambda.alloc(nb, st));
+            SYL_TRY(S.res_ok.alloc(nb, st));
+            SYL_TRY(S.reject.alloc(n_boot, st));
+        }
+        SYL_CUDA(cudaMemsetAsync(S.reject.p, 0, (size_t)n_boot * 4, st));
+        for (uint32_t r0 = 0; r0 < n_boot; r0 += 32768) {  // gridDim.y limit
+            const uint32_t nr = std::min<uint32_t>(32768, n_boot - r0);
+            k_boot_iter<<<dim3(BOOT_ITERS, nr), BOOT_THREADS, 0, st>>>(S.boot_sel.p + r0, S.hist.p, P,
+                                                                       S.res_ani.p + (uint64_t)r0 * BOOT_ITERS,
+                                                                       S.res_lambda.p + (uint64_t)r0 * BOOT_ITERS,
+                                                                       S.res_ok.p + (uint64_t)r0 * BOOT_ITERS,
+                                                                       S.reject.p + r0);
+            ctx->launches++;
+        }
+        k_boot_seq<<<nblk(n_boot, 32), 32, 0, st>>>(S.boot_sel.p, S.hist.p, n_boot, P, S.reject.p, S.res_ani.p,
+                                                    S.res_lambda.p, S.res_ok.p);
+        k_boot_final<<<nblk(n_boot, 32), 32, 0, st>>>(S.boot_sel.p, n_boot, S.res_ani.p, S.res_lambda.p, S.res_ok.p,
+                                                      S.rows.p);
+        ctx->launches += 2;
+        SYL_CUDA(cudaGetLastError());
+    }
+    if (n_valid) {
+        if (n_valid > S.out_rows.n) SYL_TRY(S.out_rows.alloc(n_valid + 1024, st));
+        k_gather_rows<<<nblk(n_valid, 128), 128, 0, st>>>(S.rows.p, S.sel.p, n_valid, S.out_rows.p);
+        ctx->launches++;
+        const size_t base = rows_out.size();
+        rows_out.resize(base + n_valid);
+        SYL_CUDA(cudaMemcpyAsync(rows_out.data() + base, S.out_rows.p, (size_t)n_valid * sizeof(syl_ani_row),
+                                 cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaStreamSynchronize(st));
+    }
+    return SYL_OK;
+}
+
+static int scratch_init(syl_ctx *ctx, const syl_db *db, ContainScratch &S) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t G = std::max<uint64_t>(db->n_genomes, 1);
+    SYL_TRY(S.cnt.alloc(G, st)); SYL_TRY(S.cursor.alloc(G, st)); SYL_TRY(S.lost.alloc(G, st));
+    SYL_TRY(S.sel.alloc(G, st)); SYL_TRY(S.boot_sel.alloc(G, st)); SYL_TRY(S.hist.alloc(G * 17, st));
+    SYL_TRY(S.off.alloc(G + 1, st));
+    SYL_TRY(S.valid.alloc(G, st)); SYL_TRY(S.need_boot.alloc(G, st)); SYL_TRY(S.survivor.alloc(G, st));
+    SYL_TRY(S.ani1.alloc(G, st));
+    SYL_TRY(S.rows.alloc(G, st));
+    SYL_TRY(S.covs.alloc(1 << 16, st));
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t1, S.cnt.p, S.off.p, G, st);
+    cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<uint32_t>(0), S.valid.p, S.sel.p,
+                               reinterpret_cast<uint32_t *>(ctx->d_counters), (int)G, st);
+    S.tmp_bytes = std::max(t1, t2);
+    SYL_TRY(S.tmp.alloc(S.tmp_bytes, st));
+    SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, G * 4, st));
+    return SYL_OK;
+}
+
+static int check_pair_args(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+                           const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows) {
+    if (!ctx || !db || !p || !n_rows || (n_samples && !samples) || (cap && !rows)) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    for (uint32_t i = 0; i < n_samples; i++) {
+        if (!samples[i]) { set_error("NULL sample"); return SYL_ERR_ARG; }
+        if (samples[i]->k != db->k) {  // src/contain.rs:608-615 (log::error + exit(1))
+            set_error("k parameter for reads != k parameter for genome");
+            return SYL_ERR_ARG;
+        }
+        if (db->c < samples[i]->c) {   // src/contain.rs:616-623
+            set_error("c parameter for reads > c parameter for genome");
+            return SYL_ERR_ARG;
+        }
+    }
+    if (p->k != db->k) { set_error("params.k != db k"); return SYL_ERR_ARG; }
+    return SYL_OK;
+}
+
+}  // namespace syl
+
+using namespace syl;
+
+extern "C" {
+
+int syl_db_build(syl_ctx *ctx, const syl_genomes *g, uint32_t genome_base, syl_db **out) {
+    if (!ctx || !g || !out) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t nk = g->total_kmers, nt = g->has_tracked ? g->total_tracked : 0, N = nk + nt;
+    if (N >= 0xFFFFFFFFull) { set_error("db shard holds more than 2^32-2 k-mers; shard the database"); return SYL_ERR_ARG; }
+    if (g->n >= 0x7FFFFFFFull) { set_error("too many genomes in one db shard"); return SYL_ERR_ARG; }
+    syl_db *db = new (std::nothrow) syl_db();
+    if (!db) return SYL_ERR_OOM;
+    db->device = ctx->device;
+    db->n_genomes = g->n;
+    db->genome_base = genome_base;
+    db->N = N;
+    db->has_tracked = g->has_tracked;
+    db->k = g->k;
+    db->c = g->c;
+    auto fail = [&](int rc) { syl_db_free(db); return rc; };
+#define DB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(_e)); return fail(SYL_ERR_CUDA); } } while (0)
+    DB_CUDA(cudaMalloc((void **)&db->keys, std::max<uint64_t>(N, 1) * 8));
+    DB_CUDA(cudaMalloc((void **)&db->gid, std::max<uint64_t>(N, 1) * 4));
+    DB_CUDA(cudaMalloc((void **)&db->glen, std::max<uint64_t>(g->n, 1) * 4));
+    db->h_gn_size.resize(g->n);
+    if (g->n) {
+        DB_CUDA(cudaMemcpyAsync(db->h_gn_size.data(), g->gn_size, g->n * 8, cudaMemcpyDeviceToHost, st));
+        k_glen<<<nblk(g->n, 256), 256, 0, st>>>(g->kmer_off, g->n, db->glen);
+        ctx->launches++;
+    }
+    uint64_t NB = 1024;
+    while (NB < N / 4) NB <<= 1;
+    db->NB = NB;
+    DB_CUDA(cudaMalloc((void **)&db->bstart, (NB + 2) * 4));
+    if (N) {
+        DevBuf<uint64_t> kin;
+        DevBuf<uint32_t> gin;
+        DevBuf<uint8_t> tmp;
+        int rc;
+        if ((rc = kin.alloc(N, st)) != SYL_OK || (rc = gin.alloc(N, st)) != SYL_OK) return fail(rc);
+        k_db_entries<<<nblk(N, 256), 256, 0, st>>>(g->kmers, g->kmer_off, g->tracked, g->tracked_off, g->n, nk, nt, kin.p, gin.p);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, kin.p, db->keys, gin.p, db->gid, N, 0, 64, st);
+        if ((rc = tmp.alloc(tb, st)) != SYL_OK) return fail(rc);
+        DB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kin.p, db->keys, gin.p, db->gid, N, 0, 64, st));
+        DB_CUDA(cudaMemcpyAsync(ctx->h_counters + 14, db->keys + (N - 1), 8, cudaMemcpyDeviceToHost, st));
+        DB_CUDA(cudaStreamSynchronize(st));
+        db->maxkey = ctx->h_counters[14];
+        unsigned __int128 m = ((unsigned __int128)NB << 64) / ((unsigned __int128)db->maxkey + 1);
+        db->M = m > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)m;
+        k_bucket_starts<<<nblk(N + 1, 256), 256, 0, st>>>(db->keys, N, db->M, NB, db->bstart);
+        ctx->launches += 3;
+        DB_CUDA(cudaGetLastError());
+    } else {
+        DB_CUDA(cudaMemsetAsync(db->bstart, 0, (NB + 2) * 4, st));
+        db->M = 0;
+        db->maxkey = 0;
+    }
+    DB_CUDA(cudaStreamSynchronize(st));
+#undef DB_CUDA
+    *out = db;
+    return SYL_OK;
+}
+
+uint64_t syl_db_num_genomes(const syl_db *db) { return db ? db->n_genomes : 0; }
+
+void syl_db_free(syl_db *db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    if (db->keys) cudaFree(db->keys);
+    if (db->gid) cudaFree(db->gid);
+    if (db->bstart) cudaFree(db->bstart);
+    if (db->glen) cudaFree(db->glen);
+    delete db;
+}
+
+void syl_contain_params_default(syl_contain_params *p, int k, int pseudotax) {
+    if (!p) return;
+    p->k = k;
+    p->pseudotax = pseudotax;
+    p->no_ci = 0;
+    p->no_adj = 0;
+    p->mean_coverage = 0;
+    p->reserved = 0;
+    p->min_number_kmers = 50.;
+    p->min_count_correct = 3.;
+    p->minimum_ani = -1.;
+    p->redundant_ani = 99.;
+}
+
+int syl_query(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+              const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows) {
+    SYL_TRY(check_pair_args(ctx, db, samples, n_samples, p, rows, cap, n_rows));
+    *n_rows = 0;
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
+    ContainScratch S;
+    SYL_TRY(scratch_init(ctx, db, S));
+    const StatParams P = make_params(p);
+    std::vector<syl_ani_row> out;
+    for (uint32_t i = 0; i < n_samples; i++) SYL_TRY(contain_pass(ctx, db, samples[i], i, P, false, S, out, false));
+    *n_rows = out.size();
+    if (out.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
+    std::copy(out.begin(), out.end(), rows);
+    return SYL_OK;
+}
+
+int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+                const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows) {
+    SYL_TRY(check_pair_args(ctx, db, samples, n_samples, p, rows, cap, n_rows));
+    *n_rows = 0;
+    if (!db->has_tracked) {  // src/contain.rs:231-234
+        set_error("Attempting profiling, but the database was sketched with the --disable-profiling option");
+        return SYL_ERR_ARG;
+    }
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
+    cudaStream_t st = ctx->stream;
+    ContainScratch S;
+    SYL_TRY(scratch_init(ctx, db, S));
+    syl_contain_params pp = *p;
+    pp.pseudotax = 1;
+    const StatParams P = make_params(&pp);
+    std::vector<syl_ani_row> all;
+    for (uint32_t i = 0; i < n_samples; i++) {
+        std::vector<syl_ani_row> r1, r2;
+        SYL_TRY(contain_pass(ctx, db, samples[i], i, P, false, S, r1, true));
+        if (r1.empty()) continue;
+        // pass-1 rows are still in S.rows / S.valid (indexed by genome): they define the winner table
+        k_mark_survivors<<<nblk(db->n_genomes, 256), 256, 0, st>>>(S.rows.p, S.valid.p, db->n_genomes, S.survivor.p, S.ani1.p);
+        ctx->launches++;
+        SYL_TRY(contain_pass(ctx, db, samples[i], i, P, true, S, r2, false));
+        // derep_if_reassign_threshold (src/contain.rs:353-375)
+        const double threshold = std::pow(pp.redundant_ani / 100., (double)pp.k);
+        std::vector<syl_ani_row> kept;
+        size_t j = 0;
+        for (const syl_ani_row &n2 : r2) {
+            while (j < r1.size() && r1[j].genome < n2.genome) j++;
+            const syl_ani_row &o = r1[j];
+            const double num_reassign = (double)(o.contain - n2.contain);
+            const double reass_thresh = threshold * (double)n2.glen;
+            if (num_reassign < reass_thresh) kept.push_back(n2);
+        }
+        // abundances (src/contain.rs:319-326), summed in genome order
+        double total_cov = 0., total_seq_cov = 0.;
+        for (const syl_ani_row &r : kept) {
+            total_cov += r.final_est_cov;
+            total_seq_cov += r.final_est_cov * (double)db->h_gn_size[r.genome - db->genome_base];
+        }
+        for (syl_ani_row &r : kept) {
+            r.rel_abund = r.final_est_cov / total_cov * 100.;
+            r.seq_abund = r.final_est_cov * (double)db->h_gn_size[r.genome - db->genome_base] / total_seq_cov * 100. * 1.;
+        }
+        std::stable_sort(kept.begin(), kept.end(),
+                         [](const syl_ani_row &a, const syl_ani_row &b) { return a.rel_abund > b.rel_abund; });
+        all.insert(all.end(), kept.begin(), kept.end());
+    }
+    *n_rows = all.size();
+    if (all.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
+    std::copy(all.begin(), all.end(), rows);
+    return SYL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// genome.cu — genome (database) sketches from seeding survivors.
+//
+// Replaces sketch_genome (src/sketch.rs:550-622) and sketch_genome_individual (:481-548) for a
+// batch of genomes:
+//   (contig, pos, hash) tuples of all contigs        extract_markers_positions  :582 / :508
+//   vec.sort()                                        :593 -> radix sort by (contig, pos)
+//   k-mers seen >= 2x in the genome are dropped       :594-600,605 -> stable radix sort by hash:
+//        equal hashes of one genome end up adjacent (genomes own contiguous contig ranges)
+//   greedy min-spacing scan, per contig               :602-614 -> one thread per contig; the
+//        reference's `last_contig != contig` reset makes every contig's chain independent and
+//        its `last_pos == 0` sentinel can never collide with a real position (pos >= k-1)
+//   kept -> genome_kmers, thinned -> pseudotax_tracked_nonused_kmers, both in position order
+#include <cub/cub.cuh>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace syl {
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off,
+                uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
+                uint64_t cap, uint64_t *n_out);
+}
+
+namespace syl {
+
+static inline unsigned nblk(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+static inline int bits_for(uint64_t maxval) {
+    int b = 1;
+    while (b < 64 && (maxval >> b)) b++;
+    return b;
+}
+
+__global__ void k_split(const syl_survivor *__restrict__ sv, uint64_t n, uint64_t *__restrict__ key,
+                        uint64_t *__restrict__ hash) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const syl_survivor s = sv[i];
+    key[i] = ((uint64_t)s.rec << 32) | s.pos;
+    hash[i] = s.hash;
+}
+
+__global__ void k_iota32(uint32_t *idx, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (uint32_t)i;
+}
+
+__global__ void k_iota64(uint64_t *v, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+
+// contig -> genome (upper_bound over genome_off)
+__global__ void k_contig_genome(const uint64_t *__restrict__ genome_off, uint64_t n_genomes, uint64_t n_contigs,
+                                uint32_t *__restrict__ cg) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_contigs) return;
+    uint64_t lo = 0, hi = n_genomes + 1;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (genome_off[mid] > r) hi = mid; else lo = mid + 1;
+    }
+    cg[r] = (uint32_t)(lo - 1);
+}
+
+// hs/ix: survivors stably sorted by hash (ix = index into the position-sorted arrays).
+// A hash occurring >= 2x inside one genome marks all its occurrences (src/sketch.rs:594-600).
+__global__ void k_flag_dups(const uint64_t *__restrict__ hs, const uint32_t *__restrict__ ix, uint64_t n,
+                            const uint64_t *__restrict__ poskey, const uint32_t *__restrict__ cg,
+                            uint8_t *__restrict__ flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t h = hs[i];
+    const uint32_t me = ix[i];
+    const uint32_t g = cg[poskey[me] >> 32];
+    bool dup = false;
+    if (i > 0 && hs[i - 1] == h) dup |= cg[poskey[ix[i - 1]] >> 32] == g;
+    if (i + 1 < n && hs[i + 1] == h) dup |= cg[poskey[ix[i + 1]] >> 32] == g;
+    flag[me] = dup ? 0 : 3;  // 0 = duplicate (dropped); 3 = undecided, resolved by k_spacing
+}
+
+__device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t *a, uint64_t n, uint64_t v) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// greedy spacing chain of one contig (src/sketch.rs:602-614): 1 = kept, 2 = tracked (thinned out)
+__global__ void k_spacing(const uint64_t *__restrict__ poskey, uint64_t n, uint64_t n_contigs, uint64_t min_spacing,
+                          uint8_t *__restrict__ flag) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_contigs) return;
+    uint64_t i = lower_bound_u64(poskey, n, r << 32);
+    const uint64_t end = lower_bound_u64(poskey, n, (r + 1) << 32);
+    uint64_t last_pos = 0;
+    for (; i < end; i++) {
+        if (flag[i] == 0) continue;
+        const uint64_t pos = poskey[i] & 0xFFFFFFFFull;
+        if (last_pos == 0 || pos - last_pos > min_spacing) {
+            flag[i] = 1;
+            last_pos = pos;
+        } else {
+            flag[i] = 2;
+        }
+    }
+}
+
+struct FlagIs {
+    uint8_t want;
+    __host__ __device__ __forceinline__ FlagIs(uint8_t w) : want(w) {}
+    __host__ __device__ __forceinline__ bool operator()(const uint8_t &f) const { return f == want; }
+};
+
+// per-genome CSR offsets: number of flag==want survivors before the genome's first survivor
+__global__ void k_genome_offsets(const uint64_t *__restrict__ poskey, uint64_t n, const uint64_t *__restrict__ genome_off,
+                                 uint64_t n_genomes, const uint64_t *__restrict__ scan_kept,
+                                 const uint64_t *__restrict__ scan_tracked, uint64_t total_kept,
+                                 uint64_t total_tracked, const uint64_t *__restrict__ contig_off,
+                                 uint64_t *__restrict__ kmer_off, uint64_t *__restrict__ tracked_off,
+                                 uint64_t *__restrict__ gn_size) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_genomes) return;
+    if (g == n_genomes) {
+        kmer_off[g] = total_kept;
+        tracked_off[g] = total_tracked;
+        return;
+    }
+    const uint64_t first = lower_bound_u64(poskey, n, genome_off[g] << 32);
+    kmer_off[g] = first < n ? scan_kept[first] : total_kept;
+    tracked_off[g] = first < n ? scan_tracked[first] : total_tracked;
+    gn_size[g] = contig_off[genome_off[g + 1]] - contig_off[genome_off[g]];  // src/sketch.rs:581
+}
+
+__global__ void k_scatter_flagged(const uint64_t *__restrict__ hash, const uint8_t *__restrict__ flag, uint64_t n,
+                                  const uint64_t *__restrict__ scan_kept, const uint64_t *__restrict__ scan_tracked,
+                                  uint64_t *__restrict__ kmers, uint64_t *__restrict__ tracked) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t f = flag[i];
+    if (f == 1) kmers[scan_kept[i]] = hash[i];
+    else if (f == 2 && tracked) tracked[scan_tracked[i]] = hash[i];
+}
+
+__global__ void k_flag_to_u64(const uint8_t *__restrict__ flag, uint64_t n, uint8_t want, uint64_t *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = flag[i] == want ? 1ull : 0ull;
+}
+
+static int genomes_alloc(syl_genomes *g, uint64_t n_genomes, uint64_t nk, uint64_t nt) {
+    SYL_CUDA(cudaMalloc((void **)&g->kmers, std::max<uint64_t>(nk, 1) * 8));
+    SYL_CUDA(cudaMalloc((void **)&g->tracked, std::max<uint64_t>(nt, 1) * 8));
+    SYL_CUDA(cudaMalloc((void **)&g->kmer_off, (n_genomes + 1) * 8));
+    SYL_CUDA(cudaMalloc((void **)&g->tracked_off, (n_genomes + 1) * 8));
+    SYL_CUDA(cudaMalloc((void **)&g->gn_size, std::max<uint64_t>(n_genomes, 1) * 8));
+    g->n = n_genomes;
+    g->total_kmers = nk;
+    g->total_tracked = nt;
+    return SYL_OK;
+}
+
+int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_contig_off,
+                          uint64_t n_contigs, const uint64_t *d_genome_off, uint64_t n_genomes, int k, uint64_t c,
+                          uint64_t min_spacing, int pseudotax, int sem, syl_genomes *out) {
+    cudaStream_t st = ctx->stream;
+    // 1. survivors with positions
+    uint64_t scap = n_bases / c + n_bases / (4 * c) + 65536;
+    if (scap > n_bases) scap = n_bases + 16;
+    DevBuf<syl_survivor> sv;
+    uint64_t N = 0;
+    for (;;) {
+        SYL_TRY(sv.alloc(scap, st));
+        int rc = seed_device(ctx, d_bases, n_bases, d_contig_off, n_contigs, k, c, sem, /*with_pos=*/1, sv.p, scap, &N);
+        if (rc == SYL_ERR_CAPACITY) { scap = N + 16; continue; }
+        if (rc != SYL_OK) return rc;
+        break;
+    }
+    if (N >= 0xFFFFFFFFull) { set_error("more than 2^32-2 survivors in one genome batch; split the batch"); return SYL_ERR_ARG; }
+    DevBuf<uint64_t> key_a, key_b, hash_a, hash_b, scan_k, scan_t;
+    DevBuf<uint32_t> idx_a, idx_b, cg;
+    DevBuf<uint8_t> flag, tmp;
+    const uint64_t NA = std::max<uint64_t>(N, 1);
+    SYL_TRY(key_a.alloc(NA, st)); SYL_TRY(key_b.alloc(NA, st));
+    SYL_TRY(hash_a.alloc(NA, st)); SYL_TRY(hash_b.alloc(NA, st));
+    SYL_TRY(idx_a.alloc(NA, st)); SYL_TRY(idx_b.alloc(NA, st));
+    SYL_TRY(scan_k.alloc(NA, st)); SYL_TRY(scan_t.alloc(NA, st));
+    SYL_TRY(flag.alloc(NA, st));
+    SYL_TRY(cg.alloc(n_contigs, st));
+    k_contig_genome<<<nblk(n_contigs, 256), 256, 0, st>>>(d_genome_off, n_genomes, n_contigs, cg.p);
+    ctx->launches++;
+    uint64_t total_kept = 0, total_tracked = 0;
+    if (N) {
+        k_split<<<nblk(N, 256), 256, 0, st>>>(sv.p, N, key_a.p, hash_a.p);
+        // 2. position order: sort by (contig, pos)
+        const int pos_bits = 32 + bits_for(n_contigs);
+        const int hash_bits = bits_for(fmh_threshold(c));
+        size_t t1 = 0, t2 = 0, t3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t1, key_a.p, key_b.p, hash_a.p, hash_b.p, N, 0, pos_bits, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, t2, hash_b.p, hash_a.p, idx_a.p, idx_b.p, N, 0, hash_bits, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, t3, scan_k.p, scan_k.p, N, st);
+        size_t tb = std::max(t1, std::max(t2, t3));
+        SYL_TRY(tmp.alloc(tb, st));
+        SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key_a.p, key_b.p, hash_a.p, hash_b.p, N, 0, pos_bits, st));
+        // now: key_b = poskey sorted, hash_b = hashes in position order
+        // 3. duplicates inside a genome: stable sort of (hash, position index) by hash
+        k_iota32<<<nblk(N, 256), 256, 0, st>>>(idx_a.p, N);
+        tb = std::max(t1, std::max(t2, t3));
+        SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, hash_b.p, hash_a.p, idx_a.p, idx_b.p, N, 0, hash_bits, st));
+        k_flag_dups<<<nblk(N, 256), 256, 0, st>>>(hash_a.p, idx_b.p, N, key_b.p, cg.p, flag.p);
+        // 4. greedy spacing per contig
+        k_spacing<<<nblk(n_contigs, 64), 64, 0, st>>>(key_b.p, N, n_contigs, min_spacing, flag.p);
+        // 5. compaction
+        k_flag_to_u64<<<nblk(N, 256), 256, 0, st>>>(flag.p, N, 1, scan_k.p);
+        k_flag_to_u64<<<nblk(N, 256), 256, 0, st>>>(flag.p, N, 2, scan_t.p);
+        uint64_t *d_last = ctx->d_counters + 4;  // [4],[5]: last flags, [6],[7]: last scans
+        SYL_CUDA(cudaMemcpyAsync(d_last, scan_k.p + (N - 1), 8, cudaMemcpyDeviceToDevice, st));
+        SYL_CUDA(cudaMemcpyAsync(d_last + 1, scan_t.p + (N - 1), 8, cudaMemcpyDeviceToDevice, st));
+        tb = std::max(t1, std::max(t2, t3));
+        SYL_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, scan_k.p, scan_k.p, N, st));
+        tb = std::max(t1, std::max(t2, t3));
+        SYL_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, scan_t.p, scan_t.p, N, st));
+        SYL_CUDA(cudaMemcpyAsync(d_last + 2, scan_k.p + (N - 1), 8, cudaMemcpyDeviceToDevice, st));
+        SYL_CUDA(cudaMemcpyAsync(d_last + 3, scan_t.p + (N - 1), 8, cudaMemcpyDeviceToDevice, st));
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 4, d_last, 32, cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaStreamSynchronize(st));
+        total_kept = ctx->h_counters[4] + ctx->h_counters[6];
+        total_tracked = ctx->h_counters[5] + ctx->h_counters[7];
+        ctx->launches += 7 + 4;
+    }
+    out->has_tracked = pseudotax ? 1 : 0;
+    if (!pseudotax) total_tracked = 0;
+    SYL_TRY(genomes_alloc(out, n_genomes, total_kept, total_tracked));
+    if (N) {
+        k_scatter_flagged<<<nblk(N, 256), 256, 0, st>>>(hash_b.p, flag.p, N, scan_k.p, scan_t.p, out->kmers,
+                                                         pseudotax ? out->tracked : nullptr);
+        ctx->launches++;
+    }
+    k_genome_offsets<<<nblk(n_genomes + 1, 128), 128, 0, st>>>(key_b.p, N, d_genome_off, n_genomes, scan_k.p, scan_t.p,
+                                                               total_kept, pseudotax ? total_tracked : 0, d_contig_off,
+                                                               out->kmer_off, out->tracked_off, out->gn_size);
+    ctx->launches++;
+    SYL_CUDA(cudaGetLastError());
+    if (!pseudotax) SYL_CUDA(cudaMemsetAsync(out->tracked_off, 0, (n_genomes + 1) * 8, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    return SYL_OK;
+}
+
+}  // namespace syl
+
+using namespace syl;
+
+extern "C" {
+
+int syl_sketch_genomes(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
+                       const uint64_t *contig_off, uint64_t n_contigs, const uint64_t *genome_off,
+                       uint64_t n_genomes, int k, uint64_t c, uint64_t min_spacing, int pseudotax,
+                       int individual, int sem, syl_genomes **out) {
+    if (!ctx || !out || (!bases && n_bases) || !contig_off || (!individual && !genome_off)) {
+        set_error("NULL argument");
+        return SYL_ERR_ARG;
+    }
+    if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint8_t> hb;
+    DevBuf<uint64_t> hc, hg;
+    const uint8_t *d_bases = bases;
+    const uint64_t *d_coff = contig_off, *d_goff = genome_off;
+    if (individual) n_genomes = n_contigs;
+    if (mem == SYL_MEM_HOST) {
+        SYL_TRY(hb.alloc(n_bases + 64, st));
+        SYL_TRY(hc.alloc(n_contigs + 1, st));
+        if (n_bases) SYL_CUDA(cudaMemcpyAsync(hb.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+        SYL_CUDA(cudaMemcpyAsync(hc.p, contig_off, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
+        d_bases = hb.p;
+        d_coff = hc.p;
+        if (!individual) {
+            SYL_TRY(hg.alloc(n_genomes + 1, st));
+            SYL_CUDA(cudaMemcpyAsync(hg.p, genome_off, (n_genomes + 1) * 8, cudaMemcpyHostToDevice, st));
+            d_goff = hg.p;
+        }
+    } else if (mem != SYL_MEM_DEVICE) {
+        set_error("bad mem");
+        return SYL_ERR_ARG;
+    }
+    if (individual) {  // every record is its own genome (src/sketch.rs:481-548)
+        SYL_TRY(hg.alloc(n_contigs + 1, st));
+        k_iota64<<<nblk(n_contigs + 1, 256), 256, 0, st>>>(hg.p, n_contigs + 1);
+        ctx->launches++;
+        d_goff = hg.p;
+    }
+    syl_genomes *g = new (std::nothrow) syl_genomes();
+    if (!g) return SYL_ERR_OOM;
+    g->device = ctx->device;
+    g->k = k;
+    g->c = c;
+    int rc = sketch_genomes_device(ctx, d_bases, n_bases, d_coff, n_contigs, d_goff, n_genomes, k, c, min_spacing,
+                                   pseudotax, sem, g);
+    if (rc != SYL_OK) { syl_genomes_free(g); return rc; }
+    *out = g;
+    return SYL_OK;
+}
+
+int syl_genomes_upload(syl_ctx *ctx, int mem, const uint64_t *kmers, const uint64_t *kmer_off,
+                       const uint64_t *tracked, const uint64_t *tracked_off, const uint64_t *gn_size,
+                       uint64_t n_genomes, int k, uint64_t c, syl_genomes **out) {
+    if (!ctx || !out || !kmer_off) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    cudaMemcpyKind kind = mem == SYL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    uint64_t nk = 0, nt = 0;
+    if (mem == SYL_MEM_HOST) {
+        nk = kmer_off[n_genomes];
+        nt = tracked_off ? tracked_off[n_genomes] : 0;
+    } else {
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 8, kmer_off + n_genomes, 8, cudaMemcpyDeviceToHost, st));
+        if (tracked_off) SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 9, tracked_off + n_genomes, 8, cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaStreamSynchronize(st));
+        nk = ctx->h_counters[8];
+        nt = tracked_off ? ctx->h_counters[9] : 0;
+    }
+    syl_genomes *g = new (std::nothrow) syl_genomes();
+    if (!g) return SYL_ERR_OOM;
+    g->device = ctx->device; g->k = k; g->c = c;
+    g->has_tracked = (tracked && tracked_off) ? 1 : 0;
+    int rc = genomes_alloc(g, n_genomes, nk, nt);
+    if (rc != SYL_OK) { syl_genomes_free(g); return rc; }
+    if (nk) SYL_CUDA(cudaMemcpyAsync(g->kmers, kmers, nk * 8, kind, st));
+    SYL_CUDA(cudaMemcpyAsync(g->kmer_off, kmer_off, (n_genomes + 1) * 8, kind, st));
+    if (g->has_tracked) {
+        if (nt) SYL_CUDA(cudaMemcpyAsync(g->tracked, tracked, nt * 8, kind, st));
+        SYL_CUDA(cudaMemcpyAsync(g->tracked_off, tracked_off, (n_genomes + 1) * 8, kind, st));
+    } else {
+        SYL_CUDA(cudaMemsetAsync(g->tracked_off, 0, (n_genomes + 1) * 8, st));
+    }
+    if (gn_size && n_genomes) SYL_CUDA(cudaMemcpyAsync(g->gn_size, gn_size, n_genomes * 8, kind, st));
+    else if (n_genomes) SYL_CUDA(cudaMemsetAsync(g->gn_size, 0, n_genomes * 8, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    *out = g;
+    return SYL_OK;
+}
+
+uint64_t syl_genomes_count(const syl_genomes *g) { return g ? g->n : 0; }
+uint64_t syl_genomes_total_kmers(const syl_genomes *g) { return g ? g->total_kmers : 0; }
+uint64_t syl_genomes_total_tracked(const syl_genomes *g) { return g ? g->total_tracked : 0; }
+int syl_genomes_has_tracked(const syl_genomes *g) { return g ? g->has_tracked : 0; }
+
+int syl_genomes_download(syl_ctx *ctx, const syl_genomes *g, uint64_t *kmers, uint64_t *kmer_off,
+                         uint64_t *tracked, uint64_t *tracked_off, uint64_t *gn_size) {
+    if (!ctx || !g) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (kmers && g->total_kmers) SYL_CUDA(cudaMemcpyAsync(kmers, g->kmers, g->total_kmers * 8, cudaMemcpyDeviceToHost, st));
+    if (kmer_off) SYL_CUDA(cudaMemcpyAsync(kmer_off, g->kmer_off, (g->n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (tracked && g->total_tracked) SYL_CUDA(cudaMemcpyAsync(tracked, g->tracked, g->total_tracked * 8, cudaMemcpyDeviceToHost, st));
+    if (tracked_off) SYL_CUDA(cudaMemcpyAsync(tracked_off, g->tracked_off, (g->n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (gn_size && g->n) SYL_CUDA(cudaMemcpyAsync(gn_size, g->gn_size, g->n * 8, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    return SYL_OK;
+}
+
+void syl_genomes_free(syl_genomes *g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->kmers) cudaFree(g->kmers);
+    if (g->kmer_off) cudaFree(g->kmer_off);
+    if (g->tracked) cudaFree(g->tracked);
+    if (g->tracked_off) cudaFree(g->tracked_off);
+    if (g->gn_size) cudaFree(g->gn_size);
+    delete g;
+}
+
+}  // extern "C"

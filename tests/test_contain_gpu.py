@@ -1,0 +1,156 @@
+"""GPU parity: containment query/profile vs the CPU oracle.
+Integers bit-exact; floats within 1e-6 relative (north_star tolerance); bootstrap CI columns
+checked to the same tolerance (they depend on the restated fastrand stream, see oracle header)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import DATA, flatten, read_fastx
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_TOL = 1e-6
+
+
+def oracle_rows(db, sample_hc, pseudotax, **kw):
+    from oracle import oracle as O
+    p = O.default_params(pseudotax=pseudotax, **kw)
+    smp = O.Sample(*sample_hc)
+    return O.contain_sample(p, db["kmers"], db["kmer_off"], db["tracked"], db["tracked_off"], db["gn_size"], smp)
+
+
+def compare(rows, exp, pseudotax):
+    assert len(rows) == len(exp), (len(rows), len(exp))
+    for r, e in zip(rows, exp):
+        assert int(r["genome"]) == e.genome
+        assert int(r["contain"]) == e.contain and int(r["glen"]) == e.glen
+        assert int(r["lambda_status"]) == e.lambda_status
+        assert int(r["kmers_lost"]) == e.kmers_lost
+        assert float(r["median_cov"]) == e.median_cov
+        for f in ("naive_ani", "final_est_ani", "final_est_cov", "mean_cov"):
+            assert abs(float(r[f]) - getattr(e, f)) <= FLOAT_TOL * max(1.0, abs(getattr(e, f))), f
+        if e.lambda_status == 2:
+            assert abs(float(r["lambda"]) - e.lambda_) <= FLOAT_TOL * max(1.0, abs(e.lambda_))
+        assert int(r["ci_valid"]) == e.ci_valid
+        if e.ci_valid:
+            for i in range(4):
+                assert abs(float(r["ci"][i]) - e.ci[i]) <= FLOAT_TOL * max(1.0, abs(e.ci[i])), ("ci", i)
+        if pseudotax:
+            assert abs(float(r["rel_abund"]) - e.rel_abund) <= 1e-6 * max(1.0, abs(e.rel_abund))
+            assert abs(float(r["seq_abund"]) - e.seq_abund) <= 1e-6 * max(1.0, abs(e.seq_abund))
+
+
+def sort_query_rows(rows):
+    """syl_query returns (sample, genome) order; the reference prints by ANI descending (stable)."""
+    order = sorted(range(len(rows)), key=lambda i: (-float(rows[i]["final_est_ani"]), i))
+    return rows[order]
+
+
+@pytest.fixture(scope="module")
+def ecoli(ctx):
+    bufs, coffs, goff = [], [0], [0]
+    for name in ("e.coli-EC590.fasta.gz", "e.coli-o157.fasta.gz", "e.coli-K12.fasta.gz"):
+        for _, s in read_fastx(os.path.join(DATA, name)):
+            bufs.append(s)
+            coffs.append(coffs[-1] + len(s))
+        goff.append(len(coffs) - 1)
+    buf = np.frombuffer(b"".join(bufs), dtype=np.uint8)
+    g = ctx.sketch_genomes(buf, np.array(coffs, np.uint64), np.array(goff, np.uint64))
+    recs = read_fastx(os.path.join(DATA, "o157_reads.fastq.gz"))
+    rb, ro = flatten([s for _, s in recs])
+    smp = ctx.sketch_sequences(rb, ro)
+    return g, g.download(), smp, smp.download()
+
+
+def test_config1_query_three_rows(ctx, ecoli):
+    g, d, smp, hc = ecoli
+    db = ctx.build_db(g)
+    rows = sort_query_rows(ctx.query(db, [smp]))
+    exp = oracle_rows(d, hc, False)
+    assert len(rows) == 3  # tests/integration_test.rs:128-140: header + 3 rows
+    compare(rows, exp, False)
+
+
+def test_config1_profile_one_row_vs_ec590(ctx, ecoli):
+    g, d, smp, hc = ecoli
+    one = {k: v for k, v in d.items()}
+    n0, t0 = int(d["kmer_off"][1]), int(d["tracked_off"][1])
+    one = dict(kmers=d["kmers"][:n0], kmer_off=d["kmer_off"][:2], tracked=d["tracked"][:t0],
+               tracked_off=d["tracked_off"][:2], gn_size=d["gn_size"][:1])
+    g1 = ctx.upload_genomes(one["kmers"], one["kmer_off"], one["tracked"], one["tracked_off"], one["gn_size"])
+    db = ctx.build_db(g1)
+    rows = ctx.profile(db, [smp])
+    assert len(rows) == 1  # tests/integration_test.rs:117-126: header + 1 row
+    compare(rows, oracle_rows(one, hc, True), True)
+
+
+def test_config1_profile_three(ctx, ecoli):
+    g, d, smp, hc = ecoli
+    db = ctx.build_db(g)
+    rows = ctx.profile(db, [smp])
+    compare(rows, oracle_rows(d, hc, True), True)
+
+
+def synth_db_and_sample(ctx, n_genomes, genome_len, n_reads, n_comm, c=200, read_seed=None):
+    from sylph_b200 import synth
+    bases, off = synth.db_chunk(0, n_genomes, genome_len)
+    goff = np.arange(n_genomes + 1, dtype=np.uint64)
+    g = ctx.sketch_genomes(bases.numpy(), off.numpy().astype(np.uint64), goff, c=c)
+    kw = {} if read_seed is None else {"seed": read_seed}
+    rb, ro = synth.reads(n_reads, n_comm=n_comm, genome_len=genome_len, **kw)
+    smp = ctx.sketch_sequences(rb.numpy(), ro.numpy().astype(np.uint64), c=c)
+    return g, smp
+
+
+@pytest.mark.parametrize("pseudotax", [False, True])
+def test_synthetic_community_with_mutant_genomes(ctx, pseudotax):
+    """200 genomes (genomes 99 and 199 are ~97 % mutants of 98 / 198 => shared k-mers, k-mer
+    reassignment and derep in profile), community = first 120 genomes, coverage from <0.1x to >20x
+    so LOW / lambda / HIGH statuses and the bootstrap all occur."""
+    g, smp = synth_db_and_sample(ctx, 200, 120000, 150000, 120, c=20)
+    d, hc = g.download(), smp.download()
+    db = ctx.build_db(g)
+    if pseudotax:
+        rows = ctx.profile(db, [smp])
+    else:
+        rows = sort_query_rows(ctx.query(db, [smp]))
+    exp = oracle_rows(d, hc, pseudotax)
+    assert len(exp) > 20
+    st = {e.lambda_status for e in exp}
+    assert 2 in st and 1 in st
+    compare(rows, exp, pseudotax)
+
+
+def test_params_variants_and_multi_sample(ctx):
+    from sylph_b200.api import contain_params
+    g, s1 = synth_db_and_sample(ctx, 60, 100000, 40000, 30, c=20)
+    _, s2 = synth_db_and_sample(ctx, 1, 100000, 20000, 60, c=20, read_seed=0x5EED0011)
+    d = g.download()
+    db = ctx.build_db(g, genome_base=0)
+    for kw in (dict(no_ci=1), dict(no_adj=1), dict(minimum_ani=50.0), dict(min_number_kmers=6000.0),
+               dict(min_count_correct=1.0), dict(mean_coverage=1)):
+        rows = ctx.query(db, [s1, s2], contain_params(pseudotax=False, **kw))
+        for si, s in enumerate((s1, s2)):
+            sub = sort_query_rows(rows[rows["sample"] == si])
+            compare(sub, oracle_rows(d, s.download(), False, **kw), False)
+
+
+def test_uploaded_sketches_and_zero_counts(ctx):
+    """Sketches that come from files: unsorted sample pairs, a zero count (skipped, src/contain.rs:634)."""
+    rng = np.random.default_rng(4)
+    kmers = np.unique(rng.integers(1, 2**57, size=5000, dtype=np.uint64))[:4000]
+    rng.shuffle(kmers)
+    koff = np.array([0, 1500, 1500, 4000], dtype=np.uint64)   # genome 1 is empty
+    tracked = np.unique(rng.integers(1, 2**57, size=300, dtype=np.uint64))
+    toff = np.array([0, 100, 100, len(tracked)], dtype=np.uint64)
+    gs = np.array([1000000, 0, 2000000], dtype=np.uint64)
+    g = ctx.upload_genomes(kmers, koff, tracked, toff, gs)
+    sh = np.concatenate([kmers[:1200], kmers[2000:3900], rng.integers(2**57, 2**58, size=500, dtype=np.uint64)])
+    sc = rng.integers(0, 6, size=len(sh)).astype(np.uint32)
+    perm = rng.permutation(len(sh))
+    smp = ctx.upload_sample(sh[perm], sc[perm])
+    db = ctx.build_db(g)
+    d = dict(kmers=kmers, kmer_off=koff, tracked=tracked, tracked_off=toff, gn_size=gs)
+    compare(sort_query_rows(ctx.query(db, [smp])), oracle_rows(d, (sh, sc), False), False)
+    compare(ctx.profile(db, [smp]), oracle_rows(d, (sh, sc), True), True)

@@ -1,0 +1,146 @@
+"""GPU parity: sample sketch (a5) and genome sketch (a4) vs the CPU oracle, bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import DATA, flatten, read_fastx
+
+pytestmark = pytest.mark.gpu
+
+
+def check_reads(ctx, buf, off, k=31, c=200, no_dedup=False, sem=1):
+    from oracle import oracle as O
+    s = ctx.sketch_sequences(buf, off, k=k, c=c, no_dedup=no_dedup, sem=sem)
+    h, cnt = s.download()
+    eh, ec, mean, nd = O.sketch_reads(buf, off, k=k, c=c, no_dedup=no_dedup, sem=sem)
+    assert len(h) == len(eh)
+    assert np.array_equal(h, eh)
+    assert np.array_equal(cnt, ec)
+    assert s.num_dup_removed == nd
+    assert abs(s.mean_read_length - mean) <= 1e-6 * max(1.0, mean)
+    return len(h), nd
+
+
+def check_genomes(ctx, buf, coff, goff, k=31, c=200, min_spacing=30, pseudotax=True, individual=False, sem=1):
+    from oracle import oracle as O
+    g = ctx.sketch_genomes(buf, coff, None if individual else goff, k=k, c=c, min_spacing=min_spacing,
+                           pseudotax=pseudotax, individual=individual, sem=sem)
+    d = g.download()
+    if individual:
+        goff = np.arange(len(coff), dtype=np.uint64)
+    assert len(g) == len(goff) - 1
+    for gi in range(len(goff) - 1):
+        c0, c1 = int(goff[gi]), int(goff[gi + 1])
+        b0, b1 = int(coff[c0]), int(coff[c1])
+        sub_off = (coff[c0:c1 + 1] - coff[c0]).astype(np.uint64)
+        km, tr, gs = O.sketch_genome(buf[b0:b1], sub_off, k=k, c=c, min_spacing=min_spacing, pseudotax=pseudotax, sem=sem)
+        got_k = d["kmers"][int(d["kmer_off"][gi]):int(d["kmer_off"][gi + 1])]
+        got_t = d["tracked"][int(d["tracked_off"][gi]):int(d["tracked_off"][gi + 1])]
+        assert np.array_equal(got_k, km), "genome %d kmers" % gi
+        assert np.array_equal(got_t, tr), "genome %d tracked" % gi
+        assert int(d["gn_size"][gi]) == gs
+    return d
+
+
+def rand_seqs(rng, lengths, alphabet=b"ACGT"):
+    return [bytes(rng.choice(list(alphabet), size=int(n)).astype(np.uint8)) for n in lengths]
+
+
+def test_reads_dedup_k12(ctx):
+    recs = read_fastx(os.path.join(DATA, "k12_R1.fq"))
+    buf, off = flatten([s for _, s in recs])
+    check_reads(ctx, buf, off, c=20)
+    check_reads(ctx, buf, off, c=200)
+
+
+def test_reads_o157_long(ctx):
+    recs = read_fastx(os.path.join(DATA, "o157_reads.fastq.gz"))
+    buf, off = flatten([s for _, s in recs])
+    n, nd = check_reads(ctx, buf, off)
+    assert n == 25621
+
+
+@pytest.mark.parametrize("no_dedup", [False, True])
+def test_reads_heavy_duplicates(ctx, no_dedup):
+    """Exercise the c<4 state machine: exact duplicate reads, shifted duplicates that share only
+    one pair key, reads > 400 bp (no pair), reads < 66 bp (no pair), homopolymers (p0 == p1)."""
+    rng = np.random.default_rng(123)
+    genome = rand_seqs(rng, [150000])[0]
+    seqs = []
+    for i in range(6000):
+        st = int(rng.integers(0, 150000 - 500))
+        ln = int(rng.choice([60, 70, 100, 150, 150, 150, 250, 401, 500]))
+        s = genome[st:st + ln]
+        seqs.append(s)
+        if rng.random() < 0.3:
+            seqs.append(s)                      # exact duplicate
+        if rng.random() < 0.1:
+            seqs.append(genome[st:st + ln - 2])  # same start, different half => shares one key
+    seqs += [b"A" * 150, b"A" * 150, b"A" * 150, b"ACGT" * 40, b"ACGT" * 40, b"", b"ACG"]
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    buf, off = flatten(seqs)
+    n, nd = check_reads(ctx, buf, off, c=5, no_dedup=no_dedup)
+    if not no_dedup:
+        assert nd > 300
+
+
+def test_reads_synthetic_community(ctx):
+    from sylph_b200 import synth
+    b, o = synth.reads(60000, n_comm=4, genome_len=200000)
+    check_reads(ctx, b.numpy(), o.numpy().astype(np.uint64))
+    check_reads(ctx, b.numpy(), o.numpy().astype(np.uint64), k=21, c=50, sem=0)
+
+
+def test_reads_device_resident_and_empty(ctx):
+    import torch
+    from sylph_b200 import synth
+    b, o = synth.reads(20000, n_comm=2, genome_len=100000)
+    s_h = ctx.sketch_sequences(b.numpy(), o.numpy().astype(np.uint64))
+    s_d = ctx.sketch_sequences(b.cuda(), o.cuda())
+    for x, y in zip(s_h.download(), s_d.download()):
+        assert np.array_equal(x, y)
+    e = ctx.sketch_sequences(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(e) == 0
+
+
+def test_genomes_ecoli(ctx):
+    bufs, coffs, goff = [], [0], [0]
+    for name in ("e.coli-EC590.fasta.gz", "e.coli-o157.fasta.gz", "e.coli-K12.fasta.gz"):
+        recs = read_fastx(os.path.join(DATA, name))
+        for _, s in recs:
+            bufs.append(s)
+            coffs.append(coffs[-1] + len(s))
+        goff.append(len(coffs) - 1)
+    buf = np.frombuffer(b"".join(bufs), dtype=np.uint8)
+    coff = np.array(coffs, dtype=np.uint64)
+    goff = np.array(goff, dtype=np.uint64)
+    d = check_genomes(ctx, buf, coff, goff)
+    assert [int(x) for x in np.diff(d["kmer_off"])] == [19330, 21899, 19485]
+    check_genomes(ctx, buf, coff, goff, pseudotax=False)
+    check_genomes(ctx, buf, coff, goff, individual=True)
+
+
+@pytest.mark.parametrize("k,sem", [(31, 1), (21, 0)])
+def test_genomes_multicontig_with_repeats(ctx, k, sem):
+    """Many genomes, ragged contigs (incl. < 2k and empty), repeated segments inside a genome
+    (must be dropped entirely) and shared segments across genomes (must be kept)."""
+    rng = np.random.default_rng(77)
+    shared = rand_seqs(rng, [5000])[0]
+    contigs, goff = [], [0]
+    for g in range(40):
+        nc = int(rng.integers(0, 12))
+        rep = rand_seqs(rng, [800])[0]
+        for ci in range(nc):
+            ln = int(rng.choice([0, 10, 40, 61, 62, 63, 500, 3000, 20000]))
+            s = rand_seqs(rng, [ln])[0]
+            if ln >= 3000 and rng.random() < 0.7:
+                s = s[:1000] + rep + s[1800:]       # repeat inside the genome
+            if ln >= 20000 and rng.random() < 0.5:
+                s = s[:6000] + shared + s[11000:]   # shared across genomes
+            contigs.append(s)
+        goff.append(len(contigs))
+    buf, coff = flatten(contigs)
+    check_genomes(ctx, buf, coff, np.array(goff, dtype=np.uint64), k=k, c=11, min_spacing=30, sem=sem)
+    check_genomes(ctx, buf, coff, np.array(goff, dtype=np.uint64), k=k, c=3, min_spacing=5, sem=sem)
