@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the sylph_b200 hot paths (contract: see DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sketch|profile]
+
+Primary line (default --workload sketch) = BASELINE.json configs[1]:
+  sketch 1 Gbp of synthetic 150 bp single-end reads, k=31 c=200, per GPU (weak scaling: every
+  rank sketches its own 1 Gbp sample; no data-path collective).
+  step   = bases resident in HBM -> sample sketch (sorted hash/count table) resident in HBM
+  value  = whole-job bases/s, CUDA events, max over ranks
+  e2e    = same through the C ABI with PINNED HOST buffers: H2D of bases+offsets and D2H of the
+           sketch inside the timed region
+  roofline = the seeding kernel (dominant), algorithmic bytes (1 B/base + 16 B/survivor) over its
+           CUDA-event time measured inside the library on the launching stream
+The same JSON line carries "pairs": the containment metric (BASELINE.json configs[2]:
+1 sample vs 10k synthetic 4 Mbp genome sketches) measured the same way.
+--impl reference times the CPU restatement of the reference (oracle/, AVX2 intrinsics + OpenMP)
+on a bounded sample of the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READ_LEN = 150
+K, C = 31, 200
+GENOME_LEN = 4_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sketch", choices=["sketch", "profile"])
+    ap.add_argument("--reads", type=int, default=6_666_667, help="reads per GPU (150 bp each)")
+    ap.add_argument("--genomes", type=int, default=10_000, help="genomes per GPU for the containment metric")
+    ap.add_argument("--samples", type=int, default=None, help="samples for the containment metric (1; 16 when N>1)")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the secondary containment measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def dist_setup(n):
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, steps, world):
+    """barrier+sync, K steps between CUDA events on the current stream, sync+barrier; -> ms (max over ranks)"""
+    import torch
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world), max_over_ranks(wall_ms, world)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sketch_baseline(host_bases, host_off, n_reads_sample, repeats=1):
+    """Oracle (AVX2-intrinsic seeding + OpenMP, dedup sequential like the reference) on a bounded sample."""
+    import numpy as np
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    nb = int(host_off[n_reads_sample])
+    b = host_bases[:nb]
+    o = host_off[:n_reads_sample + 1].astype(np.uint64)
+    O.sketch_reads(b[: nb // 50], o[: n_reads_sample // 50 + 1], k=K, c=C, sem=O.SEM_AVX2_INTRIN, nthreads=cores)
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        O.sketch_reads(b, o, k=K, c=C, sem=O.SEM_AVX2_INTRIN, nthreads=cores)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    t = time.perf_counter()
+    O.sketch_reads(b[: nb // 4], o[: n_reads_sample // 4 + 1], k=K, c=C, sem=O.SEM_AVX2_INTRIN, nthreads=1)
+    dt1 = time.perf_counter() - t
+    return {"value": nb / best, "unit": "bases/s", "cores": cores, "kind": "port",
+            "sample": "%d reads (%d bases) of the same synthetic sample; AVX2-intrinsic seeding over %d OpenMP "
+                      "threads + sequential dedup (reference decomposition: 1 thread per file)" % (n_reads_sample, nb, cores),
+            "single_thread_value": (nb // 4) / dt1}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: no Rust toolchain in the image)."""
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from sylph_b200 import synth
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    if args.workload == "sketch":
+        n_sample = min(args.reads, 1_000_000)  # 150 Mbases per step
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        if dev == "cpu":
+            n_sample = min(n_sample, 100_000)
+        b, o = synth.reads(n_sample, READ_LEN, device=dev)
+        b, o = b.cpu().numpy(), o.cpu().numpy().astype(np.uint64)
+        fn = lambda: O.sketch_reads(b, o, k=K, c=C, sem=O.SEM_AVX2_INTRIN, nthreads=cores)
+        units, unit, metric = len(b), "bases/s", "bases/s sketched"
+        sample = "%d of %d reads per step (%d bases)" % (n_sample, args.reads, len(b))
+        cfg = {"workload": "sketch 1 Gbp synthetic 150 bp SE reads k=31 c=200 (BASELINE.json configs[1])",
+               "reads": args.reads, "read_len": READ_LEN, "k": K, "c": C}
+    else:
+        raise SystemExit("--impl reference --workload profile: use the default run's pairs.cpu_baseline")
+    for _ in range(args.warmup):
+        fn()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t
+    v = units * args.steps / dt
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def bench_sketch(args, ctx, rank, world, local):
+    import numpy as np
+    import torch
+    from sylph_b200 import synth
+    n_reads = args.reads
+    bases, off = synth.reads(n_reads, READ_LEN, seed=synth.SEED_READS + 0x10 * rank, device="cuda")
+    n_bases = bases.numel()
+    torch.cuda.synchronize()
+    state = {}
+
+    def step_resident():
+        s = ctx.sketch_sequences(bases, off, k=K, c=C)
+        state["n"] = len(s)
+        s.free()
+
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.enable_timing(True)
+    ctx.seed_kernel_time(reset=True)
+    l0 = ctx.launches
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, _ = timed(step_resident, args.steps, world)
+    clk = clocks.stop()
+    launches = ctx.launches - l0
+    kms, klaunch, kbases = ctx.seed_kernel_time(reset=True)
+    ctx.enable_timing(False)
+    total_bases = sum_over_ranks(float(n_bases), world)
+    value = total_bases * args.steps / (ms * 1e-3)
+
+    # one extra call for the survivor count (algorithmic output bytes of the seeding kernel)
+    surv_buf = torch.empty(int(n_bases / C * 1.3 + 65536) * 2, dtype=torch.int64, device="cuda")
+    n_surv = ctx.extract_markers_batch(bases, off, k=K, c=C, out=surv_buf)
+    del surv_buf
+    alg_bytes = n_bases + 16 * n_surv
+    peak, peak_src = measured_peak_hbm()
+    k_ms = kms / max(klaunch, 1)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_seed<31>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": k_ms, "kernel_share_of_step": kms / ms if ms else None,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "integer-issue bound (about 40 SASS integer instructions per window), not HBM bound; "
+                        "see DESIGN.md and profiles/"}
+
+    # ---- e2e: pinned host buffers through the C ABI, H2D + D2H inside the timed region
+    hb = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
+    ho = torch.empty(n_reads + 1, dtype=torch.int64, pin_memory=True)
+    hb.copy_(bases)
+    ho.copy_(off)
+    torch.cuda.synchronize()
+    hb_np, ho_np = hb.numpy(), ho.numpy().view(np.uint64)
+    e2e_state = {}
+
+    def step_e2e():
+        s = ctx.sketch_sequences(hb_np, ho_np, k=K, c=C)
+        h, c = s.download()
+        e2e_state["n"] = len(h)
+        s.free()
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    e2e_steps = max(1, min(args.steps, 5))
+    _, wall_ms = timed(step_e2e, e2e_steps, world)
+    e2e_value = total_bases * e2e_steps / (wall_ms * 1e-3)
+    e2e = {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
+           "d2h_bytes_per_step": int(12 * e2e_state["n"]), "steps": e2e_steps, "ms_per_step": wall_ms / e2e_steps,
+           "timing": "wall clock bracketed by device syncs, max over ranks"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_sketch_baseline(hb_np, ho_np, min(n_reads, 2_000_000))
+    line = {"metric": "bases/s sketched", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "sketch 1 Gbp synthetic 150 bp SE reads k=31 c=200 (BASELINE.json configs[1])",
+                       "reads_per_gpu": n_reads, "read_len": READ_LEN, "k": K, "c": C, "sem": "avx2-lane",
+                       "l2": "inputs (%.2f GB per step) are larger than L2; no flush needed" % (n_bases / 1e9),
+                       "sketch_entries": state["n"], "survivors": int(n_surv)},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    return line, (bases, off)
+
+
+def build_db(ctx, g0, g1, chunk=125):
+    from sylph_b200 import synth
+    parts = []
+    for a in range(g0, g1, chunk):
+        b = min(g1, a + chunk)
+        bases, off = synth.db_chunk(a, b, GENOME_LEN, device="cuda")
+        import torch
+        goff = torch.arange(b - a + 1, dtype=torch.int64, device="cuda")
+        parts.append(ctx.sketch_genomes(bases, off, goff, k=K, c=C))
+        del bases
+    g = ctx.concat_genomes(parts)
+    for p in parts:
+        p.free()
+    return g
+
+
+def bench_pairs(args, ctx, rank, world, local, reads):
+    """BASELINE.json configs[2] (N=1) / configs[3] shape (N>1: genome-sharded db, replicated samples)."""
+    import numpy as np
+    import torch
+    from sylph_b200 import synth
+    n_samples = args.samples or (1 if world == 1 else 16)
+    G = args.genomes
+    t0 = time.perf_counter()
+    genomes = build_db(ctx, rank * G, (rank + 1) * G)
+    db = ctx.build_db(genomes, genome_base=rank * G)
+    torch.cuda.synchronize()
+    t_db = time.perf_counter() - t0
+    samples = []
+    bases, off = reads
+    for si in range(n_samples):
+        if si == 0:
+            samples.append(ctx.sketch_sequences(bases, off, k=K, c=C))
+        else:  # further samples: different community draws, 1/8 of the depth each to bound setup time
+            b, o = synth.reads(max(10000, args.reads // 8), READ_LEN, seed=synth.SEED_READS + 0x10 + si, device="cuda")
+            samples.append(ctx.sketch_sequences(b, o, k=K, c=C))
+            del b, o
+    from sylph_b200.api import contain_params
+    P = contain_params(k=K, pseudotax=False)
+    st = {}
+
+    def step():
+        rows = ctx.query(db, samples, P)
+        st["rows"] = rows
+        if world > 1:  # the one collective of the path: all-gather of the per-shard result rows
+            import torch.distributed as dist
+            n_local = torch.tensor([len(rows)], dtype=torch.int64, device="cuda")
+            counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(counts, n_local)
+            mx = max(int(c.item()) for c in counts)
+            buf = torch.zeros(max(mx, 1) * 144, dtype=torch.uint8, device="cuda")
+            if len(rows):
+                buf[: len(rows) * 144] = torch.from_numpy(rows.view(np.uint8).reshape(-1)).cuda()
+            out = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(out, buf)
+            st["gathered"] = sum(int(c.item()) for c in counts)
+
+    for _ in range(args.warmup):
+        step()
+    l0 = ctx.launches
+    ms, wall = timed(step, args.steps, world)
+    launches = ctx.launches - l0
+    pairs = float(n_samples) * G * world
+    value = pairs * args.steps / (ms * 1e-3)
+    d = genomes.download() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    nk_total = sum_over_ranks(float(int(np.sum([len(s) for s in samples]))), 1)
+    out = {"metric": "(sample x genome) containment pairs/s", "value": value, "unit": "pairs/s", "ms_per_step": ms / args.steps,
+           "wall_ms_per_step": wall / args.steps, "steps": args.steps, "gpu_launches": int(launches),
+           "config": {"workload": "query %d sample sketch(es) vs %d synthetic 4 Mbp genome sketches per GPU "
+                                  "(BASELINE.json configs[%d])" % (n_samples, G, 2 if world == 1 else 3),
+                      "genomes_per_gpu": G, "samples": n_samples, "sample_keys": int(nk_total),
+                      "rows_per_step": int(len(st["rows"])), "db_build_s": t_db,
+                      "collective": "all_gather of result rows (NCCL)" if world > 1 else "none"},
+           "e2e_note": "syl_query returns rows in host memory: the D2H of the result rows is inside the timed region"}
+    if d is not None:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        h, c = samples[0].download()
+        smp = O.Sample(h, c)
+        p = O.default_params(pseudotax=False)
+        t = time.perf_counter()
+        res = O.contain_sample(p, d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"], smp, nthreads=cores)
+        dt = time.perf_counter() - t
+        out["cpu_baseline"] = {"value": G / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                               "sample": "all %d pairs of the same db/sample, oracle get_stats over %d OpenMP threads" % (G, cores),
+                               "rows": len(res)}
+        assert len(res) == len(st["rows"]), (len(res), len(st["rows"]))
+        kbytes = 8.0 * float(d["kmer_off"][-1])
+        out["roofline_equiv"] = {
+            "streaming_bytes_per_step": kbytes + 64.0 * G,
+            "equiv_GBps": (kbytes + 64.0 * G) / (ms / args.steps * 1e-3) / 1e9,
+            "note": "SURVEY §8(d) counts 8 B x |G| per pair for a genome-streaming probe loop; this implementation "
+                    "probes a sorted db index with the sample keys instead and never streams the db, so the "
+                    "equivalent bandwidth may exceed the HBM peak; see DESIGN.md"}
+    for s in samples:
+        s.free()
+    db.free()
+    genomes.free()
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    rank, world, local = dist_setup(args.gpus)
+    import sylph_b200
+    ctx = sylph_b200.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    if args.workload == "sketch":
+        line, reads = bench_sketch(args, ctx, rank, world, local)
+        if not args.no_pairs:
+            line["pairs"] = bench_pairs(args, ctx, rank, world, local, reads)
+    else:
+        from sylph_b200 import synth
+        reads = synth.reads(args.reads, READ_LEN, seed=synth.SEED_READS + 0x10 * rank, device="cuda")
+        p = bench_pairs(args, ctx, rank, world, local, reads)
+        line = {"metric": p["metric"], "value": p["value"], "unit": p["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": p["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": p["config"],
+                "gpu_launches": p["gpu_launches"], "pairs": p}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

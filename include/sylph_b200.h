@@ -66,6 +66,11 @@ void syl_ctx_destroy(syl_ctx *ctx);
 int syl_ctx_sync(syl_ctx *ctx);
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches counter). */
 uint64_t syl_ctx_launch_count(const syl_ctx *ctx);
+/* Optional device-side timing of the dominant kernel (the seeding kernel): when enabled, every
+ * launch is bracketed by CUDA events on the ctx stream; syl_ctx_seed_kernel_time returns the
+ * accumulated milliseconds, launches and bases since the last reset (and resets when asked). */
+int syl_ctx_enable_timing(syl_ctx *ctx, int on);
+int syl_ctx_seed_kernel_time(syl_ctx *ctx, double *total_ms, uint64_t *launches, uint64_t *bases, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * (1) Seeding — replaces extract_markers / extract_markers_positions over a whole batch
@@ -134,6 +139,9 @@ int syl_sketch_genomes(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_b
 int syl_genomes_upload(syl_ctx *ctx, int mem, const uint64_t *kmers, const uint64_t *kmer_off,
                        const uint64_t *tracked, const uint64_t *tracked_off, const uint64_t *gn_size,
                        uint64_t n_genomes, int k, uint64_t c, syl_genomes **out);
+/* Concatenate batches (database build in chunks): genome i of part p becomes genome
+ * (sum of earlier parts' counts) + i.  All parts must agree on k, c and has_tracked. */
+int syl_genomes_concat(syl_ctx *ctx, const syl_genomes *const *parts, uint32_t n_parts, syl_genomes **out);
 uint64_t syl_genomes_count(const syl_genomes *g);
 uint64_t syl_genomes_total_kmers(const syl_genomes *g);
 uint64_t syl_genomes_total_tracked(const syl_genomes *g);

@@ -14,6 +14,7 @@ _LIB = None
 
 SEM_SCALAR = 0
 SEM_AVX2 = 1
+SEM_AVX2_INTRIN = 2
 
 
 class Params(C.Structure):

@@ -138,6 +138,7 @@ static int seeds_avx2sem(const uint8_t *s, size_t len, size_t k, uint64_t c, siz
 size_t syo_extract_markers(const uint8_t *s, size_t len, int k, uint64_t c, int sem,
                            uint64_t *out_hash, size_t cap) {
     emit_t e = {NULL, out_hash, cap, 0};
+    if (sem == SYO_SEM_AVX2_INTRIN) return syo_extract_markers_avx2_intrin(s, len, k, c, out_hash, cap);
     if (sem == SYO_SEM_SCALAR) {
         seeds_scalar(s, len, (size_t)k, c, &e);
     } else {

@@ -30,7 +30,8 @@ extern "C" {
 /* Which window set a record contributes (src/sketch.rs:53-93 runtime dispatch). */
 enum {
     SYO_SEM_SCALAR = 0, /* fmh_seeds: all L-k+1 windows            (src/seeding.rs:86-146)      */
-    SYO_SEM_AVX2 = 1    /* 4-lane split, trailing windows dropped  (src/avx2_seeding.rs:33-148) */
+    SYO_SEM_AVX2 = 1,   /* 4-lane split, trailing windows dropped  (src/avx2_seeding.rs:33-148) */
+    SYO_SEM_AVX2_INTRIN = 2 /* same window set as SYO_SEM_AVX2, computed with AVX2 intrinsics (timed baseline) */
 };
 
 /* src/seeding.rs:4-15 (the shipped, "bugged" minimap2-style hash). */

@@ -50,6 +50,8 @@ SIGNATURES = {
     "syl_ctx_destroy": (None, [_vp]),
     "syl_ctx_sync": (_i, [_vp]),
     "syl_ctx_launch_count": (_u64, [_vp]),
+    "syl_ctx_enable_timing": (_i, [_vp, _i]),
+    "syl_ctx_seed_kernel_time": (_i, [_vp, C.POINTER(C.c_double), _pu64, _pu64, _i]),
     "syl_seed_batch": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _vp, _u64, _pu64]),
     "syl_sketch_reads": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _pp]),
     "syl_sample_upload": (_i, [_vp, _i, _vp, _vp, _u64, _i, _u64, _pp]),
@@ -61,6 +63,7 @@ SIGNATURES = {
     "syl_sample_free": (None, [_vp]),
     "syl_sketch_genomes": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _vp, _u64, _i, _u64, _u64, _i, _i, _i, _pp]),
     "syl_genomes_upload": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _u64, _i, _u64, _pp]),
+    "syl_genomes_concat": (_i, [_vp, _pp, _u32, _pp]),
     "syl_genomes_count": (_u64, [_vp]),
     "syl_genomes_total_kmers": (_u64, [_vp]),
     "syl_genomes_total_tracked": (_u64, [_vp]),

@@ -73,6 +73,16 @@ class Context:
     def launches(self):
         return int(_lib.lib().syl_ctx_launch_count(self._h))
 
+    def enable_timing(self, on=True):
+        _lib.check(_lib.lib().syl_ctx_enable_timing(self._h, int(on)))
+
+    def seed_kernel_time(self, reset=True):
+        """-> (total_ms, launches, bases) of the seeding kernel since the last reset (CUDA events
+        on the ctx stream, recorded inside the library around each launch)."""
+        ms, n, b = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        _lib.check(_lib.lib().syl_ctx_seed_kernel_time(self._h, C.byref(ms), C.byref(n), C.byref(b), int(reset)))
+        return ms.value, n.value, b.value
+
     # ---- (1) seeding -------------------------------------------------------------------------
     def extract_markers_batch(self, bases, rec_off, k=31, c=200, sem=SEM_AVX2, with_pos=False, cap=None,
                               out=None):
@@ -161,6 +171,12 @@ class Context:
         _, pg, ngs, k5 = _arg(gn_size, np.uint64)
         h = C.c_void_p()
         _lib.check(L.syl_genomes_upload(self._h, mem, pk, pko, pt, pto, pg, nko - 1, k, c, C.byref(h)))
+        return Genomes(self, h)
+
+    def concat_genomes(self, parts):
+        arr = (C.c_void_p * max(len(parts), 1))(*[p._h for p in parts])
+        h = C.c_void_p()
+        _lib.check(_lib.lib().syl_genomes_concat(self._h, arr, len(parts), C.byref(h)))
         return Genomes(self, h)
 
     # ---- (4) containment ---------------------------------------------------------------------

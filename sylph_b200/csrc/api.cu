@@ -10,7 +10,7 @@ namespace syl {
 static thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
 
-int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off,
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                 uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
                 uint64_t cap, uint64_t *n_out);
 
@@ -88,6 +88,15 @@ void syl_ctx_destroy(syl_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->stage_b[i]) cudaFree(ctx->stage_b[i]);
+        if (ctx->stage_o[i]) cudaFree(ctx->stage_o[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -102,6 +111,26 @@ int syl_ctx_sync(syl_ctx *ctx) {
 
 uint64_t syl_ctx_launch_count(const syl_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int syl_ctx_enable_timing(syl_ctx *ctx, int on) {
+    if (!ctx) { set_error("ctx is NULL"); return SYL_ERR_ARG; }
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev0) {
+        SYL_CUDA(cudaEventCreate(&ctx->ev0));
+        SYL_CUDA(cudaEventCreate(&ctx->ev1));
+    }
+    ctx->timing = on != 0;
+    return SYL_OK;
+}
+
+int syl_ctx_seed_kernel_time(syl_ctx *ctx, double *total_ms, uint64_t *launches, uint64_t *bases, int reset) {
+    if (!ctx) { set_error("ctx is NULL"); return SYL_ERR_ARG; }
+    if (total_ms) *total_ms = ctx->seed_ms;
+    if (launches) *launches = ctx->seed_launches;
+    if (bases) *bases = ctx->seed_bases;
+    if (reset) { ctx->seed_ms = 0.; ctx->seed_launches = 0; ctx->seed_bases = 0; }
+    return SYL_OK;
+}
+
 int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
                    const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
                    syl_survivor *out, uint64_t cap, uint64_t *n_out) {
@@ -114,10 +143,10 @@ int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases
     Staged<uint64_t> so;
     SYL_TRY(sb.init(ctx, mem, bases, n_bases));
     SYL_TRY(so.init(ctx, mem, rec_off, n_rec + 1));
-    if (mem == SYL_MEM_DEVICE) return seed_device(ctx, sb.p, n_bases, so.p, n_rec, k, c, sem, with_pos, out, cap, n_out);
+    if (mem == SYL_MEM_DEVICE) return seed_device(ctx, sb.p, n_bases, so.p, 0, n_rec, k, c, sem, with_pos, out, cap, n_out);
     DevBuf<syl_survivor> d_out;
     SYL_TRY(d_out.alloc(cap, ctx->stream));
-    int rc = seed_device(ctx, sb.p, n_bases, so.p, n_rec, k, c, sem, with_pos, d_out.p, cap, n_out);
+    int rc = seed_device(ctx, sb.p, n_bases, so.p, 0, n_rec, k, c, sem, with_pos, d_out.p, cap, n_out);
     if (rc != SYL_OK) return rc;
     if (*n_out) {
         SYL_CUDA(cudaMemcpyAsync(out, d_out.p, *n_out * sizeof(syl_survivor), cudaMemcpyDeviceToHost, ctx->stream));

@@ -48,11 +48,23 @@ struct syl_ctx {
     // small persistent scratch: device counters + pinned host mirror
     uint64_t *d_counters = nullptr;  // 16 x u64
     uint64_t *h_counters = nullptr;  // pinned
+    // optional timing of the seeding kernel (syl_ctx_enable_timing)
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double seed_ms = 0.;
+    uint64_t seed_launches = 0, seed_bases = 0;
+    // double-buffered H2D staging for host-memory inputs (lazily allocated, reused across calls)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    uint8_t *stage_b[2] = {nullptr, nullptr};
+    uint64_t *stage_o[2] = {nullptr, nullptr};
+    uint64_t stage_cap_b[2] = {0, 0}, stage_cap_o[2] = {0, 0};
 };
 
 // Device-resident SequencesSketch.kmer_counts (src/types.rs:145-155): parallel arrays sorted by hash
 struct syl_sample {
     int device = 0;
+    cudaStream_t stream = nullptr;  // arrays are stream-ordered allocations of this stream
     uint64_t *hash = nullptr;  // ascending, distinct
     uint32_t *count = nullptr;
     uint64_t n = 0;

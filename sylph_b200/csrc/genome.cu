@@ -17,7 +17,7 @@
 #include "common.cuh"
 
 namespace syl {
-int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off,
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                 uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
                 uint64_t cap, uint64_t *n_out);
 }
@@ -149,6 +149,11 @@ __global__ void k_flag_to_u64(const uint8_t *__restrict__ flag, uint64_t n, uint
     if (i < n) out[i] = flag[i] == want ? 1ull : 0ull;
 }
 
+__global__ void k_add_offset(const uint64_t *__restrict__ src, uint64_t n, uint64_t add, uint64_t *__restrict__ dst) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
+
 static int genomes_alloc(syl_genomes *g, uint64_t n_genomes, uint64_t nk, uint64_t nt) {
     SYL_CUDA(cudaMalloc((void **)&g->kmers, std::max<uint64_t>(nk, 1) * 8));
     SYL_CUDA(cudaMalloc((void **)&g->tracked, std::max<uint64_t>(nt, 1) * 8));
@@ -172,7 +177,7 @@ int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases
     uint64_t N = 0;
     for (;;) {
         SYL_TRY(sv.alloc(scap, st));
-        int rc = seed_device(ctx, d_bases, n_bases, d_contig_off, n_contigs, k, c, sem, /*with_pos=*/1, sv.p, scap, &N);
+        int rc = seed_device(ctx, d_bases, n_bases, d_contig_off, 0, n_contigs, k, c, sem, /*with_pos=*/1, sv.p, scap, &N);
         if (rc == SYL_ERR_CAPACITY) { scap = N + 16; continue; }
         if (rc != SYL_OK) return rc;
         break;
@@ -339,6 +344,47 @@ int syl_genomes_upload(syl_ctx *ctx, int mem, const uint64_t *kmers, const uint6
     }
     if (gn_size && n_genomes) SYL_CUDA(cudaMemcpyAsync(g->gn_size, gn_size, n_genomes * 8, kind, st));
     else if (n_genomes) SYL_CUDA(cudaMemsetAsync(g->gn_size, 0, n_genomes * 8, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    *out = g;
+    return SYL_OK;
+}
+
+int syl_genomes_concat(syl_ctx *ctx, const syl_genomes *const *parts, uint32_t n_parts, syl_genomes **out) {
+    if (!ctx || !out || (n_parts && !parts)) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint64_t G = 0, nk = 0, nt = 0;
+    for (uint32_t i = 0; i < n_parts; i++) {
+        if (!parts[i]) { set_error("NULL part"); return SYL_ERR_ARG; }
+        if (parts[i]->k != parts[0]->k || parts[i]->c != parts[0]->c || parts[i]->has_tracked != parts[0]->has_tracked) {
+            set_error("parts disagree on k / c / has_tracked");
+            return SYL_ERR_ARG;
+        }
+        G += parts[i]->n; nk += parts[i]->total_kmers; nt += parts[i]->total_tracked;
+    }
+    syl_genomes *g = new (std::nothrow) syl_genomes();
+    if (!g) return SYL_ERR_OOM;
+    g->device = ctx->device;
+    if (n_parts) { g->k = parts[0]->k; g->c = parts[0]->c; g->has_tracked = parts[0]->has_tracked; }
+    int rc = genomes_alloc(g, G, nk, nt);
+    if (rc != SYL_OK) { syl_genomes_free(g); return rc; }
+    uint64_t g0 = 0, k0 = 0, t0 = 0;
+    for (uint32_t i = 0; i < n_parts; i++) {
+        const syl_genomes *p = parts[i];
+        if (p->total_kmers) SYL_CUDA(cudaMemcpyAsync(g->kmers + k0, p->kmers, p->total_kmers * 8, cudaMemcpyDeviceToDevice, st));
+        if (p->total_tracked) SYL_CUDA(cudaMemcpyAsync(g->tracked + t0, p->tracked, p->total_tracked * 8, cudaMemcpyDeviceToDevice, st));
+        if (p->n) SYL_CUDA(cudaMemcpyAsync(g->gn_size + g0, p->gn_size, p->n * 8, cudaMemcpyDeviceToDevice, st));
+        k_add_offset<<<nblk(p->n + 1, 256), 256, 0, st>>>(p->kmer_off, p->n + 1, k0, g->kmer_off + g0);
+        k_add_offset<<<nblk(p->n + 1, 256), 256, 0, st>>>(p->tracked_off, p->n + 1, t0, g->tracked_off + g0);
+        ctx->launches += 2;
+        g0 += p->n; k0 += p->total_kmers; t0 += p->total_tracked;
+    }
+    if (n_parts == 0) {
+        SYL_CUDA(cudaMemsetAsync(g->kmer_off, 0, 8, st));
+        SYL_CUDA(cudaMemsetAsync(g->tracked_off, 0, 8, st));
+    }
+    SYL_CUDA(cudaGetLastError());
     SYL_CUDA(cudaStreamSynchronize(st));
     *out = g;
     return SYL_OK;

@@ -13,6 +13,8 @@
 // repeated k-mers is irrelevant (identical events; the second is a duplicate either way).
 #include <cub/cub.cuh>
 
+#include <chrono>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -20,7 +22,7 @@
 
 namespace syl {
 
-int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off,
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                 uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
                 uint64_t cap, uint64_t *n_out);
 
@@ -32,34 +34,56 @@ constexpr uint64_t NO_PAIR = 1ull;  // bit 0 of recflag set => the read has no p
 
 // pair_kmer_single (src/sketch.rs:624-656): four 16-base keys sampled at even/odd offsets from
 // the read start and from the middle.  len > 400 (src/sketch.rs:923) or len < 66 (:627) => None.
-__global__ void k_events(const syl_survivor *__restrict__ sv, uint64_t n, const uint8_t *__restrict__ bases,
-                         const uint64_t *__restrict__ rec_off, uint64_t rec_base, int no_dedup,
-                         uint64_t *__restrict__ hash, uint64_t *__restrict__ recflag,
-                         uint64_t *__restrict__ p0, uint64_t *__restrict__ p1) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const syl_survivor s = sv[i];
-    hash[i] = s.hash;
-    const uint64_t a = rec_off[s.rec], L = rec_off[s.rec + 1] - a;
-    const bool has_pair = !no_dedup && L <= 400 && L >= 66;
-    recflag[i] = ((rec_base + s.rec) << 1) | (has_pair ? 0ull : NO_PAIR);
-    uint64_t k0 = 0, k1 = 0;
-    if (has_pair) {
-        const uint8_t *p = bases + a;
-        const uint64_t half = L / 2;
-        uint32_t f = 0, g = 0, r = 0, t = 0;
-#pragma unroll 4
-        for (int j = 0; j < 16; j++) {
-            f = (f << 2) | byte_to_seq(p[2 * j]);
-            r = (r << 2) | byte_to_seq(p[2 * j + half]);
-            g = (g << 2) | byte_to_seq(p[1 + 2 * j]);
-            t = (t << 2) | byte_to_seq(p[1 + 2 * j + half]);
-        }
-        k0 = ((uint64_t)f << 32) | r;  // doublepairs.0 = [kmer_f, kmer_r]
-        k1 = ((uint64_t)g << 32) | t;  // doublepairs.1 = [kmer_g, kmer_t]
+// Warp-cooperative: a warp owns 32 survivors; for each of them the 32 lanes fetch the 32 bytes a
+// key is drawn from with ONE coalesced byte load per lane and assemble the 32-bit key with one
+// ballot: lane l supplies bit l of the key, i.e. one bit of the 2-bit code of base
+// 2*((31-l)>>1) (+1 for the odd keys), so no per-thread byte gathers are needed.
+constexpr int EV_THREADS = 256;
+__global__ void __launch_bounds__(EV_THREADS)
+k_events(const syl_survivor *__restrict__ sv, uint64_t n, const uint8_t *__restrict__ bases,
+         const uint64_t *__restrict__ rec_off, uint64_t off_bias, uint64_t rec_base, int no_dedup,
+         uint64_t *__restrict__ hash, uint64_t *__restrict__ recflag,
+         uint64_t *__restrict__ p0, uint64_t *__restrict__ p1) {
+    __shared__ uint8_t lut[256];
+    for (int i = threadIdx.x; i < 256; i += EV_THREADS) lut[i] = (uint8_t)byte_to_seq((uint32_t)i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * EV_THREADS + threadIdx.x) >> 5;
+    const uint64_t base_i = warp * 32;
+    if (base_i >= n) return;
+    const uint64_t i = base_i + lane;
+    uint64_t a = 0, L = 0;
+    bool has_pair = false;
+    if (i < n) {
+        const syl_survivor s = sv[i];
+        hash[i] = s.hash;
+        a = rec_off[s.rec] - off_bias;
+        L = rec_off[s.rec + 1] - off_bias - a;
+        has_pair = !no_dedup && L <= 400 && L >= 66;
+        recflag[i] = ((rec_base + s.rec) << 1) | (has_pair ? 0ull : NO_PAIR);
     }
-    p0[i] = k0;
-    p1[i] = k1;
+    const uint32_t fld = (uint32_t)(31 - lane) >> 1;       // which of the 16 bases this lane's bit belongs to
+    const uint32_t bit = ((31 - lane) & 1) ? 0u : 1u;      // low or high bit of its 2-bit code
+    uint64_t k0 = 0, k1 = 0;
+    const unsigned todo = __ballot_sync(0xffffffffu, has_pair);
+    for (unsigned m = todo; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const uint64_t aj = __shfl_sync(0xffffffffu, a, j);
+        const uint64_t half = __shfl_sync(0xffffffffu, L, j) >> 1;
+        const uint8_t *p = bases + aj + 2 * fld;
+        const uint32_t f = __ballot_sync(0xffffffffu, (lut[p[0]] >> bit) & 1u);
+        const uint32_t r = __ballot_sync(0xffffffffu, (lut[p[half]] >> bit) & 1u);
+        const uint32_t g = __ballot_sync(0xffffffffu, (lut[p[1]] >> bit) & 1u);
+        const uint32_t t = __ballot_sync(0xffffffffu, (lut[p[1 + half]] >> bit) & 1u);
+        if (lane == j) {
+            k0 = ((uint64_t)f << 32) | r;  // doublepairs.0 = [kmer_f, kmer_r]
+            k1 = ((uint64_t)g << 32) | t;  // doublepairs.1 = [kmer_g, kmer_t]
+        }
+    }
+    if (i < n) {
+        p0[i] = k0;
+        p1[i] = k1;
+    }
 }
 
 __global__ void k_iota(uint32_t *idx, uint64_t n) {
@@ -167,7 +191,7 @@ struct SampleBuilder {
     }
 
     // one batch of reads, device resident; read indices continue from the previous batch
-    int add(const uint8_t *d_bases, uint64_t nb, const uint64_t *d_off, uint64_t nr) {
+    int add(const uint8_t *d_bases, uint64_t nb, const uint64_t *d_off, uint64_t off_bias, uint64_t nr) {
         cudaStream_t st = ctx->stream;
         if (nr == 0) return SYL_OK;
         uint64_t scap = nb / c + nb / (4 * c) + 65536;
@@ -176,14 +200,14 @@ struct SampleBuilder {
         uint64_t n = 0;
         for (;;) {
             SYL_TRY(sv.alloc(scap, st));
-            int rc = seed_device(ctx, d_bases, nb, d_off, nr, k, c, sem, /*with_pos=*/0, sv.p, scap, &n);
+            int rc = seed_device(ctx, d_bases, nb, d_off, off_bias, nr, k, c, sem, /*with_pos=*/0, sv.p, scap, &n);
             if (rc == SYL_ERR_CAPACITY) { scap = n + 16; continue; }
             if (rc != SYL_OK) return rc;
             break;
         }
         SYL_TRY(reserve(n_events + n));
         if (n) {
-            k_events<<<nblk(n, 256), 256, 0, st>>>(sv.p, n, d_bases, d_off, n_reads, no_dedup, hash + n_events,
+            k_events<<<nblk(n, EV_THREADS), EV_THREADS, 0, st>>>(sv.p, n, d_bases, d_off, off_bias, n_reads, no_dedup, hash + n_events,
                                                     recflag + n_events, p0 + n_events, p1 + n_events);
             ctx->launches++;
             SYL_CUDA(cudaGetLastError());
@@ -199,6 +223,7 @@ struct SampleBuilder {
         syl_sample *s = new (std::nothrow) syl_sample();
         if (!s) return SYL_ERR_OOM;
         s->device = ctx->device;
+        s->stream = ctx->stream;
         s->k = k;
         s->c = c;
         s->mean_read_length = n_reads ? (double)n_bases / (double)n_reads : 0.;
@@ -255,8 +280,8 @@ struct SampleBuilder {
         SYL_CUDA(cudaStreamSynchronize(st));
         const uint64_t U = ctx->h_counters[1];
         ctx->launches += 2;
-        SYL_CUDA(cudaMalloc((void **)&s->hash, std::max<uint64_t>(U, 1) * 8));
-        SYL_CUDA(cudaMalloc((void **)&s->count, std::max<uint64_t>(U, 1) * 4));
+        SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(U, 1) * 8, st));
+        SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(U, 1) * 4, st));
         SYL_CUDA(cudaMemcpyAsync(s->hash, uniq.p, U * 8, cudaMemcpyDeviceToDevice, st));
         s->n = U;
         if (no_dedup) {
@@ -298,44 +323,34 @@ int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bas
     SampleBuilder b{ctx, k, c, no_dedup, sem};
     cudaStream_t st = ctx->stream;
     if (mem == SYL_MEM_DEVICE) {
-        SYL_TRY(b.add(bases, n_bases, rec_off, n_reads));
+        SYL_TRY(b.add(bases, n_bases, rec_off, 0, n_reads));
         return b.finish(out);
     }
     if (mem != SYL_MEM_HOST) { set_error("bad mem"); return SYL_ERR_ARG; }
-    // Host buffers: cut the reads into chunks of ~CHUNK bytes on record boundaries, copy chunk
-    // i+1 on a side stream while chunk i is being seeded (pinned caller memory overlaps fully).
+    // Host buffers: cut the reads into chunks of <= CHUNK bytes on record boundaries and copy
+    // chunk i+1 on the ctx copy stream while chunk i is being seeded (pinned caller memory
+    // overlaps fully).  Bases and the matching slice of rec_off are copied verbatim; kernels
+    // subtract the slice's first offset (off_bias).  Staging buffers live in the ctx.
     const uint64_t CHUNK = 128ull << 20;
-    cudaStream_t cs;
-    SYL_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    cudaEvent_t ev_copied[2], ev_used[2];
-    for (int i = 0; i < 2; i++) {
-        cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_used[i], cudaEventDisableTiming);
+    static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    if (!ctx->copy_stream) {
+        SYL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            SYL_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            SYL_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+        }
     }
-    uint8_t *d_b[2] = {nullptr, nullptr};
-    uint64_t *d_o[2] = {nullptr, nullptr};
-    uint64_t cap_b[2] = {0, 0}, cap_o[2] = {0, 0};
-    std::vector<uint64_t> h_off;  // chunk-relative offsets (pageable; small next to the bases)
+    cudaStream_t cs = ctx->copy_stream;
     int rc = SYL_OK;
     uint64_t r0 = 0;
     int slot = 0;
-    struct Pending { uint64_t nb, nr; int slot; bool valid; } pend = {0, 0, 0, false};
-    auto cleanup = [&]() {
-        cudaStreamSynchronize(cs);
-        cudaStreamSynchronize(st);
-        for (int i = 0; i < 2; i++) {
-            if (d_b[i]) cudaFree(d_b[i]);
-            if (d_o[i]) cudaFree(d_o[i]);
-            cudaEventDestroy(ev_copied[i]);
-            cudaEventDestroy(ev_used[i]);
-        }
-        cudaStreamDestroy(cs);
-    };
-    std::vector<uint64_t> rel[2];
+    struct Pending { uint64_t nb, nr, bias; int slot; bool valid; } pend = {0, 0, 0, 0, false};
     while (r0 < n_reads || pend.valid) {
-        Pending next = {0, 0, slot, false};
+        Pending next = {0, 0, 0, slot, false};
         if (r0 < n_reads) {
-            // pick r1: records [r0, r1) with total bytes <= CHUNK (at least one record)
+            // records [r0, r1) with total bytes <= CHUNK (at least one record)
             uint64_t lo = r0 + 1, hi = n_reads;
             const uint64_t base = rec_off[r0];
             while (lo < hi) {
@@ -343,38 +358,48 @@ int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bas
                 if (rec_off[mid] - base <= CHUNK) lo = mid; else hi = mid - 1;
             }
             const uint64_t r1 = lo, nb = rec_off[r1] - base, nr = r1 - r0;
-            if (nb + 64 > cap_b[slot]) {
-                if (d_b[slot]) { cudaStreamSynchronize(st); cudaFree(d_b[slot]); }
-                cap_b[slot] = std::max<uint64_t>(nb + 64, CHUNK + 64);
-                if (cudaMalloc((void **)&d_b[slot], cap_b[slot]) != cudaSuccess) { rc = SYL_ERR_OOM; set_error("chunk alloc"); break; }
+            if (nb + 64 > ctx->stage_cap_b[slot]) {
+                cudaStreamSynchronize(st);
+                cudaStreamSynchronize(cs);
+                if (ctx->stage_b[slot]) cudaFree(ctx->stage_b[slot]);
+                ctx->stage_b[slot] = nullptr;
+                ctx->stage_cap_b[slot] = std::max<uint64_t>(nb + 64, CHUNK + 64);
+                if (cudaMalloc((void **)&ctx->stage_b[slot], ctx->stage_cap_b[slot]) != cudaSuccess) {
+                    ctx->stage_cap_b[slot] = 0; rc = SYL_ERR_OOM; set_error("staging alloc failed"); break;
+                }
             }
-            if (nr + 1 > cap_o[slot]) {
-                if (d_o[slot]) { cudaStreamSynchronize(st); cudaFree(d_o[slot]); }
-                cap_o[slot] = (nr + 1) * 2;
-                if (cudaMalloc((void **)&d_o[slot], cap_o[slot] * 8) != cudaSuccess) { rc = SYL_ERR_OOM; set_error("chunk alloc"); break; }
+            if (nr + 1 > ctx->stage_cap_o[slot]) {
+                cudaStreamSynchronize(st);
+                cudaStreamSynchronize(cs);
+                if (ctx->stage_o[slot]) cudaFree(ctx->stage_o[slot]);
+                ctx->stage_o[slot] = nullptr;
+                ctx->stage_cap_o[slot] = (nr + 1) * 2;
+                if (cudaMalloc((void **)&ctx->stage_o[slot], ctx->stage_cap_o[slot] * 8) != cudaSuccess) {
+                    ctx->stage_cap_o[slot] = 0; rc = SYL_ERR_OOM; set_error("staging alloc failed"); break;
+                }
             }
-            rel[slot].resize(nr + 1);
-            for (uint64_t i = 0; i <= nr; i++) rel[slot][i] = rec_off[r0 + i] - base;
-            cudaStreamWaitEvent(cs, ev_used[slot], 0);  // previous user of this slot is done
-            if (cudaMemcpyAsync(d_b[slot], bases + base, nb, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
-                cudaMemcpyAsync(d_o[slot], rel[slot].data(), (nr + 1) * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
+            cudaStreamWaitEvent(cs, ctx->ev_used[slot], 0);  // previous user of this slot is done
+            if (cudaMemcpyAsync(ctx->stage_b[slot], bases + base, nb, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+                cudaMemcpyAsync(ctx->stage_o[slot], rec_off + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
                 rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
             }
-            cudaEventRecord(ev_copied[slot], cs);
-            next = {nb, nr, slot, true};
+            cudaEventRecord(ctx->ev_copied[slot], cs);
+            next = {nb, nr, base, slot, true};
             r0 = r1;
             slot ^= 1;
         }
         if (pend.valid) {
-            cudaStreamWaitEvent(st, ev_copied[pend.slot], 0);
-            rc = b.add(d_b[pend.slot], pend.nb, d_o[pend.slot], pend.nr);
-            cudaEventRecord(ev_used[pend.slot], st);
+            cudaStreamWaitEvent(st, ctx->ev_copied[pend.slot], 0);
+            rc = b.add(ctx->stage_b[pend.slot], pend.nb, ctx->stage_o[pend.slot], pend.bias, pend.nr);
+            cudaEventRecord(ctx->ev_used[pend.slot], st);
             if (rc != SYL_OK) break;
         }
         pend = next;
     }
+    const double t_loop = now() - t_start, t0 = now();
     if (rc == SYL_OK) rc = b.finish(out);
-    cleanup();
+    else { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
+    if (dbg) fprintf(stderr, "[syl_sketch_reads host] chunk loop %.2f ms, finish %.2f ms\n", t_loop, now() - t0);
     return rc;
 }
 
@@ -386,9 +411,9 @@ int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_
     cudaStream_t st = ctx->stream;
     syl_sample *s = new (std::nothrow) syl_sample();
     if (!s) return SYL_ERR_OOM;
-    s->device = ctx->device; s->k = k; s->c = c; s->n = n;
-    SYL_CUDA(cudaMalloc((void **)&s->hash, std::max<uint64_t>(n, 1) * 8));
-    SYL_CUDA(cudaMalloc((void **)&s->count, std::max<uint64_t>(n, 1) * 4));
+    s->device = ctx->device; s->stream = st; s->k = k; s->c = c; s->n = n;
+    SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(n, 1) * 8, st));
+    SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(n, 1) * 4, st));
     if (n) {
         DevBuf<uint64_t> kin;
         DevBuf<uint32_t> vin;
@@ -431,8 +456,9 @@ int syl_sample_device_ptrs(const syl_sample *s, const uint64_t **hash, const uin
 void syl_sample_free(syl_sample *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (s->hash) cudaFree(s->hash);
-    if (s->count) cudaFree(s->count);
+    // stream-ordered free on the creating ctx stream (free samples before destroying their ctx)
+    if (s->hash) cudaFreeAsync(s->hash, s->stream);
+    if (s->count) cudaFreeAsync(s->count, s->stream);
     delete s;
 }
 

@@ -20,6 +20,7 @@
 //   * survivors (1/c of windows) are staged in shared memory and flushed with one global
 //     atomic per CTA
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -41,7 +42,7 @@ struct SeedSmem {
     alignas(128) uint8_t asc[SEED_ASC_BYTES + 16];
     alignas(16) uint32_t fw[SEED_FW_WORDS];
     alignas(16) uint32_t cw[SEED_CW_WORDS];
-    alignas(16) uint8_t lut[256];
+    alignas(16) uint8_t lut[4][256];  // lut[j][b] = BYTE_TO_SEQ[b] << (6 - 2j)
     alignas(8) unsigned long long mbar;
 };
 // views into region A once the ASCII bytes are dead
@@ -57,12 +58,53 @@ struct SeedMeta {
 };
 static_assert(sizeof(SeedMeta) <= SEED_ASC_BYTES, "meta must fit in the dead ASCII region");
 
+// Multipliers 2^(32-s) for the three xor-shift distances, passed as kernel parameters so that
+// ptxas cannot strength-reduce "mul.hi by a power of two" back into an ALU-pipe shift.
+struct ShiftMul { uint32_t m24, m14, m28; };  // = 1<<8, 1<<18, 1<<4
+
+// 64-bit multiply by a 32-bit constant as IMAD.WIDE + IMAD (2 FMA-pipe instructions)
+__device__ __forceinline__ void mul64c(uint32_t lo, uint32_t hi, uint32_t c, uint32_t &plo, uint32_t &phi) {
+    uint64_t t;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(lo), "r"(c));
+    plo = (uint32_t)t;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(phi) : "r"(hi), "r"(c), "r"((uint32_t)(t >> 32)));
+}
+
+// x ^= x >> s on halves. VAR 0: 2 SHF + 2 LOP3 (ALU pipe). VAR 1: the high-word shift is an
+// IMAD.HI (FMA pipe). VAR 2: the funnel shift of the low word also goes to the FMA pipe
+// (IMAD.HI + IMAD). The ALU pipe issues one warp instruction every 2 cycles and is the limiter.
+template <int VAR, int SH>
+__device__ __forceinline__ void xorshift(uint32_t &lo, uint32_t &hi, uint32_t mul, uint32_t extra_hi) {
+    uint32_t sl, sh;
+    if (VAR >= 1) sh = __umulhi(hi, mul); else sh = hi >> SH;
+    if (VAR >= 2) sl = __umulhi(lo, mul) + hi * mul; else sl = __funnelshift_r(lo, hi, SH);
+    lo ^= sl;
+    hi = hi ^ sh ^ extra_hi;
+}
+
+// High 32 bits of mm_hash64 (src/seeding.rs:4-15) on a k-mer given as two 32-bit halves.
+//   * the NOT of step 1 is folded into the first xor-shift: for X = ~x,
+//       (X ^ X>>24).lo = x.lo ^ (x>>24).lo            (the complements cancel)
+//       (X ^ X>>24).hi = x.hi ^ (x.hi>>24) ^ 0xFFFFFF00
+//   * only the high word of the last multiply is formed; survivors re-derive the full hash
+template <int VAR>
+__device__ __forceinline__ uint32_t hash_hi32(uint32_t lo, uint32_t hi, const ShiftMul sm) {
+    uint32_t a, b;
+    mul64c(lo, hi, 0x200001u, a, b);
+    xorshift<VAR, 24>(a, b, sm.m24, 0xFFFFFF00u);
+    mul64c(a, b, 265u, lo, hi);
+    xorshift<VAR, 14>(lo, hi, sm.m14, 0u);
+    mul64c(lo, hi, 21u, a, b);
+    xorshift<VAR, 28>(a, b, sm.m28, 0u);
+    return __umulhi(a, 0x80000001u) + b * 0x80000001u;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
 // tile t -> index of the record that contains flat position t*SEED_TILE
-__global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t n_rec,
+__global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t off_bias, uint64_t n_rec,
                                  uint64_t n_tiles, uint32_t *__restrict__ tile_rec) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
@@ -70,7 +112,7 @@ __global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t 
         tile_rec[t] = (uint32_t)(n_rec - 1);
         return;
     }
-    uint64_t pos = t * (uint64_t)SEED_TILE;
+    uint64_t pos = t * (uint64_t)SEED_TILE + off_bias;
     // upper_bound over rec_off[0..n_rec]: first i with rec_off[i] > pos
     uint64_t lo = 0, hi = n_rec + 1;
     while (lo < hi) {
@@ -82,11 +124,12 @@ __global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t 
     tile_rec[t] = (uint32_t)r;
 }
 
-template <int K>
+template <int K, int VAR>
 __global__ void __launch_bounds__(SEED_THREADS, 4)
-k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__restrict__ rec_off,
+k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__restrict__ rec_off, uint64_t off_bias,
        const uint32_t *__restrict__ tile_rec, uint64_t thr, int sem, int with_pos,
-       syl_survivor *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count) {
+       syl_survivor *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count,
+       const ShiftMul smul) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SeedSmem &S = *reinterpret_cast<SeedSmem *>(smem_raw);
     SeedMeta &M = *reinterpret_cast<SeedMeta *>(S.asc);
@@ -120,7 +163,13 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
     // tail (< 16 bytes) and zero fill of everything past the end of the buffer
     for (uint32_t i = nbulk + tid; i < (uint32_t)SEED_ASC_BYTES + 16; i += SEED_THREADS)
         S.asc[i] = (i < avail) ? bases[T0 + i] : (uint8_t)0;
-    S.lut[tid] = (uint8_t)byte_to_seq((uint32_t)tid);
+    {
+        const uint32_t code = byte_to_seq((uint32_t)tid);
+        S.lut[0][tid] = (uint8_t)(code << 6);
+        S.lut[1][tid] = (uint8_t)(code << 4);
+        S.lut[2][tid] = (uint8_t)(code << 2);
+        S.lut[3][tid] = (uint8_t)code;
+    }
     if (tid < 8) {
         S.fw[SEED_NCHUNK16 + 1 + tid] = 0u;
         S.cw[SEED_NCHUNK16 + tid] = 0u;
@@ -141,18 +190,19 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
     __syncthreads();
 
     // ---- pack: 16 ASCII bytes -> one forward word (MSB-first) + one complement word (LSB-first)
+    // per byte: one PRMT (extract) + one LDS.U8 from the pre-shifted table; per 4 bytes two 3-input ORs
     for (int ch = tid; ch < SEED_NCHUNK16; ch += SEED_THREADS) {
         const uint4 v = *reinterpret_cast<const uint4 *>(S.asc + 16 * ch);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t f = 0;
+        uint32_t g[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                uint32_t byte = (w[q] >> (8 * b)) & 0xFFu;
-                f = (f << 2) | (uint32_t)S.lut[byte];
-            }
+            const uint32_t b0 = __byte_perm(w[q], 0u, 0x4440), b1 = __byte_perm(w[q], 0u, 0x4441);
+            const uint32_t b2 = __byte_perm(w[q], 0u, 0x4442), b3 = __byte_perm(w[q], 0u, 0x4443);
+            g[q] = ((uint32_t)S.lut[0][b0] | (uint32_t)S.lut[1][b1] | (uint32_t)S.lut[2][b2]) | (uint32_t)S.lut[3][b3];
         }
+        const uint32_t lo16 = __byte_perm(g[3], g[2], 0x0040), hi16 = __byte_perm(g[1], g[0], 0x0040);
+        const uint32_t f = __byte_perm(lo16, hi16, 0x5410);
         // complement stream: base j's (3 - code) at bits [2j, 2j+2): reverse the 16 fields of f
         uint32_t x = __brev(f);                                        // fields reversed, bits swapped in each
         x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);       // swap bits back inside each field
@@ -172,7 +222,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
         int runs = 0;
         const uint64_t r = rc + tid;
         if (r <= (uint64_t)r_hi) {
-            const uint64_t a = rec_off[r], b = rec_off[r + 1];
+            const uint64_t a = rec_off[r] - off_bias, b = rec_off[r + 1] - off_bias;
             const uint64_t L = b - a;
             const uint64_t nv = valid_windows(L, (uint32_t)K, sem, with_pos);
             const uint64_t lo = a > T0 ? a : T0;
@@ -237,31 +287,45 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
                 G[2] = __funnelshift_r(c2, c3, csh);
                 G[3] = __funnelshift_r(c3, c4, csh);
             }
+            // hot loop: high word of the hash only; candidates (1/c of windows) are collected in a
+            // bit mask and re-derived exactly afterwards, so the loop has no divergent code
+            uint32_t cand = 0u;
 #pragma unroll
             for (int i = 0; i < SEED_W; i++) {
                 const int jb = (2 * i) >> 5;
-                const uint32_t s = (uint32_t)((2 * i) & 31);
-                const uint32_t f_hi = __funnelshift_l(F[jb + 1], F[jb], s) & HI_MASK;
-                const uint32_t f_lo = __funnelshift_l(F[jb + 2], F[jb + 1], s);
-                const uint32_t r_lo32 = __funnelshift_r(G[jb], G[jb + 1], s);
-                const uint32_t r_hi32 = __funnelshift_r(G[jb + 1], G[jb + 2], s) & HI_MASK;
-                const uint64_t f = ((uint64_t)f_hi << 32) | f_lo;
-                const uint64_t rr = ((uint64_t)r_hi32 << 32) | r_lo32;
+                const uint32_t sft = (uint32_t)((2 * i) & 31);
+                const uint32_t f_hi = __funnelshift_l(F[jb + 1], F[jb], sft) & HI_MASK;
+                const uint32_t f_lo = __funnelshift_l(F[jb + 2], F[jb + 1], sft);
+                const uint32_t r_lo = __funnelshift_r(G[jb], G[jb + 1], sft);
+                const uint32_t r_hi = __funnelshift_r(G[jb + 1], G[jb + 2], sft) & HI_MASK;
+                const uint64_t f = ((uint64_t)f_hi << 32) | f_lo, rr = ((uint64_t)r_hi << 32) | r_lo;
                 const uint64_t canon = f < rr ? f : rr;  // src/seeding.rs:131-136
-                const uint64_t h = mm_hash64(canon);
-                if ((uint32_t)(h >> 32) <= thr_hi) {      // cheap pre-test on the high word
-                    if (h < thr && i < n) {               // src/seeding.rs:139
-                        syl_survivor sv;
-                        sv.hash = h;
-                        sv.rec = rec;
-                        sv.pos = pos0 + (uint32_t)i;
-                        const unsigned int idx = atomicAdd(&M.stage_count, 1u);
-                        if (idx < (unsigned)SEED_STAGE) {
-                            M.stage[idx] = sv;
-                        } else {
-                            const unsigned long long g = atomicAdd(g_count, 1ull);
-                            if (g < cap) out[g] = sv;
-                        }
+                const uint32_t hh = hash_hi32<VAR>((uint32_t)canon, (uint32_t)(canon >> 32), smul);
+                asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                    : "+r"(cand) : "r"(hh), "r"(thr_hi), "r"(1u << i));
+            }
+            while (cand) {
+                const int i = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                if (i >= n) continue;
+                const uint32_t sft = (uint32_t)((2 * i) & 31);
+                const bool up = (2 * i) >= 32;
+                const uint32_t A0 = up ? F[1] : F[0], A1 = up ? F[2] : F[1], A2 = up ? F[3] : F[2];
+                const uint32_t B0 = up ? G[1] : G[0], B1 = up ? G[2] : G[1], B2 = up ? G[3] : G[2];
+                const uint64_t f = ((uint64_t)(__funnelshift_l(A1, A0, sft) & HI_MASK) << 32) | __funnelshift_l(A2, A1, sft);
+                const uint64_t rr = ((uint64_t)(__funnelshift_r(B1, B2, sft) & HI_MASK) << 32) | __funnelshift_r(B0, B1, sft);
+                const uint64_t h = mm_hash64(f < rr ? f : rr);
+                if (h < thr) {  // src/seeding.rs:139
+                    syl_survivor sv;
+                    sv.hash = h;
+                    sv.rec = rec;
+                    sv.pos = pos0 + (uint32_t)i;
+                    const unsigned int idx = atomicAdd(&M.stage_count, 1u);
+                    if (idx < (unsigned)SEED_STAGE) {
+                        M.stage[idx] = sv;
+                    } else {
+                        const unsigned long long gi = atomicAdd(g_count, 1ull);
+                        if (gi < cap) out[gi] = sv;
                     }
                 }
             }
@@ -283,7 +347,9 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
 
 // Host launcher: device-resident inputs, survivors to a device buffer. *n_out is the true
 // number of survivors even when it exceeds cap (then SYL_ERR_CAPACITY).
-int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off,
+// d_rec_off[i] - off_bias is the start of record i inside d_bases (off_bias lets a caller pass a
+// slice of a larger offset array unchanged).
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                 uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
                 uint64_t cap, uint64_t *n_out) {
     *n_out = 0;
@@ -306,21 +372,40 @@ int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const ui
     {
         const int bs = 256;
         const uint64_t nb = (n_tiles + 1 + bs - 1) / bs;
-        k_tile_first_rec<<<(unsigned)nb, bs, 0, st>>>(d_rec_off, n_rec, n_tiles, tile_rec.p);
+        k_tile_first_rec<<<(unsigned)nb, bs, 0, st>>>(d_rec_off, off_bias, n_rec, n_tiles, tile_rec.p);
         ctx->launches++;
     }
     SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint64_t), st));
     const uint64_t thr = fmh_threshold(c);
     const size_t smem = sizeof(SeedSmem);
-    auto kern = (k == 31) ? k_seed<31> : k_seed<21>;
+    static const int variant = []() {
+        const char *e = getenv("SYL_SEED_VARIANT");  // tuning knob: which pipe the xor-shifts use
+        int v = e ? atoi(e) : 0;
+        return v < 0 ? 0 : (v > 2 ? 2 : v);
+    }();
+    using kern_t = void (*)(const uint8_t *, uint64_t, const uint64_t *, uint64_t, const uint32_t *, uint64_t, int, int,
+                            syl_survivor *, uint64_t, unsigned long long *, const ShiftMul);
+    static const kern_t table[2][3] = {{k_seed<31, 0>, k_seed<31, 1>, k_seed<31, 2>},
+                                       {k_seed<21, 0>, k_seed<21, 1>, k_seed<21, 2>}};
+    kern_t kern = table[k == 31 ? 0 : 1][variant];
+    const ShiftMul smul = {1u << 8, 1u << 18, 1u << 4};
     SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev0, st));
     kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
-        d_bases, n_bases, d_rec_off, tile_rec.p, thr, sem, with_pos, d_out, cap,
-        reinterpret_cast<unsigned long long *>(ctx->d_counters));
+        d_bases, n_bases, d_rec_off, off_bias, tile_rec.p, thr, sem, with_pos, d_out, cap,
+        reinterpret_cast<unsigned long long *>(ctx->d_counters), smul);
+    if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev1, st));
     ctx->launches++;
     SYL_CUDA(cudaGetLastError());
     SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SYL_CUDA(cudaStreamSynchronize(st));
+    if (ctx->timing) {
+        float ms = 0.f;
+        SYL_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->seed_ms += ms;
+        ctx->seed_launches++;
+        ctx->seed_bases += n_bases;
+    }
     *n_out = ctx->h_counters[0];
     if (*n_out > cap) {
         set_error("survivor buffer too small");
