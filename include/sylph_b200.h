@@ -142,6 +142,9 @@ int syl_genomes_upload(syl_ctx *ctx, int mem, const uint64_t *kmers, const uint6
 /* Concatenate batches (database build in chunks): genome i of part p becomes genome
  * (sum of earlier parts' counts) + i.  All parts must agree on k, c and has_tracked. */
 int syl_genomes_concat(syl_ctx *ctx, const syl_genomes *const *parts, uint32_t n_parts, syl_genomes **out);
+/* New batch holding genomes idx[0..n) of g (host index array), e.g. the pass-1 survivors of a
+ * shard that are gathered into a small survivor database for the multi-GPU profile. */
+int syl_genomes_select(syl_ctx *ctx, const syl_genomes *g, const uint32_t *idx, uint32_t n, syl_genomes **out);
 uint64_t syl_genomes_count(const syl_genomes *g);
 uint64_t syl_genomes_total_kmers(const syl_genomes *g);
 uint64_t syl_genomes_total_tracked(const syl_genomes *g);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "syl_sketch_genomes": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _vp, _u64, _i, _u64, _u64, _i, _i, _i, _pp]),
     "syl_genomes_upload": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _u64, _i, _u64, _pp]),
     "syl_genomes_concat": (_i, [_vp, _pp, _u32, _pp]),
+    "syl_genomes_select": (_i, [_vp, _vp, _vp, _u32, _pp]),
     "syl_genomes_count": (_u64, [_vp]),
     "syl_genomes_total_kmers": (_u64, [_vp]),
     "syl_genomes_total_tracked": (_u64, [_vp]),

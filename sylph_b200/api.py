@@ -27,6 +27,9 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+_CTX_STREAM = [0]  # stream of the Context currently issuing a call (set by Context._enter)
+
+
 def _arg(x, dtype):
     """-> (mem, pointer, n, keepalive)"""
     if x is None:
@@ -36,6 +39,11 @@ def _arg(x, dtype):
             x = x.numpy()
         else:
             import torch
+            # a producer on torch's current stream must be finished before the library's stream reads
+            # the tensor, unless the Context was created on that very stream
+            cur = torch.cuda.current_stream(x.device)
+            if cur.cuda_stream != _CTX_STREAM[0]:
+                cur.synchronize()
             want = {np.uint8: torch.uint8, np.uint64: torch.int64, np.uint32: torch.int32}[dtype]
             if x.dtype not in (want, getattr(torch, np.dtype(dtype).name, want)):
                 raise TypeError("expected tensor of %s-compatible dtype, got %s" % (np.dtype(dtype).name, x.dtype))
@@ -54,6 +62,7 @@ class Context:
         L = _lib.lib()
         _lib.check(L.syl_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.device = device
+        self._stream = int(stream) if stream else -1
 
     def close(self):
         if self._h:
@@ -89,6 +98,7 @@ class Context:
         """Batched extract_markers / extract_markers_positions (src/sketch.rs:53-93).
         Returns a numpy structured array (hash, rec, pos) in unspecified order, or — when `out`
         is a torch CUDA tensor of >= cap*16 bytes — the survivor count (survivors stay on device)."""
+        _CTX_STREAM[0] = self._stream
         L = _lib.lib()
         mem_b, pb, nb, kb = _arg(bases, np.uint8)
         mem_o, po, no, ko = _arg(rec_off, np.uint64)
@@ -126,6 +136,7 @@ class Context:
     # ---- (2) sample sketch -------------------------------------------------------------------
     def sketch_sequences(self, bases, rec_off, k=31, c=200, no_dedup=False, sem=SEM_AVX2):
         """Batched body of sketch_sequences_needle (src/sketch.rs:897-959) -> Sample."""
+        _CTX_STREAM[0] = self._stream
         L = _lib.lib()
         mem_b, pb, nb, kb = _arg(bases, np.uint8)
         mem_o, po, no, ko = _arg(rec_off, np.uint64)
@@ -136,6 +147,7 @@ class Context:
         return Sample(self, h)
 
     def upload_sample(self, hashes, counts, k=31, c=200):
+        _CTX_STREAM[0] = self._stream
         L = _lib.lib()
         mem_h, ph, nh, kh = _arg(hashes, np.uint64)
         mem_c, pc, nc, kc = _arg(counts, np.uint32)
@@ -148,6 +160,7 @@ class Context:
     def sketch_genomes(self, bases, contig_off, genome_off=None, k=31, c=200, min_spacing=30, pseudotax=True,
                        individual=False, sem=SEM_AVX2):
         """Batched sketch_genome / sketch_genome_individual (src/sketch.rs:550-622, 481-548)."""
+        _CTX_STREAM[0] = self._stream
         L = _lib.lib()
         mem_b, pb, nb, kb = _arg(bases, np.uint8)
         mem_o, po, no, ko = _arg(contig_off, np.uint64)
@@ -163,6 +176,7 @@ class Context:
         return Genomes(self, h)
 
     def upload_genomes(self, kmers, kmer_off, tracked=None, tracked_off=None, gn_size=None, k=31, c=200):
+        _CTX_STREAM[0] = self._stream
         L = _lib.lib()
         mem, pk, nk, k1 = _arg(kmers, np.uint64)
         _, pko, nko, k2 = _arg(kmer_off, np.uint64)
@@ -177,6 +191,12 @@ class Context:
         arr = (C.c_void_p * max(len(parts), 1))(*[p._h for p in parts])
         h = C.c_void_p()
         _lib.check(_lib.lib().syl_genomes_concat(self._h, arr, len(parts), C.byref(h)))
+        return Genomes(self, h)
+
+    def select_genomes(self, genomes, idx):
+        a = np.ascontiguousarray(idx, dtype=np.uint32)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().syl_genomes_select(self._h, genomes._h, a.ctypes.data_as(C.c_void_p), len(a), C.byref(h)))
         return Genomes(self, h)
 
     # ---- (4) containment ---------------------------------------------------------------------

@@ -1,0 +1,117 @@
+"""Multi-GPU host logic: one process per GPU over torch.distributed (NCCL on GPUs, gloo in the
+CPU tests).  The path shards naturally:
+
+  sketching : independent samples / genome batches per rank, no collective
+  query     : db sharded by genome (syl_db_build(genome_base=...)), samples replicated, every rank
+              emits its rows; ONE all-gather of the row tables at the end (the only collective)
+  profile   : pass 1 per shard; the pass-1 survivors (10^1-10^3 genomes) are gathered into a small
+              survivor db on every rank; the exact two-pass profile of sample s then runs on rank
+              s % world and the rows are all-gathered
+
+torch is plumbing here (process group, collectives); all compute goes through the C ABI.
+"""
+import numpy as np
+
+from .api import ANI_ROW_DTYPE, contain_params
+
+
+def shard_range(n, rank, world):
+    """Contiguous split of n units: -> (begin, end) of `rank`."""
+    base, rem = divmod(n, world)
+    b = rank * base + min(rank, rem)
+    return b, b + base + (1 if rank < rem else 0)
+
+
+def _dev():
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def all_gather_bytes(arr):
+    """All-gather variable-length numpy arrays (any dtype): -> list of per-rank arrays (same dtype).
+    Two collectives: sizes, then the payload padded to the largest size."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [arr]
+    world, dev = dist.get_world_size(), _dev()
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    n = torch.tensor([raw.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(max(sizes), 1)
+    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    if raw.size:
+        buf[: raw.size] = torch.from_numpy(raw.copy()).to(dev)
+    out = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return [o[:s].cpu().numpy().view(arr.dtype) for o, s in zip(out, sizes)]
+
+
+def merge_rows(parts):
+    """Concatenate per-rank row tables and order them by (sample, genome) like a single-GPU syl_query."""
+    parts = [p for p in parts if len(p)]
+    if not parts:
+        return np.zeros(0, dtype=ANI_ROW_DTYPE)
+    rows = np.concatenate(parts)
+    order = np.lexsort((rows["genome"], rows["sample"]))
+    return rows[order]
+
+
+def query_sharded(ctx, db, samples, params=None):
+    """`sylph query` over a genome-sharded db: local syl_query + one all-gather of the rows."""
+    params = params or contain_params(pseudotax=False)
+    local = ctx.query(db, samples, params)
+    return merge_rows(all_gather_bytes(local))
+
+
+def gather_survivor_genomes(sub, global_ids):
+    """sub: dict from Genomes.download() of this rank's pass-1 survivors, global_ids: their global
+    genome ids. -> (merged dict, merged global ids) identical on every rank (rank order)."""
+    keys = ("kmers", "kmer_off", "tracked", "tracked_off", "gn_size")
+    parts = {k: all_gather_bytes(np.ascontiguousarray(sub[k], dtype=np.uint64)) for k in keys}
+    ids = all_gather_bytes(np.ascontiguousarray(global_ids, dtype=np.uint64))
+    out = {"kmers": np.concatenate(parts["kmers"]), "tracked": np.concatenate(parts["tracked"]),
+           "gn_size": np.concatenate(parts["gn_size"])}
+    for name in ("kmer_off", "tracked_off"):
+        offs, base = [np.zeros(1, dtype=np.uint64)], 0
+        for p in parts[name]:
+            offs.append(p[1:] + np.uint64(base))
+            base += int(p[-1]) if len(p) else 0
+        out[name] = np.concatenate(offs)
+    return out, np.concatenate(ids)
+
+
+def profile_sharded(ctx, genomes, db, samples, genome_base, params=None):
+    """`sylph profile` over a genome-sharded db (see module docstring). Returns all rows on every rank,
+    per sample sorted by rel_abund descending; row.genome is the GLOBAL genome id."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    params = params or contain_params(pseudotax=True)
+    params.pseudotax = 1
+    rows1 = ctx.query(db, samples, params)                      # pass 1 on the shard (profile ANI gate)
+    local_ids = np.unique(rows1["genome"].astype(np.int64) - int(genome_base)).astype(np.uint32)
+    sub = ctx.select_genomes(genomes, local_ids)
+    merged, gids = gather_survivor_genomes(sub.download(), local_ids.astype(np.uint64) + np.uint64(genome_base))
+    sub.free()
+    out = np.zeros(0, dtype=ANI_ROW_DTYPE)
+    if len(gids):
+        g = ctx.upload_genomes(merged["kmers"], merged["kmer_off"], merged["tracked"], merged["tracked_off"],
+                               merged["gn_size"], k=params.k)
+        sdb = ctx.build_db(g)
+        mine = [i for i in range(len(samples)) if i % world == rank]
+        if mine:
+            out = ctx.profile(sdb, [samples[i] for i in mine], params)
+            out["sample"] = np.array(mine, dtype=np.uint32)[out["sample"]]
+            out["genome"] = gids[out["genome"]].astype(np.uint32)
+        sdb.free()
+        g.free()
+    parts = [p for p in all_gather_bytes(out) if len(p)]
+    if not parts:
+        return np.zeros(0, dtype=ANI_ROW_DTYPE)
+    rows = np.concatenate(parts)
+    order = np.lexsort((-rows["rel_abund"], rows["sample"]))  # stable: per sample by abundance desc
+    return rows[order]

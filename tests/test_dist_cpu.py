@@ -1,0 +1,79 @@
+"""CPU suite: the N>1 host logic (sharding, variable-length all-gather, row merge, survivor-db
+gather) over gloo with world_size 2.  Compute kernels are not involved (no GPU here)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sylph_b200 import dist as D
+    from sylph_b200.api import ANI_ROW_DTYPE
+    try:
+        # 1. variable-length all-gather (rank r contributes r*3+1 rows; rank 1 of 2 also tests empty->nonempty mix)
+        rows = np.zeros(rank * 3 + (0 if rank == 0 else 1), dtype=ANI_ROW_DTYPE)
+        rows["sample"] = np.arange(len(rows)) % 2
+        rows["genome"] = 1000 * rank + np.arange(len(rows))[::-1]
+        rows["final_est_ani"] = 0.9 + 0.01 * rank
+        parts = D.all_gather_bytes(rows)
+        assert [len(p) for p in parts] == [r * 3 + (0 if r == 0 else 1) for r in range(world)]
+        merged = D.merge_rows(parts)
+        key = list(zip(merged["sample"].tolist(), merged["genome"].tolist()))
+        assert key == sorted(key) and len(merged) == sum(len(p) for p in parts)
+        # 2. survivor-db gather: each rank owns 2 genomes with rank-dependent sizes
+        nk = [3 + rank, 1 + 2 * rank]
+        sub = {"kmers": np.arange(sum(nk), dtype=np.uint64) + 100 * rank,
+               "kmer_off": np.array([0, nk[0], sum(nk)], dtype=np.uint64),
+               "tracked": np.arange(rank + 1, dtype=np.uint64) + 7000 * rank,
+               "tracked_off": np.array([0, rank + 1, rank + 1], dtype=np.uint64),
+               "gn_size": np.array([10 + rank, 20 + rank], dtype=np.uint64)}
+        gid = np.array([50 * rank + 1, 50 * rank + 9], dtype=np.uint64)
+        m, ids = D.gather_survivor_genomes(sub, gid)
+        assert ids.tolist() == [1, 9, 51, 59]
+        assert m["kmer_off"].tolist() == [0, 3, 4, 8, 11]
+        assert m["tracked_off"].tolist() == [0, 1, 1, 3, 3]
+        assert m["kmers"].tolist() == [0, 1, 2, 3, 100, 101, 102, 103, 104, 105, 106]
+        assert m["gn_size"].tolist() == [10, 20, 11, 21]
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range():
+    from sylph_b200.dist import shard_range
+    for n in (0, 1, 7, 8, 100000, 113104):
+        for w in (1, 2, 3, 8):
+            r = [shard_range(n, i, w) for i in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_gloo_world2_gather_and_merge():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
