@@ -34,56 +34,70 @@ constexpr uint64_t NO_PAIR = 1ull;  // bit 0 of recflag set => the read has no p
 
 // pair_kmer_single (src/sketch.rs:624-656): four 16-base keys sampled at even/odd offsets from
 // the read start and from the middle.  len > 400 (src/sketch.rs:923) or len < 66 (:627) => None.
-// Warp-cooperative: a warp owns 32 survivors; for each of them the 32 lanes fetch the 32 bytes a
-// key is drawn from with ONE coalesced byte load per lane and assemble the 32-bit key with one
-// ballot: lane l supplies bit l of the key, i.e. one bit of the 2-bit code of base
-// 2*((31-l)>>1) (+1 for the odd keys), so no per-thread byte gathers are needed.
-constexpr int EV_THREADS = 256;
+// One thread per survivor: the 32 bytes a key pair is drawn from are fetched as nine aligned
+// 32-bit words and realigned with funnel shifts; even / odd bytes are separated with PRMT and
+// mapped through four pre-shifted copies of the exact BYTE_TO_SEQ table in shared memory.
+constexpr int EV_THREADS = 128;
+
+__device__ __forceinline__ void load32_unaligned(const uint8_t *p, uint32_t x[8]) {
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(ad & 3u) * 8u;
+    uint32_t v[9];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __ldg(w + i);
+    v[8] = sh ? __ldg(w + 8) : 0u;  // an aligned word holding a valid byte never leaves the buffer's last word
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = __funnelshift_r(v[i], v[i + 1], sh);
+}
+
+// 16 bytes picked by `sel` (0x6420 = even, 0x7531 = odd) out of 32 -> 16 two-bit codes, MSB-first
+__device__ __forceinline__ uint32_t pack16(const uint32_t x[8], uint32_t sel, const uint8_t (*lut)[256]) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const uint32_t e = __byte_perm(x[2 * m], x[2 * m + 1], sel);
+        const uint32_t g = ((uint32_t)lut[0][e & 0xFFu] | (uint32_t)lut[1][(e >> 8) & 0xFFu] |
+                            (uint32_t)lut[2][(e >> 16) & 0xFFu]) | (uint32_t)lut[3][e >> 24];
+        out = (out << 8) | g;
+    }
+    return out;
+}
+
 __global__ void __launch_bounds__(EV_THREADS)
 k_events(const syl_survivor *__restrict__ sv, uint64_t n, const uint8_t *__restrict__ bases,
          const uint64_t *__restrict__ rec_off, uint64_t off_bias, uint64_t rec_base, int no_dedup,
          uint64_t *__restrict__ hash, uint64_t *__restrict__ recflag,
          uint64_t *__restrict__ p0, uint64_t *__restrict__ p1) {
-    __shared__ uint8_t lut[256];
-    for (int i = threadIdx.x; i < 256; i += EV_THREADS) lut[i] = (uint8_t)byte_to_seq((uint32_t)i);
+    __shared__ uint8_t lut[4][256];
+    for (int i = threadIdx.x; i < 256; i += EV_THREADS) {
+        const uint32_t code = byte_to_seq((uint32_t)i);
+        lut[0][i] = (uint8_t)(code << 6);
+        lut[1][i] = (uint8_t)(code << 4);
+        lut[2][i] = (uint8_t)(code << 2);
+        lut[3][i] = (uint8_t)code;
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = ((uint64_t)blockIdx.x * EV_THREADS + threadIdx.x) >> 5;
-    const uint64_t base_i = warp * 32;
-    if (base_i >= n) return;
-    const uint64_t i = base_i + lane;
-    uint64_t a = 0, L = 0;
-    bool has_pair = false;
-    if (i < n) {
-        const syl_survivor s = sv[i];
-        hash[i] = s.hash;
-        a = rec_off[s.rec] - off_bias;
-        L = rec_off[s.rec + 1] - off_bias - a;
-        has_pair = !no_dedup && L <= 400 && L >= 66;
-        recflag[i] = ((rec_base + s.rec) << 1) | (has_pair ? 0ull : NO_PAIR);
-    }
-    const uint32_t fld = (uint32_t)(31 - lane) >> 1;       // which of the 16 bases this lane's bit belongs to
-    const uint32_t bit = ((31 - lane) & 1) ? 0u : 1u;      // low or high bit of its 2-bit code
+    const uint64_t i = (uint64_t)blockIdx.x * EV_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const syl_survivor s = sv[i];
+    hash[i] = s.hash;
+    const uint64_t a = rec_off[s.rec] - off_bias;
+    const uint64_t L = rec_off[s.rec + 1] - off_bias - a;
+    const bool has_pair = !no_dedup && L <= 400 && L >= 66;
+    recflag[i] = ((rec_base + s.rec) << 1) | (has_pair ? 0ull : NO_PAIR);
     uint64_t k0 = 0, k1 = 0;
-    const unsigned todo = __ballot_sync(0xffffffffu, has_pair);
-    for (unsigned m = todo; m; m &= m - 1) {
-        const int j = __ffs(m) - 1;
-        const uint64_t aj = __shfl_sync(0xffffffffu, a, j);
-        const uint64_t half = __shfl_sync(0xffffffffu, L, j) >> 1;
-        const uint8_t *p = bases + aj + 2 * fld;
-        const uint32_t f = __ballot_sync(0xffffffffu, (lut[p[0]] >> bit) & 1u);
-        const uint32_t r = __ballot_sync(0xffffffffu, (lut[p[half]] >> bit) & 1u);
-        const uint32_t g = __ballot_sync(0xffffffffu, (lut[p[1]] >> bit) & 1u);
-        const uint32_t t = __ballot_sync(0xffffffffu, (lut[p[1 + half]] >> bit) & 1u);
-        if (lane == j) {
-            k0 = ((uint64_t)f << 32) | r;  // doublepairs.0 = [kmer_f, kmer_r]
-            k1 = ((uint64_t)g << 32) | t;  // doublepairs.1 = [kmer_g, kmer_t]
-        }
+    if (has_pair) {
+        uint32_t x[8];
+        load32_unaligned(bases + a, x);
+        const uint32_t f = pack16(x, 0x6420, lut), g = pack16(x, 0x7531, lut);
+        load32_unaligned(bases + a + L / 2, x);
+        const uint32_t r = pack16(x, 0x6420, lut), t = pack16(x, 0x7531, lut);
+        k0 = ((uint64_t)f << 32) | r;  // doublepairs.0 = [kmer_f, kmer_r]
+        k1 = ((uint64_t)g << 32) | t;  // doublepairs.1 = [kmer_g, kmer_t]
     }
-    if (i < n) {
-        p0[i] = k0;
-        p1[i] = k1;
-    }
+    p0[i] = k0;
+    p1[i] = k1;
 }
 
 __global__ void k_iota(uint32_t *idx, uint64_t n) {

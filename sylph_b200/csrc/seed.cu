@@ -31,6 +31,10 @@ constexpr int SEED_TILE = 32768;   // window-start positions (== bases) per CTA
 constexpr int SEED_W = 32;         // windows per thread-run
 constexpr int SEED_HALO = 48;      // bytes staged past the tile (>= k-1, multiple of 16)
 constexpr int SEED_STAGE = 512;    // survivors staged per CTA before falling back to global atomics
+constexpr int SEED_CAND = 1024;    // candidate windows buffered per record chunk (overflow is handled inline)
+constexpr int SEED_RUNS_PER_THREAD = 5;
+constexpr int SEED_MAXRUNS = SEED_THREADS * SEED_RUNS_PER_THREAD;  // >= SEED_TILE / SEED_W + SEED_THREADS
+static_assert(SEED_MAXRUNS >= SEED_TILE / SEED_W + SEED_THREADS, "run table too small");
 constexpr int SEED_ASC_BYTES = SEED_TILE + SEED_HALO;  // 32816, multiple of 16
 constexpr int SEED_NCHUNK16 = SEED_ASC_BYTES / 16;     // 2051 16-base words per stream
 constexpr int SEED_FW_WORDS = SEED_NCHUNK16 + 1 + 8;   // +1 leading pad word, +8 slack for run loads
@@ -53,8 +57,11 @@ struct SeedMeta {
     int rbase[SEED_THREADS + 1];      // exclusive scan of ceil(cnt / SEED_W)
     int warp_tot[SEED_THREADS / 32];
     unsigned int stage_count;
+    unsigned int cand_count;
     unsigned long long flush_base;
     alignas(16) syl_survivor stage[SEED_STAGE];
+    uint32_t cand[SEED_CAND];          // (tile-relative window start << 8) | record slot
+    uint16_t run_rec[SEED_MAXRUNS];    // run -> record slot + 1 (filled by a max-scan over run starts)
 };
 static_assert(sizeof(SeedMeta) <= SEED_ASC_BYTES, "meta must fit in the dead ASCII region");
 
@@ -122,6 +129,37 @@ __global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t 
     uint64_t r = lo == 0 ? 0 : lo - 1;
     if (r >= n_rec) r = n_rec - 1;
     tile_rec[t] = (uint32_t)r;
+}
+
+// Exact re-derivation of one candidate window: k-mer halves from the packed streams at an arbitrary
+// position, full 64-bit hash, threshold test, survivor staged in shared memory.
+template <int K>
+__device__ __forceinline__ void seed_resolve(const SeedSmem &S, SeedMeta &M, uint32_t pw, int j, uint64_t rc, uint64_t thr,
+                                             syl_survivor *__restrict__ out, uint64_t cap,
+                                             unsigned long long *__restrict__ g_count) {
+    constexpr uint32_t PAD = 64 - 2 * K;
+    constexpr uint32_t HI_MASK = (1u << (32 - PAD)) - 1u;
+    const uint32_t bitpos = 32u + 2u * pw - PAD;
+    const uint32_t q0 = bitpos >> 5, sh = bitpos & 31u;
+    const uint32_t w0 = S.fw[q0], w1 = S.fw[q0 + 1], w2 = S.fw[q0 + 2];
+    const uint64_t f = ((uint64_t)(__funnelshift_l(w1, w0, sh) & HI_MASK) << 32) | __funnelshift_l(w2, w1, sh);
+    const uint32_t cq = pw >> 4, csh = (pw & 15u) * 2u;
+    const uint32_t c0 = S.cw[cq], c1 = S.cw[cq + 1], c2 = S.cw[cq + 2];
+    const uint64_t rr = ((uint64_t)(__funnelshift_r(c1, c2, csh) & HI_MASK) << 32) | __funnelshift_r(c0, c1, csh);
+    const uint64_t h = mm_hash64(f < rr ? f : rr);  // src/seeding.rs:131-137
+    if (h < thr) {                                  // src/seeding.rs:139
+        syl_survivor sv;
+        sv.hash = h;
+        sv.rec = (uint32_t)(rc + (uint64_t)j);
+        sv.pos = (uint32_t)((long long)pw - M.rel[j] + (K - 1));
+        const unsigned int idx = atomicAdd(&M.stage_count, 1u);
+        if (idx < (unsigned)SEED_STAGE) {
+            M.stage[idx] = sv;
+        } else {
+            const unsigned long long gi = atomicAdd(g_count, 1ull);
+            if (gi < cap) out[gi] = sv;
+        }
+    }
 }
 
 template <int K, int VAR>
@@ -250,23 +288,44 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
         if (tid == SEED_THREADS - 1) M.rbase[SEED_THREADS] = wbase + incl;
         __syncthreads();
         const int total = M.rbase[SEED_THREADS];
-        const uint64_t nrec_left = (uint64_t)r_hi - rc + 1;
-        const int nrec = nrec_left < (uint64_t)SEED_THREADS ? (int)nrec_left : SEED_THREADS;
+
+        // -- run -> record table: every record with runs marks its first run with (slot + 1); an
+        //    inclusive max-scan then spreads the marker over the record's runs (markers increase
+        //    with the run index), so a thread finds its record with one byte load instead of a
+        //    binary search per run.
+        {
+            const int base5 = tid * SEED_RUNS_PER_THREAD;
+#pragma unroll
+            for (int e = 0; e < SEED_RUNS_PER_THREAD; e++) M.run_rec[base5 + e] = 0;
+            __syncthreads();
+            if (runs > 0) M.run_rec[M.rbase[tid]] = (uint16_t)(tid + 1);
+            __syncthreads();
+            int v[SEED_RUNS_PER_THREAD], m = 0;
+#pragma unroll
+            for (int e = 0; e < SEED_RUNS_PER_THREAD; e++) { m = max(m, (int)M.run_rec[base5 + e]); v[e] = m; }
+            int inc = m;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) inc = max(inc, __shfl_up_sync(0xffffffffu, inc, d));
+            int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) excl = 0;
+            if (lane == 31) M.warp_tot[wid] = inc;
+            __syncthreads();
+            int wmax = 0;
+#pragma unroll
+            for (int w = 0; w < SEED_THREADS / 32; w++) wmax = max(wmax, (w < wid) ? M.warp_tot[w] : 0);
+            const int pre = max(excl, wmax);
+#pragma unroll
+            for (int e = 0; e < SEED_RUNS_PER_THREAD; e++) M.run_rec[base5 + e] = (uint16_t)max(v[e], pre);
+            if (tid == 0) M.cand_count = 0u;
+            __syncthreads();
+        }
 
         // -- one run of <= SEED_W windows per thread per pass
         for (int q = tid; q < total; q += SEED_THREADS) {
-            // largest j in [0,nrec) with rbase[j] <= q
-            int jlo = 0, jhi = nrec;
-            while (jhi - jlo > 1) {
-                int mid = (jlo + jhi) >> 1;
-                if (M.rbase[mid] <= q) jlo = mid; else jhi = mid;
-            }
-            const int j = jlo;
+            const int j = (int)M.run_rec[q] - 1;
             const int ridx = q - M.rbase[j];
             const int p = M.s0[j] + ridx * SEED_W;            // tile-relative first window start
             const int n = min(SEED_W, M.cnt[j] - ridx * SEED_W);
-            const uint32_t rec = (uint32_t)(rc + j);
-            const uint32_t pos0 = (uint32_t)((long long)p - M.rel[j] + (K - 1));
 
             // realign the two streams so that window i of this run starts at bit 2i
             uint32_t F[4], G[4];
@@ -288,7 +347,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
                 G[3] = __funnelshift_r(c3, c4, csh);
             }
             // hot loop: high word of the hash only; candidates (1/c of windows) are collected in a
-            // bit mask and re-derived exactly afterwards, so the loop has no divergent code
+            // bit mask, so the loop has no divergent code
             uint32_t cand = 0u;
 #pragma unroll
             for (int i = 0; i < SEED_W; i++) {
@@ -304,30 +363,25 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
                 asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
                     : "+r"(cand) : "r"(hh), "r"(thr_hi), "r"(1u << i));
             }
+            if (n < SEED_W) cand &= (1u << n) - 1u;  // n >= 1
+            // candidates go to a CTA-wide list and are re-derived exactly by all threads afterwards
             while (cand) {
                 const int i = __ffs(cand) - 1;
                 cand &= cand - 1u;
-                if (i >= n) continue;
-                const uint32_t sft = (uint32_t)((2 * i) & 31);
-                const bool up = (2 * i) >= 32;
-                const uint32_t A0 = up ? F[1] : F[0], A1 = up ? F[2] : F[1], A2 = up ? F[3] : F[2];
-                const uint32_t B0 = up ? G[1] : G[0], B1 = up ? G[2] : G[1], B2 = up ? G[3] : G[2];
-                const uint64_t f = ((uint64_t)(__funnelshift_l(A1, A0, sft) & HI_MASK) << 32) | __funnelshift_l(A2, A1, sft);
-                const uint64_t rr = ((uint64_t)(__funnelshift_r(B1, B2, sft) & HI_MASK) << 32) | __funnelshift_r(B0, B1, sft);
-                const uint64_t h = mm_hash64(f < rr ? f : rr);
-                if (h < thr) {  // src/seeding.rs:139
-                    syl_survivor sv;
-                    sv.hash = h;
-                    sv.rec = rec;
-                    sv.pos = pos0 + (uint32_t)i;
-                    const unsigned int idx = atomicAdd(&M.stage_count, 1u);
-                    if (idx < (unsigned)SEED_STAGE) {
-                        M.stage[idx] = sv;
-                    } else {
-                        const unsigned long long gi = atomicAdd(g_count, 1ull);
-                        if (gi < cap) out[gi] = sv;
-                    }
+                const unsigned int ci = atomicAdd(&M.cand_count, 1u);
+                if (ci < (unsigned)SEED_CAND) {
+                    M.cand[ci] = ((uint32_t)(p + i) << 8) | (uint32_t)j;
+                } else {  // list full (tiny c): resolve inline
+                    seed_resolve<K>(S, M, (uint32_t)(p + i), j, rc, thr, out, cap, g_count);
                 }
+            }
+        }
+        __syncthreads();
+        {
+            const unsigned int nc = min(M.cand_count, (unsigned)SEED_CAND);
+            for (unsigned int ci = tid; ci < nc; ci += SEED_THREADS) {
+                const uint32_t e = M.cand[ci];
+                seed_resolve<K>(S, M, e >> 8, (int)(e & 255u), rc, thr, out, cap, g_count);
             }
         }
         __syncthreads();  // table is rewritten by the next chunk
