@@ -106,17 +106,31 @@ __global__ void k_bucket_starts(const uint64_t *__restrict__ keys, uint64_t N, u
 //                 survivor with the best pass-1 ANI in the equal range (lowest genome on ties);
 //                 a genome_kmers hit whose genome is not the winner is "lost" (:641-646).
 // FILL == false : per-genome hit counters only;  FILL == true: scatter the counts into CSR.
+struct SampleView {
+    const uint64_t *hash;
+    const uint32_t *count;
+    uint64_t n;
+};
+
 template <bool PASS2, bool FILL>
-__global__ void k_join(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ scount, uint64_t ns,
+__global__ void k_join(const SampleView *__restrict__ views, uint64_t G,
                        const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gid,
                        const uint32_t *__restrict__ bstart, uint64_t M, uint64_t NB, uint64_t maxkey,
                        const uint8_t *__restrict__ survivor, const double *__restrict__ ani1,
                        uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, uint32_t *__restrict__ cursor,
                        uint32_t *__restrict__ covs, uint32_t *__restrict__ lost) {
+    const SampleView sv = views[blockIdx.y];
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ns) return;
-    const uint64_t key = skey[i];
-    const uint32_t c = scount[i];
+    if (i >= sv.n) return;
+    // per-(sample, genome) arrays: this sample's row
+    const uint64_t row = (uint64_t)blockIdx.y * G;
+    if (PASS2) { survivor += row; ani1 += row; }
+    if (cnt) cnt += row;
+    if (off) off += row;
+    if (cursor) cursor += row;
+    if (lost) lost += row;
+    const uint64_t key = sv.hash[i];
+    const uint32_t c = sv.count[i];
     if (key > maxkey || c == 0) return;  // count 0: src/contain.rs:634-636
     const uint64_t b = bucket_of(key, M, NB);
     uint32_t lo = bstart[b];
@@ -191,15 +205,20 @@ constexpr int STAT_WARPS = 4;
 
 __global__ void __launch_bounds__(STAT_WARPS * 32)
 k_stats(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, const uint32_t *__restrict__ covs,
-        const uint32_t *__restrict__ glen, const uint32_t *__restrict__ lost, uint64_t n_genomes,
-        uint32_t genome_base, uint32_t sample_idx, StatParams P, int pass2, syl_ani_row *__restrict__ rows,
-        uint8_t *__restrict__ valid, uint8_t *__restrict__ need_boot, uint32_t *__restrict__ hist_out) {
+        const uint32_t *__restrict__ glen, const uint32_t *__restrict__ lost, uint64_t n_genomes, uint64_t n_pairs,
+        uint32_t genome_base, StatParams P, int pass2, syl_ani_row *__restrict__ rows, uint64_t rows_cap,
+        uint32_t *__restrict__ boot_rows, uint32_t *__restrict__ hist_out, uint64_t boot_cap,
+        unsigned long long *__restrict__ n_rows, unsigned long long *__restrict__ n_boot) {
     __shared__ uint32_t s_hist[STAT_WARPS][256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t g = (uint64_t)blockIdx.x * STAT_WARPS + w;
-    if (g >= n_genomes) return;
+    const uint64_t pair = (uint64_t)blockIdx.x * STAT_WARPS + w;
+    if (pair >= n_pairs) return;
+    const uint32_t sample_idx = (uint32_t)(pair / n_genomes);
+    const uint64_t g = pair - (uint64_t)sample_idx * n_genomes;
     uint32_t *hist = s_hist[w];
-    if (lane == 0) { valid[g] = 0; need_boot[g] = 0; }
+    cnt += (uint64_t)sample_idx * n_genomes;
+    off += (uint64_t)sample_idx * n_genomes;
+    if (lost) lost += (uint64_t)sample_idx * n_genomes;
     const uint32_t n = cnt[g];
     const uint32_t gl = glen[g];
     if (n == 0) return;                                   // covs.is_empty() :654
@@ -309,11 +328,15 @@ k_stats(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, cons
     r.rel_abund = 0.;
     r.seq_abund = 0.;
     r.reserved = 0.;
-    rows[g] = r;
-    valid[g] = 1;
+    const unsigned long long ri = atomicAdd(n_rows, 1ull);  // compact output; the host orders rows
+    if (ri >= rows_cap) return;
+    rows[ri] = r;
     if (!P.no_ci && has_lambda) {
-        need_boot[g] = 1;
-        for (int v = 0; v < 17; v++) hist_out[g * 17 + v] = v == 0 ? (uint32_t)(gl - n) : hist[v];
+        const unsigned long long bi = atomicAdd(n_boot, 1ull);
+        if (bi < boot_cap) {
+            boot_rows[bi] = (uint32_t)ri;
+            for (int v = 0; v < 17; v++) hist_out[bi * 17 + v] = v == 0 ? (uint32_t)(gl - n) : hist[v];
+        }
     }
 }
 
@@ -329,44 +352,37 @@ constexpr int BOOT_ITERS = 100;
 constexpr int BOOT_THREADS = 256;
 
 // grid (BOOT_ITERS, n_boot): one CTA resamples |full| values for one iteration of one row.
-// H layout per genome: [0] = number of zeros, [v] = #values == v (v = 1..16; all values of a
-// bootstrapped row are <= 15 because its median is <= 2).
+// H layout per row: [0] = number of zeros, [v] = #values == v (v = 1..16; all values of a
+// bootstrapped row are <= 15 because its median is <= 2).  ratio_lambda / ani_from_lambda only
+// need the histogram of the NON-ZERO resampled values and the total, so zero draws (the large
+// majority) cost nothing beyond the RNG.
 __global__ void __launch_bounds__(BOOT_THREADS)
-k_boot_iter(const uint32_t *__restrict__ boot_rows, const uint32_t *__restrict__ hist_in, StatParams P,
+k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
             double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
             uint32_t *__restrict__ reject_flag) {
     __shared__ uint32_t Hb[17];
     __shared__ uint64_t cum[17];
     const uint32_t row = blockIdx.y, it = blockIdx.x;
-    const uint32_t g = boot_rows[row];
-    const uint32_t *H = hist_in + (uint64_t)g * 17;
+    const uint32_t *H = hist_in + (uint64_t)row * 17;
     if (threadIdx.x < 17) Hb[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         uint64_t acc = 0;
         for (int v = 0; v < 17; v++) { acc += H[v]; cum[v] = acc; }  // cum[v] = #values <= v
     }
     __syncthreads();
-    const uint64_t n = cum[16];
-    uint32_t local[17];
-#pragma unroll
-    for (int v = 0; v < 17; v++) local[v] = 0;
+    const uint64_t n = cum[16], z = cum[0];
     const uint64_t t = (0ull - n) % n;  // Lemire rejection threshold (fastrand gen_mod_u64)
     for (uint64_t j = threadIdx.x; j < n; j += BOOT_THREADS) {
         const uint64_t x = wyrand_at(7ull, (uint64_t)it * n + j + 1);
         const uint64_t hi = __umul64hi(x, n), lo = x * n;
         if (lo < n && lo < t) atomicExch(reject_flag + row, 1u);  // probability ~ n / 2^64 per draw
-        uint32_t v = 0;
+        if (hi >= z) {  // full_covs[hi] = v with cum[v-1] <= hi < cum[v]
+            uint32_t v = 1;
 #pragma unroll
-        for (int q = 0; q < 16; q++) v += (hi >= cum[q]) ? 1u : 0u;  // value of full_covs[hi]
-#pragma unroll
-        for (int q = 0; q < 17; q++) local[q] += (v == (uint32_t)q) ? 1u : 0u;
-    }
-#pragma unroll
-    for (int v = 0; v < 17; v++) {
-        uint32_t x = local[v];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&Hb[v], x);
+            for (int step = 8; step >= 1; step >>= 1)
+                if (v + step <= 16 && hi >= cum[v + step - 1]) v += step;
+            atomicAdd(&Hb[v], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
@@ -384,12 +400,12 @@ k_boot_iter(const uint32_t *__restrict__ boot_rows, const uint32_t *__restrict__
 
 // Exact sequential replay for a row whose counter-based draws hit Lemire's rejection branch
 // (the redraw shifts the RNG stream). One thread per flagged row; practically never runs.
-__global__ void k_boot_seq(const uint32_t *__restrict__ boot_rows, const uint32_t *__restrict__ hist_in, uint32_t n_boot,
+__global__ void k_boot_seq(const uint32_t *__restrict__ hist_in, uint32_t n_boot,
                            StatParams P, const uint32_t *__restrict__ reject_flag, double *__restrict__ res_ani,
                            double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_boot || !reject_flag[row]) return;
-    const uint32_t *H = hist_in + (uint64_t)boot_rows[row] * 17;
+    const uint32_t *H = hist_in + (uint64_t)row * 17;
     uint64_t cum[17], acc = 0;
     for (int v = 0; v < 17; v++) { acc += H[v]; cum[v] = acc; }
     const uint64_t n = acc;
@@ -428,58 +444,67 @@ __global__ void k_boot_seq(const uint32_t *__restrict__ boot_rows, const uint32_
     }
 }
 
-// percentile pick: sort the successful iterations, take suc*5/100-1 and suc*95/100-1 (:885-896)
-__global__ void k_boot_final(const uint32_t *__restrict__ boot_rows, uint32_t n_boot, const double *__restrict__ res_ani,
-                             const double *__restrict__ res_lambda, const uint8_t *__restrict__ res_ok,
-                             syl_ani_row *__restrict__ rows) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+// percentile pick (:885-896): of the successful iterations take the elements of rank suc*5/100-1
+// and suc*95/100-1 of each list (sorted independently).  One 128-thread block per row; ranks by
+// counting, so no sort is needed.
+__global__ void __launch_bounds__(128)
+k_boot_final(const uint32_t *__restrict__ boot_rows, uint32_t n_boot, const double *__restrict__ res_ani,
+             const double *__restrict__ res_lambda, const uint8_t *__restrict__ res_ok,
+             syl_ani_row *__restrict__ rows) {
+    __shared__ double a[BOOT_ITERS], l[BOOT_ITERS];
+    __shared__ int s_suc;
+    const uint32_t row = blockIdx.x;
     if (row >= n_boot) return;
-    double a[BOOT_ITERS], l[BOOT_ITERS];
-    int suc = 0;
-    for (int it = 0; it < BOOT_ITERS; it++) {
-        const uint64_t o = (uint64_t)row * BOOT_ITERS + it;
-        if (!res_ok[o]) continue;
-        // insertion sort, ascending, each list on its own
-        double x = res_ani[o], y = res_lambda[o];
-        int p = suc;
-        while (p > 0 && a[p - 1] > x) { a[p] = a[p - 1]; p--; }
-        a[p] = x;
-        p = suc;
-        while (p > 0 && l[p - 1] > y) { l[p] = l[p - 1]; p--; }
-        l[p] = y;
-        suc++;
+    const int t = threadIdx.x;
+    if (t == 0) {  // compact the successful iterations (order is irrelevant for rank selection)
+        int suc = 0;
+        for (int it = 0; it < BOOT_ITERS; it++) {
+            const uint64_t o = (uint64_t)row * BOOT_ITERS + it;
+            if (res_ok[o]) { a[suc] = res_ani[o]; l[suc] = res_lambda[o]; suc++; }
+        }
+        s_suc = suc;
     }
+    __syncthreads();
+    const int suc = s_suc;
     syl_ani_row &r = rows[boot_rows[row]];
-    if (suc < 50) { r.ci_valid = 0; return; }
-    r.ci[0] = a[suc * 5 / 100 - 1];
-    r.ci[1] = a[suc * 95 / 100 - 1];
-    r.ci[2] = l[suc * 5 / 100 - 1];
-    r.ci[3] = l[suc * 95 / 100 - 1];
-    r.ci_valid = 1;
+    if (suc < 50) { if (t == 0) r.ci_valid = 0; return; }
+    const int lo = suc * 5 / 100 - 1, hi = suc * 95 / 100 - 1;
+    if (t < suc) {
+        int ra = 0, rl = 0;
+        const double x = a[t], y = l[t];
+        for (int j = 0; j < suc; j++) {
+            ra += (a[j] < x) || (a[j] == x && j < t);
+            rl += (l[j] < y) || (l[j] == y && j < t);
+        }
+        if (ra == lo) r.ci[0] = x;
+        if (ra == hi) r.ci[1] = x;
+        if (rl == lo) r.ci[2] = y;
+        if (rl == hi) r.ci[3] = y;
+    }
+    if (t == 0) r.ci_valid = 1;
 }
 
-__global__ void k_gather_rows(const syl_ani_row *__restrict__ rows, const uint32_t *__restrict__ sel, uint32_t n,
-                              syl_ani_row *__restrict__ out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = rows[sel[i]];
-}
-
-__global__ void k_mark_survivors(const syl_ani_row *__restrict__ rows, const uint8_t *__restrict__ valid, uint64_t n,
+// mark the pass-1 survivors (rows of the compact list) in the dense (sample, genome) tables
+__global__ void k_mark_survivors(const syl_ani_row *__restrict__ rows, uint64_t n, uint64_t G, uint32_t genome_base,
                                  uint8_t *__restrict__ survivor, double *__restrict__ ani1) {
-    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n) return;
-    survivor[g] = valid[g];
-    ani1[g] = valid[g] ? rows[g].final_est_ani : 0.;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t p = (uint64_t)rows[i].sample * G + (rows[i].genome - genome_base);
+    survivor[p] = 1;
+    ani1[p] = rows[i].final_est_ani;
 }
 
-// Everything the containment passes need per context call (scratch sized by the db)
+// Scratch for one syl_query / syl_profile call: dense per-(sample, genome) tables + compact outputs
 struct ContainScratch {
-    DevBuf<uint32_t> cnt, cursor, lost, sel, boot_sel, hist, covs, reject;
+    DevBuf<SampleView> views;
+    DevBuf<uint32_t> cnt, cursor, lost, boot_rows, hist, covs, reject;
     DevBuf<uint64_t> off;
-    DevBuf<uint8_t> valid, need_boot, survivor, tmp, res_ok;
+    DevBuf<uint8_t> survivor, tmp, res_ok;
     DevBuf<double> ani1, res_ani, res_lambda;
-    DevBuf<syl_ani_row> rows, out_rows;
+    DevBuf<syl_ani_row> rows;
     size_t tmp_bytes = 0;
+    uint64_t S = 0, G = 0, P = 0, max_n = 0;
+    uint64_t rows_cap = 0, boot_cap = 0;
 };
 
 static StatParams make_params(const syl_contain_params *p) {
@@ -494,64 +519,95 @@ static StatParams make_params(const syl_contain_params *p) {
     return P;
 }
 
-// One get_stats pass of one sample over the whole db.  pass2: survivor/ani1 must be filled.
-// Appends the valid rows (genome order) to `rows_out`.
-static int contain_pass(syl_ctx *ctx, const syl_db *db, const syl_sample *s, uint32_t sample_idx, const StatParams &P,
-                        bool pass2, ContainScratch &S, std::vector<syl_ani_row> &rows_out, bool keep_device_rows) {
+static int scratch_init(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+                        bool need_pass2, ContainScratch &S) {
     cudaStream_t st = ctx->stream;
-    const uint64_t G = db->n_genomes;
-    (void)keep_device_rows;
-    SYL_CUDA(cudaMemsetAsync(S.cnt.p, 0, G * 4, st));
-    SYL_CUDA(cudaMemsetAsync(S.cursor.p, 0, G * 4, st));
-    if (pass2) SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, G * 4, st));
-    const unsigned jb = nblk(s->n, 128);
-    if (s->n && db->N) {
+    S.S = n_samples;
+    S.G = db->n_genomes;
+    S.P = S.S * S.G;
+    if (S.P >= 0x7FFFFFFFull) { set_error("samples x genomes exceeds 2^31 pairs per call; split the sample batch"); return SYL_ERR_ARG; }
+    std::vector<SampleView> hv(n_samples);
+    for (uint32_t i = 0; i < n_samples; i++) {
+        hv[i] = {samples[i]->hash, samples[i]->count, samples[i]->n};
+        S.max_n = std::max<uint64_t>(S.max_n, samples[i]->n);
+    }
+    SYL_TRY(S.views.alloc(n_samples, st));
+    SYL_CUDA(cudaMemcpyAsync(S.views.p, hv.data(), n_samples * sizeof(SampleView), cudaMemcpyHostToDevice, st));
+    SYL_CUDA(cudaStreamSynchronize(st));  // hv goes out of scope
+    SYL_TRY(S.cnt.alloc(S.P, st)); SYL_TRY(S.cursor.alloc(S.P, st)); SYL_TRY(S.off.alloc(S.P + 1, st));
+    if (need_pass2) {
+        SYL_TRY(S.lost.alloc(S.P, st)); SYL_TRY(S.survivor.alloc(S.P, st)); SYL_TRY(S.ani1.alloc(S.P, st));
+    }
+    S.rows_cap = std::min<uint64_t>(S.P, 1u << 16);
+    S.boot_cap = S.rows_cap;
+    SYL_TRY(S.rows.alloc(S.rows_cap, st));
+    SYL_TRY(S.boot_rows.alloc(S.boot_cap, st));
+    SYL_TRY(S.hist.alloc(S.boot_cap * 17, st));
+    SYL_TRY(S.covs.alloc(1 << 16, st));
+    cub::DeviceScan::ExclusiveSum(nullptr, S.tmp_bytes, S.cnt.p, S.off.p, (int)S.P, st);
+    SYL_TRY(S.tmp.alloc(S.tmp_bytes, st));
+    return SYL_OK;
+}
+
+// One get_stats pass of ALL samples over the whole db (batched: one set of launches, two host
+// syncs).  pass2: S.survivor / S.ani1 must be filled.  Output rows ordered by (sample, genome).
+static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, bool pass2, ContainScratch &S,
+                        std::vector<syl_ani_row> &rows_out, bool keep_device_rows, uint64_t *n_dev_rows) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t G = S.G, NP = S.P;
+    rows_out.clear();
+    SYL_CUDA(cudaMemsetAsync(S.cnt.p, 0, NP * 4, st));
+    SYL_CUDA(cudaMemsetAsync(S.cursor.p, 0, NP * 4, st));
+    if (pass2) SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, NP * 4, st));
+    const dim3 jgrid(nblk(std::max<uint64_t>(S.max_n, 1), 128), (unsigned)S.S);
+    const bool have = S.max_n && db->N;
+    if (have) {
         if (!pass2)
-            k_join<false, false><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
-                                                     db->maxkey, nullptr, nullptr, S.cnt.p, nullptr, nullptr, nullptr, nullptr);
+            k_join<false, false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                        nullptr, nullptr, S.cnt.p, nullptr, nullptr, nullptr, nullptr);
         else
-            k_join<true, false><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
-                                                    db->maxkey, S.survivor.p, S.ani1.p, S.cnt.p, nullptr, nullptr, nullptr,
-                                                    S.lost.p);
+            k_join<true, false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                       S.survivor.p, S.ani1.p, S.cnt.p, nullptr, nullptr, nullptr, S.lost.p);
         ctx->launches++;
     }
-    // CSR offsets of the per-genome hit lists
     size_t tb = S.tmp_bytes;
-    SYL_CUDA(cub::DeviceScan::ExclusiveSum(S.tmp.p, tb, S.cnt.p, S.off.p, G, st));
-    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 10, S.off.p + (G - 1), 8, cudaMemcpyDeviceToHost, st));
-    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 11, S.cnt.p + (G - 1), 4, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cub::DeviceScan::ExclusiveSum(S.tmp.p, tb, S.cnt.p, S.off.p, (int)NP, st));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 10, S.off.p + (NP - 1), 8, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 11, S.cnt.p + (NP - 1), 4, cudaMemcpyDeviceToHost, st));
     SYL_CUDA(cudaStreamSynchronize(st));
     const uint64_t H = ctx->h_counters[10] + (uint32_t)ctx->h_counters[11];
     if (H > S.covs.n) SYL_TRY(S.covs.alloc(H + H / 2 + 1024, st));
     if (H) {
         if (!pass2)
-            k_join<false, true><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
-                                                    db->maxkey, nullptr, nullptr, nullptr, S.off.p, S.cursor.p, S.covs.p,
-                                                    nullptr);
+            k_join<false, true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                       nullptr, nullptr, nullptr, S.off.p, S.cursor.p, S.covs.p, nullptr);
         else
-            k_join<true, true><<<jb, 128, 0, st>>>(s->hash, s->count, s->n, db->keys, db->gid, db->bstart, db->M, db->NB,
-                                                   db->maxkey, S.survivor.p, S.ani1.p, nullptr, S.off.p, S.cursor.p,
-                                                   S.covs.p, nullptr);
+            k_join<true, true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                      S.survivor.p, S.ani1.p, nullptr, S.off.p, S.cursor.p, S.covs.p, nullptr);
         ctx->launches++;
     }
-    k_stats<<<nblk(G, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.cnt.p, S.off.p, S.covs.p, db->glen, S.lost.p, G,
-                                                             db->genome_base, sample_idx, P, pass2 ? 1 : 0, S.rows.p,
-                                                             S.valid.p, S.need_boot.p, S.hist.p);
-    ctx->launches++;
-    SYL_CUDA(cudaGetLastError());
-    // select valid rows and rows that need a bootstrap (both in genome order)
-    uint64_t *d_nsel = ctx->d_counters + 12;
-    tb = S.tmp_bytes;
-    SYL_CUDA(cub::DeviceSelect::Flagged(S.tmp.p, tb, cub::CountingInputIterator<uint32_t>(0), S.valid.p, S.sel.p,
-                                        reinterpret_cast<uint32_t *>(d_nsel), (int)G, st));
-    tb = S.tmp_bytes;
-    SYL_CUDA(cub::DeviceSelect::Flagged(S.tmp.p, tb, cub::CountingInputIterator<uint32_t>(0), S.need_boot.p, S.boot_sel.p,
-                                        reinterpret_cast<uint32_t *>(d_nsel + 1), (int)G, st));
-    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 12, d_nsel, 16, cudaMemcpyDeviceToHost, st));
-    SYL_CUDA(cudaStreamSynchronize(st));
-    const uint32_t n_valid = (uint32_t)ctx->h_counters[12], n_boot = (uint32_t)ctx->h_counters[13];
+    unsigned long long *d_n = reinterpret_cast<unsigned long long *>(ctx->d_counters + 12);  // [12] rows, [13] boot rows
+    uint64_t n_rows = 0, n_boot = 0;
+    for (;;) {
+        SYL_CUDA(cudaMemsetAsync(d_n, 0, 16, st));
+        k_stats<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.cnt.p, S.off.p, S.covs.p, db->glen, pass2 ? S.lost.p : nullptr,
+                                                                  G, NP, db->genome_base, P, pass2 ? 1 : 0, S.rows.p, S.rows_cap,
+                                                                  S.boot_rows.p, S.hist.p, S.boot_cap, d_n, d_n + 1);
+        ctx->launches++;
+        SYL_CUDA(cudaGetLastError());
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 12, d_n, 16, cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaStreamSynchronize(st));
+        n_rows = ctx->h_counters[12];
+        n_boot = ctx->h_counters[13];
+        if (n_rows <= S.rows_cap && n_boot <= S.boot_cap) break;
+        S.rows_cap = std::max(S.rows_cap, n_rows);  // rare: more rows than the first guess, redo with room
+        S.boot_cap = std::max(S.boot_cap, n_boot);
+        SYL_TRY(S.rows.alloc(S.rows_cap, st));
+        SYL_TRY(S.boot_rows.alloc(S.boot_cap, st));
+        SYL_TRY(S.hist.alloc(S.boot_cap * 17, st));
+    }
     if (n_boot) {
-        const uint64_t nb = (uint64_t)n_boot * BOOT_ITERS;
+        const uint64_t nb = n_boot * BOOT_ITERS;
         if (nb > S.res_ani.n) {
             SYL_TRY(S.res_ani.alloc(nb, st));
             SYL_TRY(S.res_lambda.alloc(nb, st));
@@ -559,52 +615,28 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const syl_sample *s, uin
             SYL_TRY(S.reject.alloc(n_boot, st));
         }
         SYL_CUDA(cudaMemsetAsync(S.reject.p, 0, (size_t)n_boot * 4, st));
-        for (uint32_t r0 = 0; r0 < n_boot; r0 += 32768) {  // gridDim.y limit
-            const uint32_t nr = std::min<uint32_t>(32768, n_boot - r0);
-            k_boot_iter<<<dim3(BOOT_ITERS, nr), BOOT_THREADS, 0, st>>>(S.boot_sel.p + r0, S.hist.p, P,
-                                                                       S.res_ani.p + (uint64_t)r0 * BOOT_ITERS,
-                                                                       S.res_lambda.p + (uint64_t)r0 * BOOT_ITERS,
-                                                                       S.res_ok.p + (uint64_t)r0 * BOOT_ITERS,
-                                                                       S.reject.p + r0);
+        for (uint64_t r0 = 0; r0 < n_boot; r0 += 32768) {  // gridDim.y limit
+            const uint32_t nr = (uint32_t)std::min<uint64_t>(32768, n_boot - r0);
+            k_boot_iter<<<dim3(BOOT_ITERS, nr), BOOT_THREADS, 0, st>>>(S.hist.p + r0 * 17, P, S.res_ani.p + r0 * BOOT_ITERS,
+                                                                       S.res_lambda.p + r0 * BOOT_ITERS,
+                                                                       S.res_ok.p + r0 * BOOT_ITERS, S.reject.p + r0);
             ctx->launches++;
         }
-        k_boot_seq<<<nblk(n_boot, 32), 32, 0, st>>>(S.boot_sel.p, S.hist.p, n_boot, P, S.reject.p, S.res_ani.p,
-                                                    S.res_lambda.p, S.res_ok.p);
-        k_boot_final<<<nblk(n_boot, 32), 32, 0, st>>>(S.boot_sel.p, n_boot, S.res_ani.p, S.res_lambda.p, S.res_ok.p,
-                                                      S.rows.p);
+        k_boot_seq<<<nblk(n_boot, 32), 32, 0, st>>>(S.hist.p, (uint32_t)n_boot, P, S.reject.p, S.res_ani.p, S.res_lambda.p, S.res_ok.p);
+        k_boot_final<<<(unsigned)n_boot, 128, 0, st>>>(S.boot_rows.p, (uint32_t)n_boot, S.res_ani.p, S.res_lambda.p, S.res_ok.p, S.rows.p);
         ctx->launches += 2;
         SYL_CUDA(cudaGetLastError());
     }
-    if (n_valid) {
-        if (n_valid > S.out_rows.n) SYL_TRY(S.out_rows.alloc(n_valid + 1024, st));
-        k_gather_rows<<<nblk(n_valid, 128), 128, 0, st>>>(S.rows.p, S.sel.p, n_valid, S.out_rows.p);
-        ctx->launches++;
-        const size_t base = rows_out.size();
-        rows_out.resize(base + n_valid);
-        SYL_CUDA(cudaMemcpyAsync(rows_out.data() + base, S.out_rows.p, (size_t)n_valid * sizeof(syl_ani_row),
-                                 cudaMemcpyDeviceToHost, st));
+    if (n_rows) {
+        rows_out.resize(n_rows);
+        SYL_CUDA(cudaMemcpyAsync(rows_out.data(), S.rows.p, n_rows * sizeof(syl_ani_row), cudaMemcpyDeviceToHost, st));
         SYL_CUDA(cudaStreamSynchronize(st));
+        std::sort(rows_out.begin(), rows_out.end(), [](const syl_ani_row &a, const syl_ani_row &b) {
+            return a.sample != b.sample ? a.sample < b.sample : a.genome < b.genome;
+        });
     }
-    return SYL_OK;
-}
-
-static int scratch_init(syl_ctx *ctx, const syl_db *db, ContainScratch &S) {
-    cudaStream_t st = ctx->stream;
-    const uint64_t G = std::max<uint64_t>(db->n_genomes, 1);
-    SYL_TRY(S.cnt.alloc(G, st)); SYL_TRY(S.cursor.alloc(G, st)); SYL_TRY(S.lost.alloc(G, st));
-    SYL_TRY(S.sel.alloc(G, st)); SYL_TRY(S.boot_sel.alloc(G, st)); SYL_TRY(S.hist.alloc(G * 17, st));
-    SYL_TRY(S.off.alloc(G + 1, st));
-    SYL_TRY(S.valid.alloc(G, st)); SYL_TRY(S.need_boot.alloc(G, st)); SYL_TRY(S.survivor.alloc(G, st));
-    SYL_TRY(S.ani1.alloc(G, st));
-    SYL_TRY(S.rows.alloc(G, st));
-    SYL_TRY(S.covs.alloc(1 << 16, st));
-    size_t t1 = 0, t2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, t1, S.cnt.p, S.off.p, G, st);
-    cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<uint32_t>(0), S.valid.p, S.sel.p,
-                               reinterpret_cast<uint32_t *>(ctx->d_counters), (int)G, st);
-    S.tmp_bytes = std::max(t1, t2);
-    SYL_TRY(S.tmp.alloc(S.tmp_bytes, st));
-    SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, G * 4, st));
+    (void)keep_device_rows;
+    if (n_dev_rows) *n_dev_rows = n_rows;
     return SYL_OK;
 }
 
@@ -727,10 +759,10 @@ int syl_query(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, 
     SYL_CUDA(cudaSetDevice(ctx->device));
     if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
     ContainScratch S;
-    SYL_TRY(scratch_init(ctx, db, S));
+    SYL_TRY(scratch_init(ctx, db, samples, n_samples, false, S));
     const StatParams P = make_params(p);
     std::vector<syl_ani_row> out;
-    for (uint32_t i = 0; i < n_samples; i++) SYL_TRY(contain_pass(ctx, db, samples[i], i, P, false, S, out, false));
+    SYL_TRY(contain_pass(ctx, db, P, false, S, out, false, nullptr));
     *n_rows = out.size();
     if (out.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
     std::copy(out.begin(), out.end(), rows);
@@ -749,25 +781,30 @@ int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples
     if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
     cudaStream_t st = ctx->stream;
     ContainScratch S;
-    SYL_TRY(scratch_init(ctx, db, S));
+    SYL_TRY(scratch_init(ctx, db, samples, n_samples, true, S));
     syl_contain_params pp = *p;
     pp.pseudotax = 1;
     const StatParams P = make_params(&pp);
-    std::vector<syl_ani_row> all;
-    for (uint32_t i = 0; i < n_samples; i++) {
-        std::vector<syl_ani_row> r1, r2;
-        SYL_TRY(contain_pass(ctx, db, samples[i], i, P, false, S, r1, true));
-        if (r1.empty()) continue;
-        // pass-1 rows are still in S.rows / S.valid (indexed by genome): they define the winner table
-        k_mark_survivors<<<nblk(db->n_genomes, 256), 256, 0, st>>>(S.rows.p, S.valid.p, db->n_genomes, S.survivor.p, S.ani1.p);
-        ctx->launches++;
-        SYL_TRY(contain_pass(ctx, db, samples[i], i, P, true, S, r2, false));
-        // derep_if_reassign_threshold (src/contain.rs:353-375)
-        const double threshold = std::pow(pp.redundant_ani / 100., (double)pp.k);
+    std::vector<syl_ani_row> r1, r2, all;
+    uint64_t n1 = 0;
+    SYL_TRY(contain_pass(ctx, db, P, false, S, r1, true, &n1));
+    if (r1.empty()) return SYL_OK;
+    // the pass-1 rows (still on the device) define the winner table of every sample
+    SYL_CUDA(cudaMemsetAsync(S.survivor.p, 0, S.P, st));
+    SYL_CUDA(cudaMemsetAsync(S.ani1.p, 0, S.P * 8, st));
+    k_mark_survivors<<<nblk(n1, 256), 256, 0, st>>>(S.rows.p, n1, S.G, db->genome_base, S.survivor.p, S.ani1.p);
+    ctx->launches++;
+    SYL_TRY(contain_pass(ctx, db, P, true, S, r2, false, nullptr));
+    const double threshold = std::pow(pp.redundant_ani / 100., (double)pp.k);
+    size_t i1 = 0, i2 = 0;
+    for (uint32_t smp = 0; smp < n_samples; smp++) {
+        // derep_if_reassign_threshold (src/contain.rs:353-375), per sample, genome order
         std::vector<syl_ani_row> kept;
-        size_t j = 0;
-        for (const syl_ani_row &n2 : r2) {
-            while (j < r1.size() && r1[j].genome < n2.genome) j++;
+        while (i1 < r1.size() && r1[i1].sample < smp) i1++;
+        size_t j = i1;
+        for (; i2 < r2.size() && r2[i2].sample == smp; i2++) {
+            const syl_ani_row &n2 = r2[i2];
+            while (j < r1.size() && r1[j].sample == smp && r1[j].genome < n2.genome) j++;
             const syl_ani_row &o = r1[j];
             const double num_reassign = (double)(o.contain - n2.contain);
             const double reass_thresh = threshold * (double)n2.glen;

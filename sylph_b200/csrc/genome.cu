@@ -89,23 +89,37 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t *a, uint64_t 
     return lo;
 }
 
-// greedy spacing chain of one contig (src/sketch.rs:602-614): 1 = kept, 2 = tracked (thinned out)
-__global__ void k_spacing(const uint64_t *__restrict__ poskey, uint64_t n, uint64_t n_contigs, uint64_t min_spacing,
+// Greedy min-spacing selection (src/sketch.rs:602-614): 1 = kept, 2 = tracked (thinned out).
+// The reference walks a contig keeping a k-mer iff pos - last_kept > min_spacing.  A k-mer whose
+// distance to the PREVIOUS non-duplicate k-mer already exceeds min_spacing is kept whatever
+// happened before it (last_kept <= previous position), so the walk splits into independent
+// clusters of closely spaced k-mers, each starting with such a head.  One thread per survivor:
+// heads walk their (tiny: ~1.15 elements at c=200) cluster; everything else returns.
+__global__ void k_spacing(const uint64_t *__restrict__ poskey, uint64_t n, uint64_t min_spacing,
                           uint8_t *__restrict__ flag) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_contigs) return;
-    uint64_t i = lower_bound_u64(poskey, n, r << 32);
-    const uint64_t end = lower_bound_u64(poskey, n, (r + 1) << 32);
-    uint64_t last_pos = 0;
-    for (; i < end; i++) {
-        if (flag[i] == 0) continue;
-        const uint64_t pos = poskey[i] & 0xFFFFFFFFull;
-        if (last_pos == 0 || pos - last_pos > min_spacing) {
-            flag[i] = 1;
-            last_pos = pos;
-        } else {
-            flag[i] = 2;
-        }
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || flag[i] == 0) return;
+    const uint64_t key = poskey[i], contig = key >> 32, pos = key & 0xFFFFFFFFull;
+    // previous non-duplicate survivor of the same contig
+    bool head = true;
+    for (uint64_t j = i; j-- > 0;) {
+        const uint64_t kj = poskey[j];
+        if ((kj >> 32) != contig) break;
+        if (flag[j] == 0) continue;  // duplicates never change state, so this read races with nothing
+        head = pos - (kj & 0xFFFFFFFFull) > min_spacing;
+        break;
+    }
+    if (!head) return;
+    flag[i] = 1;
+    uint64_t last = pos, prev = pos;
+    for (uint64_t k = i + 1; k < n; k++) {
+        const uint64_t kk = poskey[k];
+        if ((kk >> 32) != contig) break;
+        if (flag[k] == 0) continue;
+        const uint64_t pk = kk & 0xFFFFFFFFull;
+        if (pk - prev > min_spacing) break;  // k is a head: its own thread takes over
+        if (pk - last > min_spacing) { flag[k] = 1; last = pk; } else { flag[k] = 2; }
+        prev = pk;
     }
 }
 
@@ -228,7 +242,7 @@ int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases
         SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, hash_b.p, hash_a.p, idx_a.p, idx_b.p, N, 0, hash_bits, st));
         k_flag_dups<<<nblk(N, 256), 256, 0, st>>>(hash_a.p, idx_b.p, N, key_b.p, cg.p, flag.p);
         // 4. greedy spacing per contig
-        k_spacing<<<nblk(n_contigs, 64), 64, 0, st>>>(key_b.p, N, n_contigs, min_spacing, flag.p);
+        k_spacing<<<nblk(N, 256), 256, 0, st>>>(key_b.p, N, min_spacing, flag.p);
         // 5. compaction
         k_flag_to_u64<<<nblk(N, 256), 256, 0, st>>>(flag.p, N, 1, scan_k.p);
         k_flag_to_u64<<<nblk(N, 256), 256, 0, st>>>(flag.p, N, 2, scan_t.p);
