@@ -1,0 +1,52 @@
+"""CPU suite: host layer — the C++ driver builds and refuses to run without a GPU; the Python
+.syldb/.sylsp codec round-trips and matches the documented bincode byte layout."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+from tests.util import REPO
+
+
+def test_host_driver_builds_and_fails_loudly_without_gpu(tmp_path):
+    from sylph_b200 import build
+    build.build()
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.check_call(["make", "-C", os.path.join(REPO, "host"), "-s"], env=env)
+    exe = os.path.join(REPO, "host", "sylph-b200")
+    assert os.path.exists(exe)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "query", "a.fa", "b.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_formats_roundtrip_and_layout(tmp_path):
+    from sylph_b200 import formats as F
+    g = [dict(genome_kmers=np.array([5, 7, 9], np.uint64), tracked=np.array([11], np.uint64), file_name="a.fa",
+              first_contig_name="chr1 desc", c=200, k=31, gn_size=1234, min_spacing=30),
+         dict(genome_kmers=np.array([], np.uint64), tracked=None, file_name="b.fa", first_contig_name="", c=100, k=21,
+              gn_size=0, min_spacing=5)]
+    p = str(tmp_path / "x.syldb")
+    F.write_syldb(p, g)
+    raw = open(p, "rb").read()
+    # u64 n_genomes | u64 3 | 3 x u64 | tag 1 | u64 1 | u64 11 | str | str | 4 x u64 | ...
+    assert raw[:8] == struct.pack("<Q", 2) and raw[8:16] == struct.pack("<Q", 3)
+    assert raw[16:40] == struct.pack("<QQQ", 5, 7, 9) and raw[40] == 1
+    back = F.read_syldb(p)
+    assert back[0]["genome_kmers"].tolist() == [5, 7, 9] and back[0]["tracked"].tolist() == [11]
+    assert back[1]["tracked"] is None and back[1]["k"] == 21 and back[0]["first_contig_name"] == "chr1 desc"
+    s = dict(hashes=np.array([3, 1], np.uint64), counts=np.array([2, 9], np.uint32), c=200, k=31, file_name="r.fq",
+             sample_name=None, paired=False, mean_read_length=150.5)
+    p2 = str(tmp_path / "r.sylsp")
+    F.write_sylsp(p2, s)
+    raw = open(p2, "rb").read()
+    assert raw[:8] == struct.pack("<Q", 2) and raw[8:20] == struct.pack("<QI", 3, 2)  # (u64, u32) pairs, no padding
+    b = F.read_sylsp(p2)
+    assert b["hashes"].tolist() == [3, 1] and b["counts"].tolist() == [2, 9] and b["mean_read_length"] == 150.5
+    s["sample_name"] = "S1"
+    F.write_sylsp(p2, s)
+    assert F.read_sylsp(p2)["sample_name"] == "S1"
