@@ -91,9 +91,11 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    so = _build.SO
-    if _build.needs_build():
-        so = _build.build()
+    so = os.environ.get("SYLPH_B200_LIB")  # tuning experiments only: an alternative build of the same sources
+    if not so:
+        so = _build.SO
+        if _build.needs_build():
+            so = _build.build()
     L = C.CDLL(so)  # raises OSError if missing: no fallback
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol

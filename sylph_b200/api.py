@@ -211,9 +211,9 @@ class Context:
         n = len(samples)
         arr = (C.c_void_p * max(n, 1))(*[s._h for s in samples])
         if cap is None:
-            cap = max(1024, min(len(db) * max(n, 1), 1 << 20))
+            cap = max(4096, 1024 * max(n, 1))  # rows are the pairs that pass the ANI gate: far fewer than pairs
         while True:
-            rows = np.zeros(cap, dtype=ANI_ROW_DTYPE)
+            rows = np.empty(cap, dtype=ANI_ROW_DTYPE)
             n_rows = C.c_uint64(0)
             rc = fn(self._h, db._h, arr, n, C.byref(params), rows.ctypes.data_as(C.c_void_p), cap, C.byref(n_rows))
             if rc == _lib.SYL_ERR_CAPACITY:

@@ -371,18 +371,45 @@ k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
     }
     __syncthreads();
     const uint64_t n = cum[16], z = cum[0];
-    const uint64_t t = (0ull - n) % n;  // Lemire rejection threshold (fastrand gen_mod_u64)
-    for (uint64_t j = threadIdx.x; j < n; j += BOOT_THREADS) {
-        const uint64_t x = wyrand_at(7ull, (uint64_t)it * n + j + 1);
-        const uint64_t hi = __umul64hi(x, n), lo = x * n;
-        if (lo < n && lo < t) atomicExch(reject_flag + row, 1u);  // probability ~ n / 2^64 per draw
-        if (hi >= z) {  // full_covs[hi] = v with cum[v-1] <= hi < cum[v]
-            uint32_t v = 1;
-#pragma unroll
-            for (int step = 8; step >= 1; step >>= 1)
-                if (v + step <= 16 && hi >= cum[v + step - 1]) v += step;
-            atomicAdd(&Hb[v], 1u);
+    const uint32_t n32 = (uint32_t)n, z32 = (uint32_t)z;  // |full| = |genome_kmers| < 2^32
+    const uint32_t c1 = (uint32_t)cum[1], c2 = (uint32_t)cum[2], c3 = (uint32_t)cum[3];
+    uint32_t n1 = 0, n2 = 0, n3 = 0;
+    // draw number d = it*n + j + 1; WyRand state s(d) = 7 + d*C0, advanced by BOOT_THREADS*C0 per trip
+    uint64_t s = 7ull + ((uint64_t)it * n + threadIdx.x + 1) * 0x2d358dccaa6c78a5ull;
+    const uint64_t s_step = (uint64_t)BOOT_THREADS * 0x2d358dccaa6c78a5ull;
+    for (uint32_t j = threadIdx.x; j < n32; j += BOOT_THREADS, s += s_step) {
+        const uint64_t tt = s ^ 0x8bb84b93962eacc9ull;
+        const uint64_t x = (s * tt) ^ __umul64hi(s, tt);
+        // fastrand gen_mod_u64 (Lemire): hi = (x*n) >> 64, lo = (x*n) mod 2^64, with n < 2^32
+        const uint64_t a = (uint64_t)(uint32_t)x * n32;                 // x_lo * n
+        const uint64_t b = (x >> 32) * n32 + (a >> 32);                 // x_hi * n + carry
+        const uint32_t hi = (uint32_t)(b >> 32);
+        if ((uint32_t)b == 0u) {  // necessary for lo < n (prob 2^-32): only then form lo exactly
+            const uint64_t lo = (b << 32) | (uint32_t)a;
+            if (lo < n && lo < (0ull - n) % n) atomicExch(reject_flag + row, 1u);  // the reference would redraw
         }
+        if (hi >= z32) {  // full_covs[hi] = v with cum[v-1] <= hi < cum[v]
+            if (hi < c1) n1++;            // the common small values stay in registers
+            else if (hi < c2) n2++;
+            else if (hi < c3) n3++;
+            else {
+                uint32_t v = 4;
+#pragma unroll
+                for (int step = 8; step >= 1; step >>= 1)
+                    if (v + step <= 16 && (uint64_t)hi >= cum[v + step - 1]) v += step;
+                atomicAdd(&Hb[v], 1u);
+            }
+        }
+    }
+    n1 += __shfl_xor_sync(0xffffffffu, n1, 16); n2 += __shfl_xor_sync(0xffffffffu, n2, 16); n3 += __shfl_xor_sync(0xffffffffu, n3, 16);
+    n1 += __shfl_xor_sync(0xffffffffu, n1, 8);  n2 += __shfl_xor_sync(0xffffffffu, n2, 8);  n3 += __shfl_xor_sync(0xffffffffu, n3, 8);
+    n1 += __shfl_xor_sync(0xffffffffu, n1, 4);  n2 += __shfl_xor_sync(0xffffffffu, n2, 4);  n3 += __shfl_xor_sync(0xffffffffu, n3, 4);
+    n1 += __shfl_xor_sync(0xffffffffu, n1, 2);  n2 += __shfl_xor_sync(0xffffffffu, n2, 2);  n3 += __shfl_xor_sync(0xffffffffu, n3, 2);
+    n1 += __shfl_xor_sync(0xffffffffu, n1, 1);  n2 += __shfl_xor_sync(0xffffffffu, n2, 1);  n3 += __shfl_xor_sync(0xffffffffu, n3, 1);
+    if ((threadIdx.x & 31) == 0) {
+        if (n1) atomicAdd(&Hb[1], n1);
+        if (n2) atomicAdd(&Hb[2], n2);
+        if (n3) atomicAdd(&Hb[3], n3);
     }
     __syncthreads();
     if (threadIdx.x != 0) return;

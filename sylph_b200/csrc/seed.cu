@@ -27,12 +27,18 @@
 namespace syl {
 
 constexpr int SEED_THREADS = 256;
-constexpr int SEED_TILE = 32768;   // window-start positions (== bases) per CTA
+#ifndef SEED_TILE_CFG
+#define SEED_TILE_CFG 32768
+#endif
+#ifndef SEED_MINB_CFG
+#define SEED_MINB_CFG 4
+#endif
+constexpr int SEED_TILE = SEED_TILE_CFG;   // window-start positions (== bases) per CTA
 constexpr int SEED_W = 32;         // windows per thread-run
 constexpr int SEED_HALO = 48;      // bytes staged past the tile (>= k-1, multiple of 16)
-constexpr int SEED_STAGE = 512;    // survivors staged per CTA before falling back to global atomics
-constexpr int SEED_CAND = 1024;    // candidate windows buffered per record chunk (overflow is handled inline)
-constexpr int SEED_RUNS_PER_THREAD = 5;
+constexpr int SEED_STAGE = SEED_TILE >= 32768 ? 512 : 256;    // survivors staged per CTA before falling back to global atomics
+constexpr int SEED_CAND = SEED_TILE >= 32768 ? 1024 : 512;    // candidate windows buffered per record chunk (overflow is handled inline)
+constexpr int SEED_RUNS_PER_THREAD = (SEED_TILE / SEED_W + 2 * SEED_THREADS - 1) / SEED_THREADS;
 constexpr int SEED_MAXRUNS = SEED_THREADS * SEED_RUNS_PER_THREAD;  // >= SEED_TILE / SEED_W + SEED_THREADS
 static_assert(SEED_MAXRUNS >= SEED_TILE / SEED_W + SEED_THREADS, "run table too small");
 constexpr int SEED_ASC_BYTES = SEED_TILE + SEED_HALO;  // 32816, multiple of 16
@@ -163,7 +169,7 @@ __device__ __forceinline__ void seed_resolve(const SeedSmem &S, SeedMeta &M, uin
 }
 
 template <int K, int VAR>
-__global__ void __launch_bounds__(SEED_THREADS, 4)
+__global__ void __launch_bounds__(SEED_THREADS, SEED_MINB_CFG)
 k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__restrict__ rec_off, uint64_t off_bias,
        const uint32_t *__restrict__ tile_rec, uint64_t thr, int sem, int with_pos,
        syl_survivor *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count,
@@ -439,9 +445,17 @@ int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const ui
     }();
     using kern_t = void (*)(const uint8_t *, uint64_t, const uint64_t *, uint64_t, const uint32_t *, uint64_t, int, int,
                             syl_survivor *, uint64_t, unsigned long long *, const ShiftMul);
+    // VAR 1/2 (xor-shifts on the FMA pipe via IMAD.HI) measured 3-8 % slower on B200: IMAD.HI and
+    // IMAD.WIDE occupy the fmaheavy pipe for 4 cycles, which then becomes the limiter. Kept as a
+    // compile-time option (-DSEED_ALL_VARIANTS) for future tuning.
+#ifdef SEED_ALL_VARIANTS
     static const kern_t table[2][3] = {{k_seed<31, 0>, k_seed<31, 1>, k_seed<31, 2>},
                                        {k_seed<21, 0>, k_seed<21, 1>, k_seed<21, 2>}};
     kern_t kern = table[k == 31 ? 0 : 1][variant];
+#else
+    (void)variant;
+    kern_t kern = k == 31 ? k_seed<31, 0> : k_seed<21, 0>;
+#endif
     const ShiftMul smul = {1u << 8, 1u << 18, 1u << 4};
     SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev0, st));
