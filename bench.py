@@ -348,31 +348,24 @@ def bench_pairs(args, ctx, rank, world, local, reads):
     samples = []
     bases, off = reads
     for si in range(n_samples):
-        if si == 0:
+        if si == 0 and world == 1:
             samples.append(ctx.sketch_sequences(bases, off, k=K, c=C))
-        else:  # further samples: different community draws, 1/8 of the depth each to bound setup time
-            b, o = synth.reads(max(10000, args.reads // 8), READ_LEN, seed=synth.SEED_READS + 0x10 + si, device="cuda")
+        else:  # replicated samples (identical on every rank): different community draws, 1/8 of the depth each
+            b, o = synth.reads(max(10000, args.reads // 8), READ_LEN, seed=synth.SEED_READS + 0x1000 + si, device="cuda")
             samples.append(ctx.sketch_sequences(b, o, k=K, c=C))
             del b, o
+    from sylph_b200 import dist as D
     from sylph_b200.api import contain_params
-    P = contain_params(k=K, pseudotax=False)
+    P = contain_params(k=K, pseudotax=True)
     st = {}
 
     def step():
-        rows = ctx.query(db, samples, P)
-        st["rows"] = rows
-        if world > 1:  # the one collective of the path: all-gather of the per-shard result rows
-            import torch.distributed as dist
-            n_local = torch.tensor([len(rows)], dtype=torch.int64, device="cuda")
-            counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(counts, n_local)
-            mx = max(int(c.item()) for c in counts)
-            buf = torch.zeros(max(mx, 1) * 144, dtype=torch.uint8, device="cuda")
-            if len(rows):
-                buf[: len(rows) * 144] = torch.from_numpy(rows.view(np.uint8).reshape(-1)).cuda()
-            out = [torch.empty_like(buf) for _ in range(world)]
-            dist.all_gather(out, buf)
-            st["gathered"] = sum(int(c.item()) for c in counts)
+        # `sylph profile`: pass 1, winner table, pass 2, derep, abundances. N>1: db sharded by genome,
+        # pass-1 survivors gathered into a survivor db, rows all-gathered (sylph_b200/dist.py)
+        if world == 1:
+            st["rows"] = ctx.profile(db, samples, P)
+        else:
+            st["rows"] = D.profile_sharded(ctx, genomes, db, samples, rank * G, P)
 
     for _ in range(args.warmup):
         step()
@@ -385,23 +378,23 @@ def bench_pairs(args, ctx, rank, world, local, reads):
     nk_total = sum_over_ranks(float(int(np.sum([len(s) for s in samples]))), 1)
     out = {"metric": "(sample x genome) containment pairs/s", "value": value, "unit": "pairs/s", "ms_per_step": ms / args.steps,
            "wall_ms_per_step": wall / args.steps, "steps": args.steps, "gpu_launches": int(launches),
-           "config": {"workload": "query %d sample sketch(es) vs %d synthetic 4 Mbp genome sketches per GPU "
+           "config": {"workload": "profile %d sample sketch(es) vs %d synthetic 4 Mbp genome sketches per GPU "
                                   "(BASELINE.json configs[%d])" % (n_samples, G, 2 if world == 1 else 3),
                       "genomes_per_gpu": G, "samples": n_samples, "sample_keys": int(nk_total),
                       "rows_per_step": int(len(st["rows"])), "db_build_s": t_db,
-                      "collective": "all_gather of result rows (NCCL)" if world > 1 else "none"},
-           "e2e_note": "syl_query returns rows in host memory: the D2H of the result rows is inside the timed region"}
+                      "collective": "all_gather of survivor sketches and of result rows (NCCL)" if world > 1 else "none"},
+           "e2e_note": "syl_profile returns rows in host memory: the D2H of the result rows is inside the timed region"}
     if d is not None:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
         h, c = samples[0].download()
         smp = O.Sample(h, c)
-        p = O.default_params(pseudotax=False)
+        p = O.default_params(pseudotax=True)
         t = time.perf_counter()
         res = O.contain_sample(p, d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"], smp, nthreads=cores)
         dt = time.perf_counter() - t
         out["cpu_baseline"] = {"value": G / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                               "sample": "all %d pairs of the same db/sample, oracle get_stats over %d OpenMP threads" % (G, cores),
+                               "sample": "all %d pairs of the same db/sample, oracle profile (2 x get_stats + winner table) over %d OpenMP threads" % (G, cores),
                                "rows": len(res)}
         assert len(res) == len(st["rows"]), (len(res), len(st["rows"]))
         kbytes = 8.0 * float(d["kmer_off"][-1])

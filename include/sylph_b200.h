@@ -152,6 +152,10 @@ int syl_genomes_has_tracked(const syl_genomes *g);
 /* Copy out: kmer_off/tracked_off have n_genomes+1 entries; any pointer may be NULL to skip. */
 int syl_genomes_download(syl_ctx *ctx, const syl_genomes *g, uint64_t *kmers, uint64_t *kmer_off,
                          uint64_t *tracked, uint64_t *tracked_off, uint64_t *gn_size);
+/* Raw device pointers of the CSR arrays (valid until syl_genomes_free), for zero-copy interop,
+ * e.g. gathering survivor sketches across GPUs with NCCL. Any out pointer may be NULL. */
+int syl_genomes_device_ptrs(const syl_genomes *g, const uint64_t **kmers, const uint64_t **kmer_off,
+                            const uint64_t **tracked, const uint64_t **tracked_off, const uint64_t **gn_size);
 void syl_genomes_free(syl_genomes *g);
 
 /* ------------------------------------------------------------------------------------------

@@ -262,6 +262,14 @@ class Db:
             pass
 
 
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier (int64 view of a device u64 array)."""
+
+    def __init__(self, ptr, n, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
 class Sample:
     """Device-resident SequencesSketch.kmer_counts (src/types.rs:145-155), sorted by hash."""
 
@@ -323,6 +331,23 @@ class Genomes:
                                                                    ("kmers", "kmer_off", "tracked", "tracked_off",
                                                                     "gn_size")]))
         return d
+
+    def device_tensors(self):
+        """Zero-copy torch views (int64) of the device CSR arrays: dict(kmers, kmer_off, tracked, tracked_off,
+        gn_size). Valid while this object is alive."""
+        import torch
+        L = _lib.lib()
+        ptrs = [C.c_void_p() for _ in range(5)]
+        _lib.check(L.syl_genomes_device_ptrs(self._h, *[C.byref(p) for p in ptrs]))
+        n = len(self)
+        sizes = (int(L.syl_genomes_total_kmers(self._h)), n + 1, int(L.syl_genomes_total_tracked(self._h)), n + 1, n)
+        out = {}
+        for name, p, sz in zip(("kmers", "kmer_off", "tracked", "tracked_off", "gn_size"), ptrs, sizes):
+            if sz == 0 or not p.value:
+                out[name] = torch.empty(0, dtype=torch.int64, device="cuda")
+            else:
+                out[name] = torch.as_tensor(_CudaArray(p.value, sz, self), device="cuda")
+        return out
 
     def free(self):
         if self._h:

@@ -814,7 +814,9 @@ int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples
     const StatParams P = make_params(&pp);
     std::vector<syl_ani_row> r1, r2, all;
     uint64_t n1 = 0;
-    SYL_TRY(contain_pass(ctx, db, P, false, S, r1, true, &n1));
+    StatParams P1 = P;
+    P1.no_ci = 1;  // pass-1 confidence intervals are never reported (pass-2 rows replace them): skip the bootstrap
+    SYL_TRY(contain_pass(ctx, db, P1, false, S, r1, true, &n1));
     if (r1.empty()) return SYL_OK;
     // the pass-1 rows (still on the device) define the winner table of every sample
     SYL_CUDA(cudaMemsetAsync(S.survivor.p, 0, S.P, st));

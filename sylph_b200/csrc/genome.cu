@@ -477,6 +477,17 @@ int syl_genomes_download(syl_ctx *ctx, const syl_genomes *g, uint64_t *kmers, ui
     return SYL_OK;
 }
 
+int syl_genomes_device_ptrs(const syl_genomes *g, const uint64_t **kmers, const uint64_t **kmer_off,
+                            const uint64_t **tracked, const uint64_t **tracked_off, const uint64_t **gn_size) {
+    if (!g) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    if (kmers) *kmers = g->kmers;
+    if (kmer_off) *kmer_off = g->kmer_off;
+    if (tracked) *tracked = g->tracked;
+    if (tracked_off) *tracked_off = g->tracked_off;
+    if (gn_size) *gn_size = g->gn_size;
+    return SYL_OK;
+}
+
 void syl_genomes_free(syl_genomes *g) {
     if (!g) return;
     cudaSetDevice(g->device);

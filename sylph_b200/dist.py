@@ -67,21 +67,53 @@ def query_sharded(ctx, db, samples, params=None):
     return merge_rows(all_gather_bytes(local))
 
 
-def gather_survivor_genomes(sub, global_ids):
-    """sub: dict from Genomes.download() of this rank's pass-1 survivors, global_ids: their global
-    genome ids. -> (merged dict, merged global ids) identical on every rank (rank order)."""
-    keys = ("kmers", "kmer_off", "tracked", "tracked_off", "gn_size")
-    parts = {k: all_gather_bytes(np.ascontiguousarray(sub[k], dtype=np.uint64)) for k in keys}
-    ids = all_gather_bytes(np.ascontiguousarray(global_ids, dtype=np.uint64))
-    out = {"kmers": np.concatenate(parts["kmers"]), "tracked": np.concatenate(parts["tracked"]),
-           "gn_size": np.concatenate(parts["gn_size"])}
+def all_gather_device(t):
+    """All-gather variable-length 1-D int64 CUDA tensors (NCCL): -> list of per-rank tensors."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    mx = max(max(sizes), 1)
+    buf = torch.zeros(mx, dtype=torch.int64, device=t.device)
+    buf[: t.numel()] = t
+    out = [torch.empty(mx, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def _merge_csr(parts):
+    """parts: per-rank dicts of arrays (numpy or torch, same kind) -> merged dict in rank order."""
+    first = parts["kmers"][0]
+    if type(first).__module__.startswith("torch"):
+        import torch
+        cat, zero = torch.cat, lambda: torch.zeros(1, dtype=torch.int64, device=first.device)
+    else:
+        cat, zero = np.concatenate, lambda: np.zeros(1, dtype=np.uint64)
+    out = {"kmers": cat(parts["kmers"]), "tracked": cat(parts["tracked"]), "gn_size": cat(parts["gn_size"])}
     for name in ("kmer_off", "tracked_off"):
-        offs, base = [np.zeros(1, dtype=np.uint64)], 0
+        offs, base = [zero()], 0
         for p in parts[name]:
-            offs.append(p[1:] + np.uint64(base))
+            offs.append(p[1:] + base)
             base += int(p[-1]) if len(p) else 0
-        out[name] = np.concatenate(offs)
-    return out, np.concatenate(ids)
+        out[name] = cat(offs)
+    return out
+
+
+def gather_survivor_genomes(sub, global_ids):
+    """sub: this rank's pass-1 survivors as a dict of CSR arrays — numpy (gloo / tests) or torch CUDA
+    int64 tensors (NCCL, stays on the device) — global_ids: their global genome ids (numpy).
+    -> (merged dict, merged global ids), identical on every rank (rank order)."""
+    keys = ("kmers", "kmer_off", "tracked", "tracked_off", "gn_size")
+    on_device = type(sub["kmers"]).__module__.startswith("torch")
+    if on_device:
+        parts = {k: all_gather_device(sub[k]) for k in keys}
+    else:
+        parts = {k: all_gather_bytes(np.ascontiguousarray(sub[k], dtype=np.uint64)) for k in keys}
+    ids = all_gather_bytes(np.ascontiguousarray(global_ids, dtype=np.uint64))
+    return _merge_csr(parts), np.concatenate(ids)
 
 
 def profile_sharded(ctx, genomes, db, samples, genome_base, params=None):
@@ -92,10 +124,19 @@ def profile_sharded(ctx, genomes, db, samples, genome_base, params=None):
     world = dist.get_world_size() if dist.is_initialized() else 1
     params = params or contain_params(pseudotax=True)
     params.pseudotax = 1
-    rows1 = ctx.query(db, samples, params)                      # pass 1 on the shard (profile ANI gate)
+    p1 = contain_params(k=params.k, pseudotax=True)
+    for f, _ in params._fields_:
+        setattr(p1, f, getattr(params, f))
+    p1.no_ci = 1                                                # pass-1 CIs are never reported
+    rows1 = ctx.query(db, samples, p1)                          # pass 1 on the shard (profile ANI gate)
     local_ids = np.unique(rows1["genome"].astype(np.int64) - int(genome_base)).astype(np.uint32)
     sub = ctx.select_genomes(genomes, local_ids)
-    merged, gids = gather_survivor_genomes(sub.download(), local_ids.astype(np.uint64) + np.uint64(genome_base))
+    on_gpu = dist.is_initialized() and dist.get_backend() == "nccl"
+    merged, gids = gather_survivor_genomes(sub.device_tensors() if on_gpu else sub.download(),
+                                           local_ids.astype(np.uint64) + np.uint64(genome_base))
+    if on_gpu:
+        import torch
+        torch.cuda.current_stream().synchronize()  # the gathered copies are complete before `sub` goes away
     sub.free()
     out = np.zeros(0, dtype=ANI_ROW_DTYPE)
     if len(gids):
