@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -156,6 +157,427 @@ __global__ void k_copy_len(const uint32_t *__restrict__ len, uint32_t *__restric
     if (i < n) count[i] = len[i];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Post-pass, primary path: MSD bucket partition + CTA-local sort + fused run-length / dedup.
+//   k_bucket_hist / k_scan_u32 / k_scatter_events : partition the events by bucket =
+//       mulhi(hash, Mb) (monotone in the hash, uniform because hashes are uniform below thr)
+//   k_group_dedup : one CTA takes the consecutive buckets whose start offset falls into
+//       [g*T, (g+1)*T) (<= GRP_CAP events), bitonic-sorts them by (hash, read) in shared memory,
+//       finds the k-mer segments and replays dup_removal_lsh_full_exact per segment
+//   k_compact_uniq : staged (hash,count) pairs -> dense arrays; buckets are monotone in the hash
+//       and every group is sorted, so the result is globally sorted without a merge.
+// Groups that do not fit (heavy-hitter k-mers, > GRP_CAP events) or whose dedup set outgrows
+// the per-thread buffer are handed to the generic radix-sort path below and merged at the end.
+struct EventRec { uint64_t hash, recflag, p0, p1; };
+static_assert(sizeof(EventRec) == 32, "EventRec is one 32-byte sector");
+
+constexpr int GRP_THREADS = 256;
+constexpr int GRP_CAP = 1024;   // most events one CTA handles in shared memory
+constexpr int GRP_T = 768;      // group span in event offsets: typical n ~ 800, leaving room for k-mers with ~200 events
+constexpr int GRP_SET = 16;     // dedup-set entries kept per k-mer before falling back
+
+__global__ void k_bucket_hist(const uint64_t *__restrict__ hash, uint64_t n, uint64_t Mb, uint32_t nbk,
+                              uint32_t *__restrict__ cnt) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t b = (uint32_t)__umul64hi(hash[i], Mb);
+    atomicAdd(&cnt[b < nbk ? b : nbk - 1], 1u);
+}
+
+// exclusive scan of n u32 values into out[0..n] (out[n] = total); single CTA, 8 values per thread
+// per trip, running carry
+__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out) {
+    constexpr int PER = 8;
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024 * PER) {
+        uint32_t v[PER], tot = 0;
+#pragma unroll
+        for (int e = 0; e < PER; e++) {
+            const uint64_t i = base + (uint64_t)tid * PER + e;
+            v[e] = i < n ? in[i] : 0u;
+            tot += v[e];
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = wsum[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += t; }
+            wsum[lane] = winc - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        uint32_t run = carry + wsum[wid] + inc - tot;
+#pragma unroll
+        for (int e = 0; e < PER; e++) {
+            const uint64_t i = base + (uint64_t)tid * PER + e;
+            if (i < n) out[i] = run;
+            run += v[e];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = run;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry_s;
+}
+
+// two-level exclusive scan for larger arrays: per-CTA local scans + block totals, a single-CTA
+// scan of the totals, then the offsets are added back
+__global__ void __launch_bounds__(1024) k_scan_local(const uint32_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out,
+                                                     uint32_t *__restrict__ block_tot) {
+    __shared__ uint32_t wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t i = (uint64_t)blockIdx.x * 1024 + tid;
+    const uint32_t v = i < n ? in[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = wsum[lane], winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += t; }
+        wsum[lane] = winc - w;
+        if (lane == 31) block_tot[blockIdx.x] = winc;
+    }
+    __syncthreads();
+    if (i < n) out[i] = wsum[wid] + inc - v;
+}
+
+__global__ void k_scan_add(uint32_t *__restrict__ out, uint64_t n, const uint32_t *__restrict__ block_off) {
+    const uint64_t i = (uint64_t)blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) out[i] += block_off[blockIdx.x];
+    if (i == n - 1) out[n] = block_off[gridDim.x];  // total
+}
+
+__global__ void k_scatter_events(const uint64_t *__restrict__ hash, const uint64_t *__restrict__ recflag,
+                                 const uint64_t *__restrict__ p0, const uint64_t *__restrict__ p1, uint64_t n,
+                                 uint64_t Mb, uint32_t nbk, const uint32_t *__restrict__ boff,
+                                 uint32_t *__restrict__ cursor, EventRec *__restrict__ part) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t h = hash[i];
+    uint32_t b = (uint32_t)__umul64hi(h, Mb);
+    if (b >= nbk) b = nbk - 1;
+    const uint32_t pos = boff[b] + atomicAdd(&cursor[b], 1u);
+    uint4 *dst = reinterpret_cast<uint4 *>(part + pos);
+    const uint64_t rf = recflag[i], a = p0[i], c = p1[i];
+    dst[0] = make_uint4((uint32_t)h, (uint32_t)(h >> 32), (uint32_t)rf, (uint32_t)(rf >> 32));
+    dst[1] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint64_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t)a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// group g = the consecutive buckets whose start offset lies in [g*T, (g+1)*T): bucket range -> g_bf / g_be
+__global__ void k_group_ranges(const uint32_t *__restrict__ boff, uint32_t nbk, uint32_t ng, uint32_t *__restrict__ g_bf,
+                               uint32_t *__restrict__ g_be) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ng) return;
+    uint32_t bf = lower_bound_u32(boff, nbk + 1, (uint64_t)g * GRP_T);
+    uint32_t be = lower_bound_u32(boff, nbk + 1, (uint64_t)(g + 1) * GRP_T);
+    if (bf > nbk) bf = nbk;
+    if (be > nbk) be = nbk;
+    if (be < bf) be = bf;
+    g_bf[g] = bf;
+    g_be[g] = be;
+}
+
+// One CTA per group (<= GRP_CAP events, consecutive buckets). Shared-memory traffic is what
+// bounds this kernel, so instead of sorting all events (a 128-bit-key bitonic sort was 4x slower)
+// it (1) groups equal hashes with an open-addressing table, (2) orders each k-mer's few events
+// by read index and replays dup_removal_lsh_full_exact, (3) sorts only the resulting unique
+// (hash, count) pairs (about n/3 single-word keys) with a bitonic network.
+constexpr int GRP_SLOTS = 2048;  // table slots (load factor <= 0.5)
+constexpr int GRP_SHORT = 8;     // k-mers with up to this many events: one thread each; longer: one warp each
+constexpr int GRP_SELECT_STEPS = 64;  // selection steps before a duplicate-heavy k-mer goes to the generic path
+
+struct GroupSmem {
+    unsigned long long ht[GRP_SLOTS];  // 16 KB  hash per slot
+    uint64_t rf[GRP_CAP];              //  8 KB  recflag per event        | after the replay: unique hashes
+    uint64_t p0[GRP_CAP];              //  8 KB  first pair key per event | after the replay: unique counts (u32)
+    uint64_t p1[GRP_CAP];              //  8 KB  second pair key per event
+    uint16_t scnt[GRP_SLOTS];          //  4 KB  events per slot, then fill cursor, then the k-mer's count
+    uint16_t soff[GRP_SLOTS + 2];      //  4 KB  exclusive scan of scnt
+    uint16_t ev_slot[GRP_CAP];         //  2 KB
+    uint16_t member[GRP_CAP];          //  2 KB  event indices grouped by slot
+    uint16_t occ[GRP_CAP];             //  2 KB  occupied slots, compacted
+    uint32_t wtot[GRP_THREADS / 32], wocc[GRP_THREADS / 32];
+    uint32_t e0, e1, overflow, dups, nuniq, nlong;
+    uint16_t longs[GRP_CAP / 2];      //  1 KB  slots of k-mers with more than GRP_SHORT events
+};
+
+__global__ void __launch_bounds__(GRP_THREADS)
+k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ boff, const uint32_t *__restrict__ g_bf,
+              const uint32_t *__restrict__ g_be, uint32_t cap,
+              int no_dedup, uint64_t *__restrict__ st_hash, uint32_t *__restrict__ st_cnt,
+              uint32_t *__restrict__ g_nuniq, uint32_t *__restrict__ g_e0, uint32_t *__restrict__ g_n,
+              uint8_t *__restrict__ g_fallback, unsigned long long *__restrict__ n_dup) {
+    extern __shared__ __align__(16) uint8_t grp_smem_raw[];
+    GroupSmem &S = *reinterpret_cast<GroupSmem *>(grp_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t g = blockIdx.x;
+    if (tid == 0) {
+        S.e0 = boff[g_bf[g]];  // boff[nbk] = N
+        S.e1 = boff[g_be[g]];
+        S.overflow = 0;
+        S.dups = 0;
+        S.nlong = 0;
+    }
+    for (int i = tid; i < GRP_SLOTS; i += GRP_THREADS) { S.ht[i] = 0xFFFFFFFFFFFFFFFFull; S.scnt[i] = 0; }
+    __syncthreads();
+    const uint32_t e0 = S.e0, n = S.e1 - S.e0;
+    if (tid == 0) { g_e0[g] = e0; g_n[g] = n; g_nuniq[g] = 0; g_fallback[g] = 0; }
+    if (n == 0) return;
+    if (n > cap) { if (tid == 0) g_fallback[g] = 1; return; }
+    // (1) stage the events, group equal hashes: slot per event, events per slot
+    for (uint32_t i = tid; i < n; i += GRP_THREADS) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(part + e0 + i);
+        const uint4 a = src[0], b = src[1];
+        const unsigned long long h = ((unsigned long long)a.y << 32) | a.x;
+        S.rf[i] = ((uint64_t)a.w << 32) | a.z;
+        S.p0[i] = ((uint64_t)b.y << 32) | b.x;
+        S.p1[i] = ((uint64_t)b.w << 32) | b.z;
+        uint32_t sl = (uint32_t)(h ^ (h >> 23)) & (GRP_SLOTS - 1);
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&S.ht[sl], 0xFFFFFFFFFFFFFFFFull, h);
+            if (prev == 0xFFFFFFFFFFFFFFFFull || prev == h) break;
+            sl = (sl + 1) & (GRP_SLOTS - 1);
+        }
+        S.ev_slot[i] = (uint16_t)sl;
+        atomicAdd(reinterpret_cast<unsigned int *>(S.scnt) + (sl >> 1), (sl & 1) ? 0x10000u : 1u);  // u16 counters, n <= 1024
+    }
+    __syncthreads();
+    // exclusive scans over the slots: events per slot -> soff, occupied slots -> occ[]
+    uint32_t nu;
+    {
+        constexpr int PER = GRP_SLOTS / GRP_THREADS;
+        uint32_t loc[PER], tot = 0, oc = 0;
+#pragma unroll
+        for (int e = 0; e < PER; e++) { loc[e] = S.scnt[tid * PER + e]; tot += loc[e]; oc += loc[e] ? 1u : 0u; }
+        uint32_t inc = tot, oinc = oc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, d), u = __shfl_up_sync(0xffffffffu, oinc, d);
+            if (lane >= d) { inc += t; oinc += u; }
+        }
+        if (lane == 31) { S.wtot[wid] = inc; S.wocc[wid] = oinc; }
+        __syncthreads();
+        uint32_t base = inc - tot, obase = oinc - oc, ototal = 0;
+#pragma unroll
+        for (int w = 0; w < GRP_THREADS / 32; w++) { if (w < wid) { base += S.wtot[w]; obase += S.wocc[w]; } ototal += S.wocc[w]; }
+        nu = ototal;
+#pragma unroll
+        for (int e = 0; e < PER; e++) {
+            S.soff[tid * PER + e] = (uint16_t)base;
+            base += loc[e];
+            if (loc[e]) S.occ[obase++] = (uint16_t)(tid * PER + e);
+        }
+        if (tid == GRP_THREADS - 1) S.soff[GRP_SLOTS] = (uint16_t)base;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < PER; e++) S.scnt[tid * PER + e] = 0;  // reused as fill cursors
+        __syncthreads();
+    }
+    for (uint32_t i = tid; i < n; i += GRP_THREADS) {
+        const uint32_t sl = S.ev_slot[i];
+        const unsigned int old = atomicAdd(reinterpret_cast<unsigned int *>(S.scnt) + (sl >> 1), (sl & 1) ? 0x10000u : 1u);
+        const uint32_t k = (sl & 1) ? (old >> 16) : (old & 0xFFFFu);
+        S.member[S.soff[sl] + k] = (uint16_t)i;
+    }
+    __syncthreads();
+    // (2) replay dup_removal_lsh_full_exact (src/sketch.rs:690-731) per k-mer; the count lands in scnt.
+    //     Short segments (<= GRP_SHORT events): one thread each (insertion sort by read index).
+    //     Longer ones are queued and taken by whole warps: the lanes hold the segment's events and
+    //     hand out the next event in read order with a warp min-reduction, so only the events up
+    //     to c == 4 are ever touched (afterwards every event counts).
+    uint32_t my_dups = 0;
+    for (uint32_t u = tid; u < nu; u += GRP_THREADS) {
+        const uint32_t sl = S.occ[u];
+        const uint32_t a0 = S.soff[sl], len = S.soff[sl + 1] - a0;
+        uint32_t c = 0;
+        if (no_dedup || len == 1) {
+            c = len;  // a first occurrence is never a duplicate (c == 0)
+        } else if (len > (uint32_t)GRP_SHORT) {
+            const uint32_t li = atomicAdd(&S.nlong, 1u);
+            S.longs[li] = (uint16_t)sl;  // at most n / (GRP_SHORT+1) < GRP_CAP/2 entries
+            continue;
+        } else {
+            uint16_t ord[GRP_SHORT];
+            for (uint32_t e = 0; e < len; e++) {  // insertion sort by (read index << 1 | no_pair)
+                const uint16_t m = S.member[a0 + e];
+                const uint64_t key = S.rf[m];
+                uint32_t q = e;
+                while (q > 0 && S.rf[ord[q - 1]] > key) { ord[q] = ord[q - 1]; q--; }
+                ord[q] = m;
+            }
+            uint64_t D[2 * GRP_SHORT];
+            uint32_t nset = 0;
+            for (uint32_t e = 0; e < len; e++) {
+                if (c >= 4u) { c += len - e; break; }  // MAX_DEDUP_COUNT (src/constants.rs:14)
+                const uint32_t m = ord[e];
+                if (S.rf[m] & NO_PAIR) { c++; continue; }
+                const uint64_t ka = S.p0[m], kb = S.p1[m];
+                bool ret = false, found = false;
+                for (uint32_t q = 0; q < nset; q++) found |= (D[q] == ka);
+                if (found) ret = c > 0; else D[nset++] = ka;
+                found = false;
+                for (uint32_t q = 0; q < nset; q++) found |= (D[q] == kb);
+                if (found) ret = ret || c > 0; else D[nset++] = kb;
+                if (ret) my_dups++; else c++;
+            }
+        }
+        S.scnt[sl] = (uint16_t)c;  // c <= len <= GRP_CAP
+    }
+    __syncthreads();
+    for (uint32_t li = wid; li < S.nlong; li += GRP_THREADS / 32) {
+        const uint32_t sl = S.longs[li];
+        const uint32_t a0 = S.soff[sl], len = S.soff[sl + 1] - a0;
+        uint32_t c = 0, done = 0, nset = 0;
+        uint64_t last_key = 0, dset = 0;  // lane q (< GRP_SET) keeps dedup-set entry q in `dset`
+        uint32_t last_m = 0;
+        bool first = true;
+        while (done < len) {
+            if (c >= 4u) { c += len - done; break; }  // MAX_DEDUP_COUNT
+            if (done >= (uint32_t)GRP_SELECT_STEPS) { if (lane == 0) S.overflow = 1; break; }  // duplicate-heavy
+            // next event after (last_key, last_m) in (read index, event index) order
+            uint64_t best = 0xFFFFFFFFFFFFFFFFull;
+            uint32_t bm = 0xFFFFFFFFu;
+            for (uint32_t e = lane; e < len; e += 32) {
+                const uint32_t m = S.member[a0 + e];
+                const uint64_t key = S.rf[m];
+                const bool after = first || key > last_key || (key == last_key && m > last_m);
+                if (after && (key < best || (key == best && m < bm))) { best = key; bm = m; }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, best, d);
+                const uint32_t om = __shfl_xor_sync(0xffffffffu, bm, d);
+                if (ok < best || (ok == best && om < bm)) { best = ok; bm = om; }
+            }
+            first = false; last_key = best; last_m = bm; done++;
+            if (best & NO_PAIR) { c++; continue; }
+            const uint64_t ka = S.p0[bm], kb = S.p1[bm];
+            const bool in_a = __any_sync(0xffffffffu, lane < (int)nset && dset == ka);
+            bool ret = in_a && c > 0;
+            if (!in_a) { if (lane == (int)nset) dset = ka; nset++; }
+            const bool in_b = __any_sync(0xffffffffu, lane < (int)nset && lane < 32 && dset == kb);
+            if (in_b) ret = ret || c > 0;
+            else { if (lane == (int)nset) dset = kb; nset++; }
+            if (nset > 32u) { if (lane == 0) S.overflow = 1; break; }
+            if (ret) { if (lane == 0) my_dups++; } else c++;
+        }
+        if (lane == 0) S.scnt[sl] = (uint16_t)c;
+    }
+    if (my_dups) atomicAdd(&S.dups, my_dups);
+    __syncthreads();
+    if (S.overflow) { if (tid == 0) g_fallback[g] = 1; return; }
+    // (3) unique pairs into the (now dead) rf / p0 arrays, sorted by hash with a bitonic network
+    uint64_t *uh = S.rf;
+    uint32_t *uc = reinterpret_cast<uint32_t *>(S.p0);
+    uint32_t P = 32;
+    while (P < nu) P <<= 1;
+    for (uint32_t i = tid; i < P; i += GRP_THREADS) {
+        if (i < nu) { const uint32_t sl = S.occ[i]; uh[i] = S.ht[sl]; uc[i] = S.scnt[sl]; }
+        else { uh[i] = 0xFFFFFFFFFFFFFFFFull; uc[i] = 0; }
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < (P >> 1); t += GRP_THREADS) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t l = i | j;
+                const bool up = (i & k) == 0;
+                const uint64_t ha = uh[i], hb = uh[l];
+                if ((ha > hb) == up) {
+                    uh[i] = hb; uh[l] = ha;
+                    const uint32_t x = uc[i]; uc[i] = uc[l]; uc[l] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = tid; i < nu; i += GRP_THREADS) { st_hash[e0 + i] = uh[i]; st_cnt[e0 + i] = uc[i]; }
+    if (tid == 0) { g_nuniq[g] = nu; if (S.dups) atomicAdd(n_dup, (unsigned long long)S.dups); }
+}
+
+// staged pairs of group g live at [e0, e0 + nuniq); dense destination starts at uoff[g]
+__global__ void k_compact_uniq(const uint64_t *__restrict__ st_hash, const uint32_t *__restrict__ st_cnt,
+                               const uint32_t *__restrict__ g_e0, const uint32_t *__restrict__ g_nuniq,
+                               const uint32_t *__restrict__ uoff, const uint8_t *__restrict__ g_fallback,
+                               const uint32_t *__restrict__ g_src, const uint64_t *__restrict__ f_hash,
+                               const uint32_t *__restrict__ f_cnt, uint64_t *__restrict__ out_hash,
+                               uint32_t *__restrict__ out_cnt) {
+    const uint32_t g = blockIdx.x, nu = g_nuniq[g], u0 = uoff[g];
+    const bool fb = g_fallback[g] != 0;
+    const uint64_t *sh = fb ? f_hash + g_src[g] : st_hash + g_e0[g];
+    const uint32_t *sc = fb ? f_cnt + g_src[g] : st_cnt + g_e0[g];
+    for (uint32_t i = threadIdx.x; i < nu; i += blockDim.x) {
+        out_hash[u0 + i] = sh[i];
+        out_cnt[u0 + i] = sc[i];
+    }
+}
+
+// The generic path returns the fallback groups' unique pairs as ONE list sorted by hash.  Groups own
+// disjoint, increasing hash ranges (bucket = mulhi(hash, Mb) is monotone), so group g's slice is
+// [lower_bound(hash >= first hash of bucket bf), lower_bound(hash >= first hash of bucket be)).
+__global__ void k_fallback_place(const uint8_t *__restrict__ g_fallback, const uint32_t *__restrict__ g_bf,
+                                 const uint32_t *__restrict__ g_be, uint32_t ng, uint32_t nbk, uint64_t Mb,
+                                 const uint64_t *__restrict__ f_hash, uint64_t fu, uint32_t *__restrict__ g_nuniq,
+                                 uint32_t *__restrict__ g_src) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ng || !g_fallback[g]) return;
+    auto first_hash_of = [&](uint32_t b) -> uint64_t {  // smallest h with mulhi(h, Mb) >= b
+        const unsigned __int128 num = ((unsigned __int128)b << 64) + (Mb - 1);
+        return (uint64_t)(num / Mb);
+    };
+    auto lb = [&](uint64_t v) -> uint64_t {
+        uint64_t lo = 0, hi = fu;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (f_hash[mid] < v) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    const uint32_t bf = g_bf[g], be = g_be[g];
+    const uint64_t a = bf == 0 ? 0 : lb(first_hash_of(bf));
+    const uint64_t b = be >= nbk ? fu : lb(first_hash_of(be));
+    g_src[g] = (uint32_t)a;
+    g_nuniq[g] = (uint32_t)(b - a);
+}
+
+// events of fallback groups -> compact SoA arrays for the generic path
+__global__ void k_gather_fallback(const EventRec *__restrict__ part, const uint32_t *__restrict__ g_e0,
+                                  const uint32_t *__restrict__ g_n, const uint8_t *__restrict__ g_fallback,
+                                  const uint32_t *__restrict__ foff, uint64_t *__restrict__ hash,
+                                  uint64_t *__restrict__ recflag, uint64_t *__restrict__ p0, uint64_t *__restrict__ p1) {
+    const uint32_t g = blockIdx.x;
+    if (!g_fallback[g]) return;
+    const uint32_t e0 = g_e0[g], n = g_n[g], f0 = foff[g];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const EventRec r = part[e0 + i];
+        hash[f0 + i] = r.hash; recflag[f0 + i] = r.recflag; p0[f0 + i] = r.p0; p1[f0 + i] = r.p1;
+    }
+}
+
+__global__ void k_fallback_sizes(const uint32_t *__restrict__ g_n, const uint8_t *__restrict__ g_fallback, uint32_t ng,
+                                 uint32_t *__restrict__ fsz) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < ng) fsz[g] = g_fallback[g] ? g_n[g] : 0u;
+}
+
 static inline unsigned nblk(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 static inline int bits_for(uint64_t maxval) {
@@ -232,54 +654,46 @@ struct SampleBuilder {
         return SYL_OK;
     }
 
-    int finish(syl_sample **out) {
+    // Generic path: two stable LSD radix sorts (read index, then hash) + run-length encode +
+    // k_dedup.  Handles any segment length in linear time; used for the groups the primary
+    // path hands over (and for everything when SYL_SAMPLE_POSTPASS=sort).
+    int dedup_sorted(const uint64_t *ev_hash, const uint64_t *ev_recflag, const uint64_t *ev_p0, const uint64_t *ev_p1,
+                     uint64_t N, DevBuf<uint64_t> &uniq, DevBuf<uint32_t> &count, uint64_t *U_out, uint64_t *ndup_out) {
         cudaStream_t st = ctx->stream;
-        syl_sample *s = new (std::nothrow) syl_sample();
-        if (!s) return SYL_ERR_OOM;
-        s->device = ctx->device;
-        s->stream = ctx->stream;
-        s->k = k;
-        s->c = c;
-        s->mean_read_length = n_reads ? (double)n_bases / (double)n_reads : 0.;
-        const uint64_t N = n_events;
-        if (N == 0) { *out = s; return SYL_OK; }
-        if (N >= 0xFFFFFFFFull) { delete s; set_error("more than 2^32-2 survivor events in one sample"); return SYL_ERR_ARG; }
-
-        // -- order events by (hash, read): sort by read first, then stable sort by hash
+        *U_out = 0;
+        *ndup_out = 0;
+        if (N == 0) return SYL_OK;
         DevBuf<uint32_t> idx_a, idx_b;
         DevBuf<uint64_t> key_a, key_b;
         SYL_TRY(idx_a.alloc(N, st)); SYL_TRY(idx_b.alloc(N, st));
         SYL_TRY(key_a.alloc(N, st)); SYL_TRY(key_b.alloc(N, st));
         k_iota<<<nblk(N, 256), 256, 0, st>>>(idx_a.p, N);
         ctx->launches++;
-        const uint64_t thr = fmh_threshold(c);
-        const int hash_bits = bits_for(thr);
+        const int hash_bits = bits_for(fmh_threshold(c));
         DevBuf<uint8_t> tmp;
         size_t tmp_bytes = 0, t2 = 0;
         uint32_t *ord = idx_a.p;  // final event order
         uint64_t *hs = key_a.p;   // hashes in final order
         if (!no_dedup) {
             const int rec_bits = bits_for((n_reads << 1) | 1);
-            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, recflag, key_b.p, idx_a.p, idx_b.p, N, 0, rec_bits, st);
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ev_recflag, key_b.p, idx_a.p, idx_b.p, N, 0, rec_bits, st);
             cub::DeviceRadixSort::SortPairs(nullptr, t2, key_a.p, key_b.p, idx_b.p, idx_a.p, N, 0, hash_bits, st);
             tmp_bytes = std::max(tmp_bytes, t2);
             SYL_TRY(tmp.alloc(tmp_bytes, st));
-            SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, recflag, key_b.p, idx_a.p, idx_b.p, N, 0, rec_bits, st));
-            k_gather<uint64_t><<<nblk(N, 256), 256, 0, st>>>(hash, idx_b.p, key_a.p, N);
+            SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ev_recflag, key_b.p, idx_a.p, idx_b.p, N, 0, rec_bits, st));
+            k_gather<uint64_t><<<nblk(N, 256), 256, 0, st>>>(ev_hash, idx_b.p, key_a.p, N);
             SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_a.p, key_b.p, idx_b.p, idx_a.p, N, 0, hash_bits, st));
-            ctx->launches += 2 + 2 * 8;
+            ctx->launches += 3;
             hs = key_b.p;
             ord = idx_a.p;
         } else {
-            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, hash, key_b.p, N, 0, hash_bits, st);
+            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ev_hash, key_b.p, N, 0, hash_bits, st);
             SYL_TRY(tmp.alloc(tmp_bytes, st));
-            SYL_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, hash, key_b.p, N, 0, hash_bits, st));
-            ctx->launches += 8;
+            SYL_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, ev_hash, key_b.p, N, 0, hash_bits, st));
+            ctx->launches += 1;
             hs = key_b.p;
         }
-
-        // -- segments = distinct hashes
-        DevBuf<uint64_t> uniq, seg_off;
+        DevBuf<uint64_t> seg_off;
         DevBuf<uint32_t> seg_len;
         SYL_TRY(uniq.alloc(N, st)); SYL_TRY(seg_off.alloc(N + 1, st)); SYL_TRY(seg_len.alloc(N, st));
         uint64_t *d_nruns = ctx->d_counters + 1;
@@ -293,13 +707,10 @@ struct SampleBuilder {
         SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 1, d_nruns, 8, cudaMemcpyDeviceToHost, st));
         SYL_CUDA(cudaStreamSynchronize(st));
         const uint64_t U = ctx->h_counters[1];
-        ctx->launches += 2;
-        SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(U, 1) * 8, st));
-        SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(U, 1) * 4, st));
-        SYL_CUDA(cudaMemcpyAsync(s->hash, uniq.p, U * 8, cudaMemcpyDeviceToDevice, st));
-        s->n = U;
+        ctx->launches += 1;
+        SYL_TRY(count.alloc(std::max<uint64_t>(U, 1), st));
         if (no_dedup) {
-            k_copy_len<<<nblk(U, 256), 256, 0, st>>>(seg_len.p, s->count, U);
+            k_copy_len<<<nblk(U, 256), 256, 0, st>>>(seg_len.p, count.p, U);
             ctx->launches++;
         } else {
             tb = std::max(rle_bytes, scan_bytes);
@@ -308,14 +719,126 @@ struct SampleBuilder {
             SYL_TRY(set.alloc(2 * N, st));
             unsigned long long *d_ndup = reinterpret_cast<unsigned long long *>(ctx->d_counters + 2);
             SYL_CUDA(cudaMemsetAsync(d_ndup, 0, 8, st));
-            k_dedup<<<nblk(U, 128), 128, 0, st>>>(seg_off.p, seg_len.p, U, ord, recflag, p0, p1, set.p, s->count, d_ndup);
+            k_dedup<<<nblk(U, 128), 128, 0, st>>>(seg_off.p, seg_len.p, U, ord, ev_recflag, ev_p0, ev_p1, set.p, count.p, d_ndup);
             ctx->launches += 2;
             SYL_CUDA(cudaGetLastError());
             SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 2, d_ndup, 8, cudaMemcpyDeviceToHost, st));
             SYL_CUDA(cudaStreamSynchronize(st));
-            s->num_dup_removed = ctx->h_counters[2];
+            *ndup_out = ctx->h_counters[2];
         }
+        *U_out = U;
+        return SYL_OK;
+    }
+
+    int finish(syl_sample **out) {
+        cudaStream_t st = ctx->stream;
+        syl_sample *s = new (std::nothrow) syl_sample();
+        if (!s) return SYL_ERR_OOM;
+        s->device = ctx->device;
+        s->stream = ctx->stream;
+        s->k = k;
+        s->c = c;
+        s->mean_read_length = n_reads ? (double)n_bases / (double)n_reads : 0.;
+        const uint64_t N = n_events;
+        if (N == 0) { *out = s; return SYL_OK; }
+        if (N >= 0xFFFFFFFFull) { delete s; set_error("more than 2^32-2 survivor events in one sample"); return SYL_ERR_ARG; }
+        static const bool force_sort = []() { const char *e = getenv("SYL_SAMPLE_POSTPASS"); return e && std::string(e) == "sort"; }();
+        static const uint32_t grp_cap = []() { const char *e = getenv("SYL_GROUP_CAP"); int v = e ? atoi(e) : GRP_CAP; return (uint32_t)std::min(std::max(v, 32), GRP_CAP); }();
+        auto fail = [&](int rc) { syl_sample_free(s); return rc; };
+        int rc;
+        if (force_sort) {
+            DevBuf<uint64_t> uq;
+            DevBuf<uint32_t> ct;
+            uint64_t U = 0, nd = 0;
+            if ((rc = dedup_sorted(hash, recflag, p0, p1, N, uq, ct, &U, &nd)) != SYL_OK) return fail(rc);
+            SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(U, 1) * 8, st));
+            SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(U, 1) * 4, st));
+            SYL_CUDA(cudaMemcpyAsync(s->hash, uq.p, U * 8, cudaMemcpyDeviceToDevice, st));
+            SYL_CUDA(cudaMemcpyAsync(s->count, ct.p, U * 4, cudaMemcpyDeviceToDevice, st));
+            SYL_CUDA(cudaStreamSynchronize(st));
+            s->n = U;
+            s->num_dup_removed = nd;
+            *out = s;
+            return SYL_OK;
+        }
+        // ---- primary path: bucket partition + CTA-local sort/dedup
+        uint32_t nbk = 4096;
+        while (nbk < N / 32 && nbk < (1u << 22)) nbk <<= 1;
+        const uint64_t thr = fmh_threshold(c);
+        unsigned __int128 mb = ((unsigned __int128)nbk << 64) / ((unsigned __int128)thr + 1);
+        const uint64_t Mb = mb > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)mb;
+        const uint32_t ng = (uint32_t)(N / GRP_T + 1);
+        DevBuf<uint32_t> cnt, boff, cursor, st_cnt, g_nuniq, g_e0, g_n, uoff, fsz, foff, g_bf, g_be, g_src;
+        DevBuf<uint64_t> st_hash;
+        DevBuf<uint8_t> g_fb;
+        DevBuf<EventRec> part;
+        if ((rc = cnt.alloc(nbk, st)) || (rc = boff.alloc((uint64_t)nbk + 1, st)) || (rc = cursor.alloc(nbk, st)) ||
+            (rc = part.alloc(N, st)) || (rc = st_hash.alloc(N, st)) || (rc = st_cnt.alloc(N, st)) ||
+            (rc = g_nuniq.alloc(ng, st)) || (rc = g_e0.alloc(ng, st)) || (rc = g_n.alloc(ng, st)) ||
+            (rc = g_fb.alloc(ng, st)) || (rc = uoff.alloc((uint64_t)ng + 1, st)) || (rc = fsz.alloc(ng, st)) ||
+            (rc = foff.alloc((uint64_t)ng + 1, st)) || (rc = g_bf.alloc(ng, st)) || (rc = g_be.alloc(ng, st)) ||
+            (rc = g_src.alloc(ng, st)))
+            return fail(rc);
+        unsigned long long *d_ndup = reinterpret_cast<unsigned long long *>(ctx->d_counters + 2);
+        SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, st));
+        SYL_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)nbk * 4, st));
+        SYL_CUDA(cudaMemsetAsync(d_ndup, 0, 8, st));
+        k_bucket_hist<<<nblk(N, 256), 256, 0, st>>>(hash, N, Mb, nbk, cnt.p);
+        {   // boff = exclusive scan of cnt (nbk >= 4096 entries): local scans, scan of block totals, add back
+            const uint32_t nblk1 = nbk / 1024;
+            DevBuf<uint32_t> btot, boff2;
+            if ((rc = btot.alloc(nblk1, st)) || (rc = boff2.alloc((uint64_t)nblk1 + 1, st))) return fail(rc);
+            k_scan_local<<<nblk1, 1024, 0, st>>>(cnt.p, nbk, boff.p, btot.p);
+            k_scan_u32<<<1, 1024, 0, st>>>(btot.p, nblk1, boff2.p);
+            k_scan_add<<<nblk1, 1024, 0, st>>>(boff.p, nbk, boff2.p);
+            ctx->launches += 2;
+        }
+        k_scatter_events<<<nblk(N, 256), 256, 0, st>>>(hash, recflag, p0, p1, N, Mb, nbk, boff.p, cursor.p, part.p);
+        SYL_CUDA(cudaFuncSetAttribute(k_group_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+        k_group_ranges<<<nblk(ng, 256), 256, 0, st>>>(boff.p, nbk, ng, g_bf.p, g_be.p);
+        k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, no_dedup, st_hash.p, st_cnt.p,
+                                                                   g_nuniq.p, g_e0.p, g_n.p, g_fb.p, d_ndup);
+        k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
+        k_fallback_sizes<<<nblk(ng, 256), 256, 0, st>>>(g_n.p, g_fb.p, ng, fsz.p);
+        k_scan_u32<<<1, 1024, 0, st>>>(fsz.p, ng, foff.p);
+        ctx->launches += 7;
+        SYL_CUDA(cudaGetLastError());
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 1, uoff.p + ng, 4, cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, foff.p + ng, 4, cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 2, d_ndup, 8, cudaMemcpyDeviceToHost, st));
         SYL_CUDA(cudaStreamSynchronize(st));
+        const uint64_t U1 = (uint32_t)ctx->h_counters[1], NF = (uint32_t)ctx->h_counters[3];
+        uint64_t ndup = ctx->h_counters[2];
+        static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
+        if (dbg) fprintf(stderr, "[sample post-pass] events %llu buckets %u groups %u: in-kernel uniques %llu, events handed to the generic path %llu (%.1f %%)\n",
+                         (unsigned long long)N, nbk, ng, (unsigned long long)U1, (unsigned long long)NF, 100.0 * NF / N);
+        // fallback groups through the generic path
+        DevBuf<uint64_t> fh, f_rf, f_p0, f_p1, f_uq;
+        DevBuf<uint32_t> f_ct;
+        uint64_t U2 = 0, nd2 = 0;
+        if (NF) {
+            if ((rc = fh.alloc(NF, st)) || (rc = f_rf.alloc(NF, st)) || (rc = f_p0.alloc(NF, st)) || (rc = f_p1.alloc(NF, st)))
+                return fail(rc);
+            k_gather_fallback<<<ng, 256, 0, st>>>(part.p, g_e0.p, g_n.p, g_fb.p, foff.p, fh.p, f_rf.p, f_p0.p, f_p1.p);
+            ctx->launches++;
+            if ((rc = dedup_sorted(fh.p, f_rf.p, f_p0.p, f_p1.p, NF, f_uq, f_ct, &U2, &nd2)) != SYL_OK) return fail(rc);
+            ndup += nd2;
+        }
+        const uint64_t U = U1 + U2;
+        SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(U, 1) * 8, st));
+        SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(U, 1) * 4, st));
+        if (U2) {  // slot the generic path's pairs into their groups' positions and redo the output offsets
+            k_fallback_place<<<nblk(ng, 128), 128, 0, st>>>(g_fb.p, g_bf.p, g_be.p, ng, nbk, Mb, f_uq.p, U2, g_nuniq.p, g_src.p);
+            k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
+            ctx->launches += 2;
+        }
+        k_compact_uniq<<<ng, 128, 0, st>>>(st_hash.p, st_cnt.p, g_e0.p, g_nuniq.p, uoff.p, g_fb.p, g_src.p, f_uq.p, f_ct.p,
+                                            s->hash, s->count);
+        ctx->launches++;
+        SYL_CUDA(cudaGetLastError());
+        SYL_CUDA(cudaStreamSynchronize(st));
+        s->n = U;
+        s->num_dup_removed = ndup;
         *out = s;
         return SYL_OK;
     }
