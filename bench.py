@@ -243,15 +243,34 @@ def bench_sketch(args, ctx, rank, world, local):
         state["n"] = len(s)
         s.free()
 
-    for _ in range(args.warmup):
+    # clocks are sampled from before the warm-up to the end of the timed region: nvidia-smi needs ~100 ms to
+    # start and its first query can stall the GPU, so neither may fall inside the (tens of ms) timed region;
+    # the warm-up keeps the same load running for >= 0.5 s so that the samples are taken under load
+    clocks = ClockSampler(local)
+    clocks.start()
+    # ... and until the device has settled: a freshly started process on an idle GPU shows sporadic
+    # 30-500 ms stalls in its first seconds (clock ramp / driver housekeeping, also seen with no sampler);
+    # the untimed warm-up therefore runs until 40 consecutive steps stay within 1.5x of the fastest step
+    # (bounded by 8 s), always at least W steps and 0.5 s
+    t_w = time.perf_counter()
+    n_w, calm, best = 0, 0, float("inf")
+    while True:
+        a = time.perf_counter()
         step_resident()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - a
+        n_w += 1
+        best = min(best, dt)
+        calm = calm + 1 if dt < 1.5 * best else 0
+        el = time.perf_counter() - t_w
+        if n_w >= args.warmup and el >= 0.5 and (calm >= 40 or el > 8.0):
+            break
     ctx.enable_timing(True)
     ctx.seed_kernel_time(reset=True)
     l0 = ctx.launches
-    clocks = ClockSampler(local)
-    clocks.start()
     ms, _ = timed(step_resident, args.steps, world)
     clk = clocks.stop()
+    clk["warmup_steps_run"] = n_w
     launches = ctx.launches - l0
     kms, klaunch, kbases = ctx.seed_kernel_time(reset=True)
     ctx.enable_timing(False)

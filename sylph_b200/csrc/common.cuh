@@ -77,6 +77,7 @@ struct syl_sample {
 // Device-resident batch of GenomeSketch (src/types.rs:163-173) in CSR form
 struct syl_genomes {
     int device = 0;
+    cudaStream_t stream = nullptr;  // arrays are stream-ordered allocations of this stream
     uint64_t n = 0;                                       // genomes
     uint64_t *kmers = nullptr, *kmer_off = nullptr;       // genome_kmers, position order
     uint64_t *tracked = nullptr, *tracked_off = nullptr;  // pseudotax_tracked_nonused_kmers

@@ -181,12 +181,14 @@ __global__ void k_copy_ranges(const uint64_t *__restrict__ src4, const uint64_t 
     for (uint64_t j = threadIdx.x; j < nt; j += blockDim.x) otracked[dt + j] = tracked[st + j];
 }
 
-static int genomes_alloc(syl_genomes *g, uint64_t n_genomes, uint64_t nk, uint64_t nt) {
-    SYL_CUDA(cudaMalloc((void **)&g->kmers, std::max<uint64_t>(nk, 1) * 8));
-    SYL_CUDA(cudaMalloc((void **)&g->tracked, std::max<uint64_t>(nt, 1) * 8));
-    SYL_CUDA(cudaMalloc((void **)&g->kmer_off, (n_genomes + 1) * 8));
-    SYL_CUDA(cudaMalloc((void **)&g->tracked_off, (n_genomes + 1) * 8));
-    SYL_CUDA(cudaMalloc((void **)&g->gn_size, std::max<uint64_t>(n_genomes, 1) * 8));
+// stream-ordered allocations on the creating ctx stream (no device-wide sync in steady-state loops)
+static int genomes_alloc(syl_genomes *g, cudaStream_t st, uint64_t n_genomes, uint64_t nk, uint64_t nt) {
+    g->stream = st;
+    SYL_CUDA(cudaMallocAsync((void **)&g->kmers, std::max<uint64_t>(nk, 1) * 8, st));
+    SYL_CUDA(cudaMallocAsync((void **)&g->tracked, std::max<uint64_t>(nt, 1) * 8, st));
+    SYL_CUDA(cudaMallocAsync((void **)&g->kmer_off, (n_genomes + 1) * 8, st));
+    SYL_CUDA(cudaMallocAsync((void **)&g->tracked_off, (n_genomes + 1) * 8, st));
+    SYL_CUDA(cudaMallocAsync((void **)&g->gn_size, std::max<uint64_t>(n_genomes, 1) * 8, st));
     g->n = n_genomes;
     g->total_kmers = nk;
     g->total_tracked = nt;
@@ -263,7 +265,7 @@ int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases
     }
     out->has_tracked = pseudotax ? 1 : 0;
     if (!pseudotax) total_tracked = 0;
-    SYL_TRY(genomes_alloc(out, n_genomes, total_kept, total_tracked));
+    SYL_TRY(genomes_alloc(out, st, n_genomes, total_kept, total_tracked));
     if (N) {
         k_scatter_flagged<<<nblk(N, 256), 256, 0, st>>>(hash_b.p, flag.p, N, scan_k.p, scan_t.p, out->kmers,
                                                          pseudotax ? out->tracked : nullptr);
@@ -359,7 +361,7 @@ int syl_genomes_upload(syl_ctx *ctx, int mem, const uint64_t *kmers, const uint6
     if (!g) return SYL_ERR_OOM;
     g->device = ctx->device; g->k = k; g->c = c;
     g->has_tracked = (tracked && tracked_off) ? 1 : 0;
-    int rc = genomes_alloc(g, n_genomes, nk, nt);
+    int rc = genomes_alloc(g, st, n_genomes, nk, nt);
     if (rc != SYL_OK) { syl_genomes_free(g); return rc; }
     if (nk) SYL_CUDA(cudaMemcpyAsync(g->kmers, kmers, nk * 8, kind, st));
     SYL_CUDA(cudaMemcpyAsync(g->kmer_off, kmer_off, (n_genomes + 1) * 8, kind, st));
@@ -394,7 +396,7 @@ int syl_genomes_concat(syl_ctx *ctx, const syl_genomes *const *parts, uint32_t n
     if (!g) return SYL_ERR_OOM;
     g->device = ctx->device;
     if (n_parts) { g->k = parts[0]->k; g->c = parts[0]->c; g->has_tracked = parts[0]->has_tracked; }
-    int rc = genomes_alloc(g, G, nk, nt);
+    int rc = genomes_alloc(g, st, G, nk, nt);
     if (rc != SYL_OK) { syl_genomes_free(g); return rc; }
     uint64_t g0 = 0, k0 = 0, t0 = 0;
     for (uint32_t i = 0; i < n_parts; i++) {
@@ -439,7 +441,7 @@ int syl_genomes_select(syl_ctx *ctx, const syl_genomes *g, const uint32_t *idx, 
     syl_genomes *o = new (std::nothrow) syl_genomes();
     if (!o) return SYL_ERR_OOM;
     o->device = ctx->device; o->k = g->k; o->c = g->c; o->has_tracked = g->has_tracked;
-    int rc = genomes_alloc(o, n, nko[n], nto[n]);
+    int rc = genomes_alloc(o, st, n, nko[n], nto[n]);
     if (rc != SYL_OK) { syl_genomes_free(o); return rc; }
     DevBuf<uint64_t> d_src;
     if ((rc = d_src.alloc(4 * (uint64_t)std::max<uint32_t>(n, 1), st)) != SYL_OK) { syl_genomes_free(o); return rc; }
@@ -491,11 +493,12 @@ int syl_genomes_device_ptrs(const syl_genomes *g, const uint64_t **kmers, const 
 void syl_genomes_free(syl_genomes *g) {
     if (!g) return;
     cudaSetDevice(g->device);
-    if (g->kmers) cudaFree(g->kmers);
-    if (g->kmer_off) cudaFree(g->kmer_off);
-    if (g->tracked) cudaFree(g->tracked);
-    if (g->tracked_off) cudaFree(g->tracked_off);
-    if (g->gn_size) cudaFree(g->gn_size);
+    // stream-ordered free on the creating ctx stream (free handles before destroying their ctx)
+    if (g->kmers) cudaFreeAsync(g->kmers, g->stream);
+    if (g->kmer_off) cudaFreeAsync(g->kmer_off, g->stream);
+    if (g->tracked) cudaFreeAsync(g->tracked, g->stream);
+    if (g->tracked_off) cudaFreeAsync(g->tracked_off, g->stream);
+    if (g->gn_size) cudaFreeAsync(g->gn_size, g->stream);
     delete g;
 }
 
