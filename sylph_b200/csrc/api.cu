@@ -8,6 +8,7 @@
 namespace syl {
 
 static thread_local std::string g_last_error;
+thread_local syl_ctx *tl_ctx = nullptr;
 void set_error(const std::string &msg) { g_last_error = msg; }
 
 int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
@@ -88,6 +89,9 @@ void syl_ctx_destroy(syl_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->free_blocks) cudaFree(b.first);
+    ctx->free_blocks.clear();
+    if (syl::tl_ctx == ctx) syl::tl_ctx = nullptr;
     for (int i = 0; i < 2; i++) {
         if (ctx->stage_b[i]) cudaFree(ctx->stage_b[i]);
         if (ctx->stage_o[i]) cudaFree(ctx->stage_o[i]);
@@ -114,6 +118,7 @@ uint64_t syl_ctx_launch_count(const syl_ctx *ctx) { return ctx ? ctx->launches :
 int syl_ctx_enable_timing(syl_ctx *ctx, int on) {
     if (!ctx) { set_error("ctx is NULL"); return SYL_ERR_ARG; }
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     if (on && !ctx->ev0) {
         SYL_CUDA(cudaEventCreate(&ctx->ev0));
         SYL_CUDA(cudaEventCreate(&ctx->ev1));
@@ -139,6 +144,7 @@ int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases
         return SYL_ERR_ARG;
     }
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     Staged<uint8_t> sb;
     Staged<uint64_t> so;
     SYL_TRY(sb.init(ctx, mem, bases, n_bases));

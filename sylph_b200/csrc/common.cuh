@@ -2,10 +2,14 @@
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/sylph_b200.h"
 
@@ -59,7 +63,18 @@ struct syl_ctx {
     uint8_t *stage_b[2] = {nullptr, nullptr};
     uint64_t *stage_o[2] = {nullptr, nullptr};
     uint64_t stage_cap_b[2] = {0, 0}, stage_cap_o[2] = {0, 0};
+    // grow-only cache of scratch blocks: all work of a ctx is ordered on ONE stream, so a block can
+    // be handed to the next user as soon as the previous user's kernels are enqueued; steady-state
+    // calls then make no allocator calls at all (the CUDA allocators take driver-wide locks and
+    // showed 30-500 ms stalls on shared hosts)
+    std::vector<std::pair<void *, size_t>> free_blocks;
+    size_t cached_bytes = 0;
 };
+
+namespace syl {
+// ctx whose scratch cache DevBuf uses on this thread (set at every API entry)
+extern thread_local syl_ctx *tl_ctx;
+}
 
 // Device-resident SequencesSketch.kmer_counts (src/types.rs:145-155): parallel arrays sorted by hash
 struct syl_sample {
@@ -94,7 +109,7 @@ namespace syl {
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap_bytes = 0;
     cudaStream_t s = nullptr;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
@@ -104,26 +119,43 @@ struct DevBuf {
         release();
         s = stream;
         n = count;
-        if (count == 0) count = 1;
-        cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), stream);
+        size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+        syl_ctx *c = tl_ctx;
+        if (c) {  // best fit from the ctx cache
+            size_t best = (size_t)-1, bi = 0;
+            for (size_t i = 0; i < c->free_blocks.size(); i++) {
+                const size_t sz = c->free_blocks[i].second;
+                if (sz >= bytes && sz < best) { best = sz; bi = i; }
+            }
+            if (best != (size_t)-1 && best <= 2 * bytes + (1u << 20)) {
+                p = reinterpret_cast<T *>(c->free_blocks[bi].first);
+                cap_bytes = best;
+                c->free_blocks[bi] = c->free_blocks.back();
+                c->free_blocks.pop_back();
+                return SYL_OK;
+            }
+        }
+        cudaError_t e = cudaMalloc((void **)&p, bytes);
         if (e != cudaSuccess) {
             p = nullptr;
-            set_error(std::string("cudaMallocAsync(") + std::to_string(count * sizeof(T)) +
-                      " B): " + cudaGetErrorString(e));
+            set_error(std::string("cudaMalloc(") + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
             return e == cudaErrorMemoryAllocation ? SYL_ERR_OOM : SYL_ERR_CUDA;
         }
+        cap_bytes = bytes;
+        if (c) c->cached_bytes += bytes;
         return SYL_OK;
     }
-    void release() {
-        if (p) cudaFreeAsync(p, s);
-        p = nullptr;
-        n = 0;
+    void swap(DevBuf &o) {
+        std::swap(p, o.p); std::swap(n, o.n); std::swap(cap_bytes, o.cap_bytes); std::swap(s, o.s);
     }
-    T *take() {
-        T *q = p;
+    void release() {
+        if (p) {
+            syl_ctx *c = tl_ctx;
+            if (c) c->free_blocks.emplace_back((void *)p, cap_bytes);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
-        return q;
     }
 };
 

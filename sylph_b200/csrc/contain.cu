@@ -696,6 +696,7 @@ int syl_db_build(syl_ctx *ctx, const syl_genomes *g, uint32_t genome_base, syl_d
     if (!ctx || !g || !out) { set_error("NULL argument"); return SYL_ERR_ARG; }
     *out = nullptr;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
     const uint64_t nk = g->total_kmers, nt = g->has_tracked ? g->total_tracked : 0, N = nk + nt;
     if (N >= 0xFFFFFFFFull) { set_error("db shard holds more than 2^32-2 k-mers; shard the database"); return SYL_ERR_ARG; }
@@ -786,6 +787,7 @@ int syl_query(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, 
     SYL_TRY(check_pair_args(ctx, db, samples, n_samples, p, rows, cap, n_rows));
     *n_rows = 0;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
     ContainScratch S;
     SYL_TRY(scratch_init(ctx, db, samples, n_samples, false, S));
@@ -807,6 +809,7 @@ int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples
         return SYL_ERR_ARG;
     }
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
     cudaStream_t st = ctx->stream;
     ContainScratch S;

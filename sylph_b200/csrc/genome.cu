@@ -298,6 +298,7 @@ int syl_sketch_genomes(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_b
     if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
     *out = nullptr;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
     DevBuf<uint8_t> hb;
     DevBuf<uint64_t> hc, hg;
@@ -344,6 +345,7 @@ int syl_genomes_upload(syl_ctx *ctx, int mem, const uint64_t *kmers, const uint6
     if (!ctx || !out || !kmer_off) { set_error("NULL argument"); return SYL_ERR_ARG; }
     *out = nullptr;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
     cudaMemcpyKind kind = mem == SYL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     uint64_t nk = 0, nt = 0;
@@ -382,6 +384,7 @@ int syl_genomes_concat(syl_ctx *ctx, const syl_genomes *const *parts, uint32_t n
     if (!ctx || !out || (n_parts && !parts)) { set_error("NULL argument"); return SYL_ERR_ARG; }
     *out = nullptr;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
     uint64_t G = 0, nk = 0, nt = 0;
     for (uint32_t i = 0; i < n_parts; i++) {
@@ -423,6 +426,7 @@ int syl_genomes_select(syl_ctx *ctx, const syl_genomes *g, const uint32_t *idx, 
     if (!ctx || !g || !out || (n && !idx)) { set_error("NULL argument"); return SYL_ERR_ARG; }
     *out = nullptr;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
     std::vector<uint64_t> koff(g->n + 1), toff(g->n + 1), gs(std::max<uint64_t>(g->n, 1));
     SYL_CUDA(cudaMemcpyAsync(koff.data(), g->kmer_off, (g->n + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -469,6 +473,7 @@ int syl_genomes_download(syl_ctx *ctx, const syl_genomes *g, uint64_t *kmers, ui
                          uint64_t *tracked, uint64_t *tracked_off, uint64_t *gn_size) {
     if (!ctx || !g) { set_error("NULL argument"); return SYL_ERR_ARG; }
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
     if (kmers && g->total_kmers) SYL_CUDA(cudaMemcpyAsync(kmers, g->kmers, g->total_kmers * 8, cudaMemcpyDeviceToHost, st));
     if (kmer_off) SYL_CUDA(cudaMemcpyAsync(kmer_off, g->kmer_off, (g->n + 1) * 8, cudaMemcpyDeviceToHost, st));

@@ -593,35 +593,23 @@ struct SampleBuilder {
     uint64_t c;
     int no_dedup, sem;
     uint64_t n_reads = 0, n_bases = 0, n_events = 0, cap = 0;
+    DevBuf<uint64_t> b_hash, b_rf, b_p0, b_p1;  // event arrays (scratch blocks of the ctx cache)
     uint64_t *hash = nullptr, *recflag = nullptr, *p0 = nullptr, *p1 = nullptr;
 
-    ~SampleBuilder() { release(); }
-    void release() {
-        cudaStream_t st = ctx->stream;
-        if (hash) cudaFreeAsync(hash, st);
-        if (recflag) cudaFreeAsync(recflag, st);
-        if (p0) cudaFreeAsync(p0, st);
-        if (p1) cudaFreeAsync(p1, st);
-        hash = recflag = p0 = p1 = nullptr;
-        cap = 0;
-    }
     int reserve(uint64_t need) {
         if (need <= cap) return SYL_OK;
-        uint64_t ncap = std::max<uint64_t>(need, cap * 2);
+        const uint64_t ncap = std::max<uint64_t>(need, cap * 2);
         cudaStream_t st = ctx->stream;
-        uint64_t *nh, *nr, *n0, *n1;
-        SYL_CUDA(cudaMallocAsync((void **)&nh, ncap * 8, st));
-        SYL_CUDA(cudaMallocAsync((void **)&nr, ncap * 8, st));
-        SYL_CUDA(cudaMallocAsync((void **)&n0, ncap * 8, st));
-        SYL_CUDA(cudaMallocAsync((void **)&n1, ncap * 8, st));
+        DevBuf<uint64_t> nh, nr, n0, n1;
+        SYL_TRY(nh.alloc(ncap, st)); SYL_TRY(nr.alloc(ncap, st)); SYL_TRY(n0.alloc(ncap, st)); SYL_TRY(n1.alloc(ncap, st));
         if (n_events) {
-            SYL_CUDA(cudaMemcpyAsync(nh, hash, n_events * 8, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaMemcpyAsync(nr, recflag, n_events * 8, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaMemcpyAsync(n0, p0, n_events * 8, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaMemcpyAsync(n1, p1, n_events * 8, cudaMemcpyDeviceToDevice, st));
+            SYL_CUDA(cudaMemcpyAsync(nh.p, hash, n_events * 8, cudaMemcpyDeviceToDevice, st));
+            SYL_CUDA(cudaMemcpyAsync(nr.p, recflag, n_events * 8, cudaMemcpyDeviceToDevice, st));
+            SYL_CUDA(cudaMemcpyAsync(n0.p, p0, n_events * 8, cudaMemcpyDeviceToDevice, st));
+            SYL_CUDA(cudaMemcpyAsync(n1.p, p1, n_events * 8, cudaMemcpyDeviceToDevice, st));
         }
-        release();
-        hash = nh; recflag = nr; p0 = n0; p1 = n1;
+        b_hash.swap(nh); b_rf.swap(nr); b_p0.swap(n0); b_p1.swap(n1);  // the old blocks go back to the cache
+        hash = b_hash.p; recflag = b_rf.p; p0 = b_p0.p; p1 = b_p1.p;
         cap = ncap;
         return SYL_OK;
     }
@@ -857,6 +845,7 @@ int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bas
     if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
     *out = nullptr;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     SampleBuilder b{ctx, k, c, no_dedup, sem};
     cudaStream_t st = ctx->stream;
     if (mem == SYL_MEM_DEVICE) {
@@ -945,6 +934,7 @@ int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_
     if (!ctx || !out || (n && (!hash || !count))) { set_error("NULL argument"); return SYL_ERR_ARG; }
     *out = nullptr;
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
     syl_sample *s = new (std::nothrow) syl_sample();
     if (!s) return SYL_ERR_OOM;
@@ -977,6 +967,7 @@ uint64_t syl_sample_num_dup_removed(const syl_sample *s) { return s ? s->num_dup
 int syl_sample_download(syl_ctx *ctx, const syl_sample *s, uint64_t *hash, uint32_t *count) {
     if (!ctx || !s) { set_error("NULL argument"); return SYL_ERR_ARG; }
     SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
     if (s->n && hash) SYL_CUDA(cudaMemcpyAsync(hash, s->hash, s->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (s->n && count) SYL_CUDA(cudaMemcpyAsync(count, s->count, s->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SYL_CUDA(cudaStreamSynchronize(ctx->stream));
