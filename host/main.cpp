@@ -313,8 +313,24 @@ static int cmd_contain(syl_ctx *ctx, const Args &a, bool pseudotax) {
     return 0;
 }
 
+// fastx-stats: parser self-check without a GPU (records, bases, first id, FNV-1a of all bases + lengths)
+static int cmd_fastx_stats(const Args &a) {
+    for (const std::string &f : a.files) {
+        FlatRecords recs;
+        std::string first;
+        if (!read_fastx(f, recs, true, &first)) { printf("%s\tINVALID\n", f.c_str()); continue; }
+        uint64_t h = 1469598103934665603ull;
+        for (uint8_t b : recs.bases) { h ^= b; h *= 1099511628211ull; }
+        for (size_t i = 0; i < recs.n(); i++) { h ^= recs.offsets[i + 1] - recs.offsets[i]; h *= 1099511628211ull; }
+        for (const std::string &id : recs.ids) for (char c : id) { h ^= (uint8_t)c; h *= 1099511628211ull; }
+        printf("%s\t%zu\t%zu\t%016llx\t%s\n", f.c_str(), recs.n(), recs.bases.size(), (unsigned long long)h, first.c_str());
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     Args a = parse(argc, argv);
+    if (a.cmd == "fastx-stats") return cmd_fastx_stats(a);
     syl_ctx *ctx = nullptr;
     check(syl_ctx_create(a.device, nullptr, &ctx), "syl_ctx_create");
     int rc;

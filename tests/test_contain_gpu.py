@@ -154,3 +154,27 @@ def test_uploaded_sketches_and_zero_counts(ctx):
     d = dict(kmers=kmers, kmer_off=koff, tracked=tracked, tracked_off=toff, gn_size=gs)
     compare(sort_query_rows(ctx.query(db, [smp])), oracle_rows(d, (sh, sc), False), False)
     compare(ctx.profile(db, [smp]), oracle_rows(d, (sh, sc), True), True)
+
+
+def test_k21_scalar_semantics_end_to_end(ctx):
+    """k = 21 with the scalar window set (what sylph computes on non-x86): sketches, query and profile."""
+    from oracle import oracle as O
+    from sylph_b200 import synth
+    from sylph_b200.api import contain_params
+    bases, off = synth.db_chunk(0, 30, 80000)
+    b, o = bases.numpy(), off.numpy().astype(np.uint64)
+    g = ctx.sketch_genomes(b, o, np.arange(31, dtype=np.uint64), k=21, c=15, sem=0)
+    rb, ro = synth.reads(40000, n_comm=30, genome_len=80000)
+    smp = ctx.sketch_sequences(rb.numpy(), ro.numpy().astype(np.uint64), k=21, c=15, sem=0)
+    d, hc = g.download(), smp.download()
+    km, tr, _ = O.sketch_genome(b[:80000], np.array([0, 80000], np.uint64), k=21, c=15, sem=0)
+    assert np.array_equal(km, d["kmers"][: int(d["kmer_off"][1])]) and np.array_equal(tr, d["tracked"][: int(d["tracked_off"][1])])
+    eh, ec, _, _ = O.sketch_reads(rb.numpy(), ro.numpy().astype(np.uint64), k=21, c=15, sem=0)
+    assert np.array_equal(hc[0], eh) and np.array_equal(hc[1], ec)
+    db = ctx.build_db(g)
+    for pt in (False, True):
+        rows = ctx.profile(db, [smp], contain_params(k=21, pseudotax=True)) if pt else sort_query_rows(ctx.query(db, [smp], contain_params(k=21)))
+        p = O.default_params(k=21, pseudotax=pt)
+        exp = O.contain_sample(p, d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"], O.Sample(*hc))
+        assert len(exp) > 5
+        compare(rows, exp, pt)

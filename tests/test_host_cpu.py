@@ -50,3 +50,48 @@ def test_formats_roundtrip_and_layout(tmp_path):
     s["sample_name"] = "S1"
     F.write_sylsp(p2, s)
     assert F.read_sylsp(p2)["sample_name"] == "S1"
+
+
+def _fnv(recs):
+    h = 1469598103934665603
+    M = (1 << 64) - 1
+    for _, s in recs:
+        for b in s:
+            h = ((h ^ b) * 1099511628211) & M
+    for _, s in recs:
+        h = ((h ^ len(s)) * 1099511628211) & M
+    for name, _ in recs:
+        for b in name:
+            h = ((h ^ b) * 1099511628211) & M
+    return h
+
+
+def test_fastx_parser_matches_needletail_semantics(tmp_path):
+    """C++ ingest (host/fastx.hpp) vs the Python reader: multi-line FASTA, CRLF, lower case / N kept as is,
+    empty records, FASTQ, gzip, and the real config-1 files."""
+    import gzip
+    from tests.util import DATA, read_fastx
+    exe = os.path.join(REPO, "host", "sylph-b200")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.check_call(["make", "-C", os.path.join(REPO, "host"), "-s"], env=env)
+    fa = tmp_path / "m.fa"
+    fa.write_bytes(b">c1 first contig\r\nACGTNNacgt\r\nTTTT\r\n>c2\n\n>c3 x\nAC\nGT\nA")
+    fq = tmp_path / "r.fq"
+    fq.write_bytes(b"@r1 d\nACGTN\n+\nIIIII\n@r2\nacg\n+r2\nIII\n")
+    gz = tmp_path / "m.fa.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(fa.read_bytes())
+    files = [str(fa), str(fq), str(gz), os.path.join(DATA, "e.coli-o157.fasta.gz"), os.path.join(DATA, "t1.fq"),
+             os.path.join(DATA, "k12_R1.fq")]
+    out = subprocess.run([exe, "fastx-stats"] + files, stdout=subprocess.PIPE, text=True, check=True).stdout.strip().split("\n")
+    assert len(out) == len(files)
+    for line, f in zip(out, files):
+        name, n, nb, h, first = line.split("\t", 4)
+        recs = read_fastx(f)
+        assert (int(n), int(nb)) == (len(recs), sum(len(s) for _, s in recs)), f
+        if sum(len(s) for _, s in recs) < 600000:  # the pure-Python FNV is slow on Mbp inputs
+            assert int(h, 16) == _fnv(recs), f
+        assert first == recs[0][0].decode(), f
+    assert read_fastx(str(fa))[0] == (b"c1 first contig", b"ACGTNNacgtTTTT") and read_fastx(str(fa))[1] == (b"c2", b"")

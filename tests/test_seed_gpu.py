@@ -108,3 +108,15 @@ def test_unsupported_k(ctx):
     buf, off = flatten([b"ACGT" * 50])
     with pytest.raises(SylphError):
         ctx.extract_markers_batch(buf, off, k=25)
+
+
+def test_all_256_byte_values(ctx):
+    """BYTE_TO_SEQ semantics for every byte value (src/types.rs:50-59): only ACGTUacgtu and 0x01..0x03 are
+    non-zero codes; everything else, N included, reads as A."""
+    rng = np.random.default_rng(256)
+    seqs = [bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8)) for n in [5000, 150, 150, 70, 31, 32, 33, 100000]]
+    seqs.append(bytes(range(256)) * 40)
+    buf, off = flatten(seqs)
+    for sem in (1, 0):
+        assert check(ctx, buf, off, 31, 3, sem, True) > 1000
+    assert check(ctx, buf, off, 21, 2, 1, False) > 1000
