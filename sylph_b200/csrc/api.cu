@@ -1,6 +1,8 @@
 // api.cu — the extern "C" boundary declared in include/sylph_b200.h (context + seeding entry
 // points; the sketch / containment entry points live next to their kernels).
+#include <algorithm>
 #include <mutex>
+#include <vector>
 #include <new>
 
 #include "common.cuh"
@@ -9,6 +11,51 @@ namespace syl {
 
 static thread_local std::string g_last_error;
 thread_local syl_ctx *tl_ctx = nullptr;
+
+static std::mutex g_live_mu;
+static std::vector<syl_ctx *> g_live_ctx;  // contexts that still exist (handles may outlive their ctx)
+static bool ctx_alive(syl_ctx *c) {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    return std::find(g_live_ctx.begin(), g_live_ctx.end(), c) != g_live_ctx.end();
+}
+
+int hblock_alloc(syl_ctx *ctx, void **p, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+    size_t best = (size_t)-1, bi = 0;
+    for (size_t i = 0; i < ctx->free_blocks.size(); i++) {
+        const size_t sz = ctx->free_blocks[i].second;
+        if (sz >= bytes && sz < best) { best = sz; bi = i; }
+    }
+    if (best != (size_t)-1 && best <= 2 * bytes + (1u << 20)) {
+        *p = ctx->free_blocks[bi].first;
+        ctx->free_blocks[bi] = ctx->free_blocks.back();
+        ctx->free_blocks.pop_back();
+        ctx->handle_blocks[*p] = best;
+        return SYL_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        set_error(std::string("cudaMalloc(") + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? SYL_ERR_OOM : SYL_ERR_CUDA;
+    }
+    ctx->handle_blocks[*p] = bytes;
+    ctx->cached_bytes += bytes;
+    return SYL_OK;
+}
+
+void hblock_free(syl_ctx *ctx, void *p) {
+    if (!p) return;
+    if (ctx && ctx_alive(ctx)) {
+        auto it = ctx->handle_blocks.find(p);
+        if (it != ctx->handle_blocks.end()) {
+            ctx->free_blocks.emplace_back(p, it->second);
+            ctx->handle_blocks.erase(it);
+            return;
+        }
+    }
+    cudaFree(p);  // the owning ctx is gone (its cache was released without this block)
+}
 void set_error(const std::string &msg) { g_last_error = msg; }
 
 int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
@@ -81,12 +128,20 @@ int syl_ctx_create(int device, void *stream, syl_ctx **out) {
         syl_ctx_destroy(ctx);
         return SYL_ERR_OOM;
     }
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live_ctx.push_back(ctx);
+    }
     *out = ctx;
     return SYL_OK;
 }
 
 void syl_ctx_destroy(syl_ctx *ctx) {
     if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live_ctx.erase(std::remove(g_live_ctx.begin(), g_live_ctx.end(), ctx), g_live_ctx.end());
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->free_blocks) cudaFree(b.first);

@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -68,18 +69,23 @@ struct syl_ctx {
     // calls then make no allocator calls at all (the CUDA allocators take driver-wide locks and
     // showed 30-500 ms stalls on shared hosts)
     std::vector<std::pair<void *, size_t>> free_blocks;
+    std::unordered_map<void *, size_t> handle_blocks;  // blocks lent to sample / genomes / db handles
     size_t cached_bytes = 0;
 };
 
 namespace syl {
 // ctx whose scratch cache DevBuf uses on this thread (set at every API entry)
 extern thread_local syl_ctx *tl_ctx;
+// device arrays owned by handles: taken from / returned to the owning ctx's block cache
+int hblock_alloc(syl_ctx *ctx, void **p, size_t bytes);
+void hblock_free(syl_ctx *ctx, void *p);
 }
 
 // Device-resident SequencesSketch.kmer_counts (src/types.rs:145-155): parallel arrays sorted by hash
 struct syl_sample {
     int device = 0;
-    cudaStream_t stream = nullptr;  // arrays are stream-ordered allocations of this stream
+    syl_ctx *owner = nullptr;       // arrays are blocks of this ctx's cache (free handles before their ctx)
+    cudaStream_t stream = nullptr;
     uint64_t *hash = nullptr;  // ascending, distinct
     uint32_t *count = nullptr;
     uint64_t n = 0;
@@ -92,7 +98,8 @@ struct syl_sample {
 // Device-resident batch of GenomeSketch (src/types.rs:163-173) in CSR form
 struct syl_genomes {
     int device = 0;
-    cudaStream_t stream = nullptr;  // arrays are stream-ordered allocations of this stream
+    syl_ctx *owner = nullptr;       // arrays are blocks of this ctx's cache (free handles before their ctx)
+    cudaStream_t stream = nullptr;
     uint64_t n = 0;                                       // genomes
     uint64_t *kmers = nullptr, *kmer_off = nullptr;       // genome_kmers, position order
     uint64_t *tracked = nullptr, *tracked_off = nullptr;  // pseudotax_tracked_nonused_kmers

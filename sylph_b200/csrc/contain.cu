@@ -32,7 +32,8 @@
 
 struct syl_db {
     int device = 0;
-    cudaStream_t stream = nullptr;  // arrays are stream-ordered allocations of this stream
+    syl_ctx *owner = nullptr;       // arrays are blocks of this ctx's cache
+    cudaStream_t stream = nullptr;
     uint64_t n_genomes = 0;
     uint32_t genome_base = 0;
     uint64_t N = 0;             // index entries (genome_kmers + tracked)
@@ -705,6 +706,7 @@ int syl_db_build(syl_ctx *ctx, const syl_genomes *g, uint32_t genome_base, syl_d
     if (!db) return SYL_ERR_OOM;
     db->device = ctx->device;
     db->stream = st;
+    db->owner = ctx;
     db->n_genomes = g->n;
     db->genome_base = genome_base;
     db->N = N;
@@ -713,9 +715,9 @@ int syl_db_build(syl_ctx *ctx, const syl_genomes *g, uint32_t genome_base, syl_d
     db->c = g->c;
     auto fail = [&](int rc) { syl_db_free(db); return rc; };
 #define DB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(_e)); return fail(SYL_ERR_CUDA); } } while (0)
-    DB_CUDA(cudaMallocAsync((void **)&db->keys, std::max<uint64_t>(N, 1) * 8, st));
-    DB_CUDA(cudaMallocAsync((void **)&db->gid, std::max<uint64_t>(N, 1) * 4, st));
-    DB_CUDA(cudaMallocAsync((void **)&db->glen, std::max<uint64_t>(g->n, 1) * 4, st));
+    if (int arc = hblock_alloc(ctx, (void **)&db->keys, std::max<uint64_t>(N, 1) * 8)) return fail(arc);
+    if (int arc = hblock_alloc(ctx, (void **)&db->gid, std::max<uint64_t>(N, 1) * 4)) return fail(arc);
+    if (int arc = hblock_alloc(ctx, (void **)&db->glen, std::max<uint64_t>(g->n, 1) * 4)) return fail(arc);
     db->h_gn_size.resize(g->n);
     if (g->n) {
         DB_CUDA(cudaMemcpyAsync(db->h_gn_size.data(), g->gn_size, g->n * 8, cudaMemcpyDeviceToHost, st));
@@ -725,7 +727,7 @@ int syl_db_build(syl_ctx *ctx, const syl_genomes *g, uint32_t genome_base, syl_d
     uint64_t NB = 1024;
     while (NB < N / 4) NB <<= 1;
     db->NB = NB;
-    DB_CUDA(cudaMallocAsync((void **)&db->bstart, (NB + 2) * 4, st));
+    if (int arc = hblock_alloc(ctx, (void **)&db->bstart, (NB + 2) * 4)) return fail(arc);
     if (N) {
         DevBuf<uint64_t> kin;
         DevBuf<uint32_t> gin;
@@ -761,10 +763,10 @@ uint64_t syl_db_num_genomes(const syl_db *db) { return db ? db->n_genomes : 0; }
 void syl_db_free(syl_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    if (db->keys) cudaFreeAsync(db->keys, db->stream);
-    if (db->gid) cudaFreeAsync(db->gid, db->stream);
-    if (db->bstart) cudaFreeAsync(db->bstart, db->stream);
-    if (db->glen) cudaFreeAsync(db->glen, db->stream);
+    hblock_free(db->owner, db->keys);
+    hblock_free(db->owner, db->gid);
+    hblock_free(db->owner, db->bstart);
+    hblock_free(db->owner, db->glen);
     delete db;
 }
 

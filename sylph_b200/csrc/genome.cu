@@ -184,11 +184,12 @@ __global__ void k_copy_ranges(const uint64_t *__restrict__ src4, const uint64_t 
 // stream-ordered allocations on the creating ctx stream (no device-wide sync in steady-state loops)
 static int genomes_alloc(syl_genomes *g, cudaStream_t st, uint64_t n_genomes, uint64_t nk, uint64_t nt) {
     g->stream = st;
-    SYL_CUDA(cudaMallocAsync((void **)&g->kmers, std::max<uint64_t>(nk, 1) * 8, st));
-    SYL_CUDA(cudaMallocAsync((void **)&g->tracked, std::max<uint64_t>(nt, 1) * 8, st));
-    SYL_CUDA(cudaMallocAsync((void **)&g->kmer_off, (n_genomes + 1) * 8, st));
-    SYL_CUDA(cudaMallocAsync((void **)&g->tracked_off, (n_genomes + 1) * 8, st));
-    SYL_CUDA(cudaMallocAsync((void **)&g->gn_size, std::max<uint64_t>(n_genomes, 1) * 8, st));
+    g->owner = tl_ctx;
+    SYL_TRY(hblock_alloc(g->owner, (void **)&g->kmers, std::max<uint64_t>(nk, 1) * 8));
+    SYL_TRY(hblock_alloc(g->owner, (void **)&g->tracked, std::max<uint64_t>(nt, 1) * 8));
+    SYL_TRY(hblock_alloc(g->owner, (void **)&g->kmer_off, (n_genomes + 1) * 8));
+    SYL_TRY(hblock_alloc(g->owner, (void **)&g->tracked_off, (n_genomes + 1) * 8));
+    SYL_TRY(hblock_alloc(g->owner, (void **)&g->gn_size, std::max<uint64_t>(n_genomes, 1) * 8));
     g->n = n_genomes;
     g->total_kmers = nk;
     g->total_tracked = nt;
@@ -498,12 +499,11 @@ int syl_genomes_device_ptrs(const syl_genomes *g, const uint64_t **kmers, const 
 void syl_genomes_free(syl_genomes *g) {
     if (!g) return;
     cudaSetDevice(g->device);
-    // stream-ordered free on the creating ctx stream (free handles before destroying their ctx)
-    if (g->kmers) cudaFreeAsync(g->kmers, g->stream);
-    if (g->kmer_off) cudaFreeAsync(g->kmer_off, g->stream);
-    if (g->tracked) cudaFreeAsync(g->tracked, g->stream);
-    if (g->tracked_off) cudaFreeAsync(g->tracked_off, g->stream);
-    if (g->gn_size) cudaFreeAsync(g->gn_size, g->stream);
+    hblock_free(g->owner, g->kmers);  // back into the owning ctx's block cache
+    hblock_free(g->owner, g->kmer_off);
+    hblock_free(g->owner, g->tracked);
+    hblock_free(g->owner, g->tracked_off);
+    hblock_free(g->owner, g->gn_size);
     delete g;
 }
 

@@ -723,6 +723,7 @@ struct SampleBuilder {
         syl_sample *s = new (std::nothrow) syl_sample();
         if (!s) return SYL_ERR_OOM;
         s->device = ctx->device;
+        s->owner = ctx;
         s->stream = ctx->stream;
         s->k = k;
         s->c = c;
@@ -739,8 +740,8 @@ struct SampleBuilder {
             DevBuf<uint32_t> ct;
             uint64_t U = 0, nd = 0;
             if ((rc = dedup_sorted(hash, recflag, p0, p1, N, uq, ct, &U, &nd)) != SYL_OK) return fail(rc);
-            SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(U, 1) * 8, st));
-            SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(U, 1) * 4, st));
+            SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8));
+            SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4));
             SYL_CUDA(cudaMemcpyAsync(s->hash, uq.p, U * 8, cudaMemcpyDeviceToDevice, st));
             SYL_CUDA(cudaMemcpyAsync(s->count, ct.p, U * 4, cudaMemcpyDeviceToDevice, st));
             SYL_CUDA(cudaStreamSynchronize(st));
@@ -813,8 +814,8 @@ struct SampleBuilder {
             ndup += nd2;
         }
         const uint64_t U = U1 + U2;
-        SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(U, 1) * 8, st));
-        SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(U, 1) * 4, st));
+        SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8));
+        SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4));
         if (U2) {  // slot the generic path's pairs into their groups' positions and redo the output offsets
             k_fallback_place<<<nblk(ng, 128), 128, 0, st>>>(g_fb.p, g_bf.p, g_be.p, ng, nbk, Mb, f_uq.p, U2, g_nuniq.p, g_src.p);
             k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
@@ -938,9 +939,9 @@ int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_
     cudaStream_t st = ctx->stream;
     syl_sample *s = new (std::nothrow) syl_sample();
     if (!s) return SYL_ERR_OOM;
-    s->device = ctx->device; s->stream = st; s->k = k; s->c = c; s->n = n;
-    SYL_CUDA(cudaMallocAsync((void **)&s->hash, std::max<uint64_t>(n, 1) * 8, st));
-    SYL_CUDA(cudaMallocAsync((void **)&s->count, std::max<uint64_t>(n, 1) * 4, st));
+    s->device = ctx->device; s->owner = ctx; s->stream = st; s->k = k; s->c = c; s->n = n;
+    SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(n, 1) * 8));
+    SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(n, 1) * 4));
     if (n) {
         DevBuf<uint64_t> kin;
         DevBuf<uint32_t> vin;
@@ -984,9 +985,8 @@ int syl_sample_device_ptrs(const syl_sample *s, const uint64_t **hash, const uin
 void syl_sample_free(syl_sample *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    // stream-ordered free on the creating ctx stream (free samples before destroying their ctx)
-    if (s->hash) cudaFreeAsync(s->hash, s->stream);
-    if (s->count) cudaFreeAsync(s->count, s->stream);
+    hblock_free(s->owner, s->hash);   // back into the owning ctx's block cache
+    hblock_free(s->owner, s->count);
     delete s;
 }
 
