@@ -112,6 +112,14 @@ struct syl_genomes {
 
 namespace syl {
 
+// One survivor of a READ sketch as the dedup post-pass consumes it (32 bytes = one sector):
+// recflag = read index << 1 | NO_PAIR, plus EV_PENDING while the pair keys still have to be
+// computed from global memory (read not fully inside the seeding tile).
+struct EventRec { uint64_t hash, recflag, p0, p1; };
+static_assert(sizeof(EventRec) == 32, "EventRec is one 32-byte sector");
+constexpr uint64_t NO_PAIR = 1ull;
+constexpr uint64_t EV_PENDING = 1ull << 63;
+
 // stream-ordered temporary device buffer (cudaMallocAsync from the device's default pool)
 template <typename T>
 struct DevBuf {

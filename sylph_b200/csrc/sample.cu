@@ -23,21 +23,23 @@
 
 namespace syl {
 
-int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
-                uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
-                uint64_t cap, uint64_t *n_out);
+int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
+                   uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
+                   uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
+                   uint32_t *d_pend, uint64_t *n_pend);
 
 }  // namespace syl
 
 namespace syl {
 
-constexpr uint64_t NO_PAIR = 1ull;  // bit 0 of recflag set => the read has no pair key
-
 // pair_kmer_single (src/sketch.rs:624-656): four 16-base keys sampled at even/odd offsets from
 // the read start and from the middle.  len > 400 (src/sketch.rs:923) or len < 66 (:627) => None.
-// One thread per survivor: the 32 bytes a key pair is drawn from are fetched as nine aligned
-// 32-bit words and realigned with funnel shifts; even / odd bytes are separated with PRMT and
-// mapped through four pre-shifted copies of the exact BYTE_TO_SEQ table in shared memory.
+// k_seed computes the keys itself from its packed tile whenever the read's first 32 bases and the
+// 32 bases from its middle are inside the tile; k_events_fix below handles the reads cut by a tile
+// edge (about 1 % of 150 bp reads).  One thread per such event: the 32 bytes a key pair is drawn
+// from are fetched as nine aligned 32-bit words and realigned with funnel shifts; even / odd bytes
+// are separated with PRMT and mapped through four pre-shifted copies of the exact BYTE_TO_SEQ
+// table in shared memory.
 constexpr int EV_THREADS = 128;
 
 __device__ __forceinline__ void load32_unaligned(const uint8_t *p, uint32_t x[8]) {
@@ -66,10 +68,8 @@ __device__ __forceinline__ uint32_t pack16(const uint32_t x[8], uint32_t sel, co
 }
 
 __global__ void __launch_bounds__(EV_THREADS)
-k_events(const syl_survivor *__restrict__ sv, uint64_t n, const uint8_t *__restrict__ bases,
-         const uint64_t *__restrict__ rec_off, uint64_t off_bias, uint64_t rec_base, int no_dedup,
-         uint64_t *__restrict__ hash, uint64_t *__restrict__ recflag,
-         uint64_t *__restrict__ p0, uint64_t *__restrict__ p1) {
+k_events_fix(EventRec *__restrict__ ev, const uint32_t *__restrict__ pend, const unsigned long long *__restrict__ n_pend,
+             const uint8_t *__restrict__ bases, const uint64_t *__restrict__ rec_off, uint64_t off_bias, uint64_t rec_base) {
     __shared__ uint8_t lut[4][256];
     for (int i = threadIdx.x; i < 256; i += EV_THREADS) {
         const uint32_t code = byte_to_seq((uint32_t)i);
@@ -79,26 +79,30 @@ k_events(const syl_survivor *__restrict__ sv, uint64_t n, const uint8_t *__restr
         lut[3][i] = (uint8_t)code;
     }
     __syncthreads();
-    const uint64_t i = (uint64_t)blockIdx.x * EV_THREADS + threadIdx.x;
-    if (i >= n) return;
-    const syl_survivor s = sv[i];
-    hash[i] = s.hash;
-    const uint64_t a = rec_off[s.rec] - off_bias;
-    const uint64_t L = rec_off[s.rec + 1] - off_bias - a;
-    const bool has_pair = !no_dedup && L <= 400 && L >= 66;
-    recflag[i] = ((rec_base + s.rec) << 1) | (has_pair ? 0ull : NO_PAIR);
-    uint64_t k0 = 0, k1 = 0;
-    if (has_pair) {
+    const uint64_t n = *n_pend;
+    for (uint64_t i = (uint64_t)blockIdx.x * EV_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * EV_THREADS) {
+        EventRec *e = ev + pend[i];
+        const uint64_t rf = e->recflag & ~EV_PENDING;
+        const uint64_t rec = (rf >> 1) - rec_base;
+        const uint64_t a = rec_off[rec] - off_bias;
+        const uint64_t L = rec_off[rec + 1] - off_bias - a;
         uint32_t x[8];
         load32_unaligned(bases + a, x);
         const uint32_t f = pack16(x, 0x6420, lut), g = pack16(x, 0x7531, lut);
         load32_unaligned(bases + a + L / 2, x);
         const uint32_t r = pack16(x, 0x6420, lut), t = pack16(x, 0x7531, lut);
-        k0 = ((uint64_t)f << 32) | r;  // doublepairs.0 = [kmer_f, kmer_r]
-        k1 = ((uint64_t)g << 32) | t;  // doublepairs.1 = [kmer_g, kmer_t]
+        e->recflag = rf;
+        e->p0 = ((uint64_t)f << 32) | r;  // doublepairs.0 = [kmer_f, kmer_r]
+        e->p1 = ((uint64_t)g << 32) | t;  // doublepairs.1 = [kmer_g, kmer_t]
     }
-    p0[i] = k0;
-    p1[i] = k1;
+}
+
+__global__ void k_unpack_events(const EventRec *__restrict__ ev, uint64_t n, uint64_t *__restrict__ hash,
+                                uint64_t *__restrict__ recflag, uint64_t *__restrict__ p0, uint64_t *__restrict__ p1) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const EventRec r = ev[i];
+    hash[i] = r.hash; recflag[i] = r.recflag; p0[i] = r.p0; p1[i] = r.p1;
 }
 
 __global__ void k_iota(uint32_t *idx, uint64_t n) {
@@ -169,19 +173,16 @@ __global__ void k_copy_len(const uint32_t *__restrict__ len, uint32_t *__restric
 //       and every group is sorted, so the result is globally sorted without a merge.
 // Groups that do not fit (heavy-hitter k-mers, > GRP_CAP events) or whose dedup set outgrows
 // the per-thread buffer are handed to the generic radix-sort path below and merged at the end.
-struct EventRec { uint64_t hash, recflag, p0, p1; };
-static_assert(sizeof(EventRec) == 32, "EventRec is one 32-byte sector");
-
 constexpr int GRP_THREADS = 256;
 constexpr int GRP_CAP = 1024;   // most events one CTA handles in shared memory
 constexpr int GRP_T = 768;      // group span in event offsets: typical n ~ 800, leaving room for k-mers with ~200 events
 constexpr int GRP_SET = 16;     // dedup-set entries kept per k-mer before falling back
 
-__global__ void k_bucket_hist(const uint64_t *__restrict__ hash, uint64_t n, uint64_t Mb, uint32_t nbk,
+__global__ void k_bucket_hist(const EventRec *__restrict__ ev, uint64_t n, uint64_t Mb, uint32_t nbk,
                               uint32_t *__restrict__ cnt) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t b = (uint32_t)__umul64hi(hash[i], Mb);
+    uint32_t b = (uint32_t)__umul64hi(ev[i].hash, Mb);
     atomicAdd(&cnt[b < nbk ? b : nbk - 1], 1u);
 }
 
@@ -259,20 +260,20 @@ __global__ void k_scan_add(uint32_t *__restrict__ out, uint64_t n, const uint32_
     if (i == n - 1) out[n] = block_off[gridDim.x];  // total
 }
 
-__global__ void k_scatter_events(const uint64_t *__restrict__ hash, const uint64_t *__restrict__ recflag,
-                                 const uint64_t *__restrict__ p0, const uint64_t *__restrict__ p1, uint64_t n,
+__global__ void k_scatter_events(const EventRec *__restrict__ ev, uint64_t n,
                                  uint64_t Mb, uint32_t nbk, const uint32_t *__restrict__ boff,
                                  uint32_t *__restrict__ cursor, EventRec *__restrict__ part) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t h = hash[i];
+    const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
+    const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+    const uint64_t h = ((uint64_t)lo.y << 32) | lo.x;
     uint32_t b = (uint32_t)__umul64hi(h, Mb);
     if (b >= nbk) b = nbk - 1;
     const uint32_t pos = boff[b] + atomicAdd(&cursor[b], 1u);
     uint4 *dst = reinterpret_cast<uint4 *>(part + pos);
-    const uint64_t rf = recflag[i], a = p0[i], c = p1[i];
-    dst[0] = make_uint4((uint32_t)h, (uint32_t)(h >> 32), (uint32_t)rf, (uint32_t)(rf >> 32));
-    dst[1] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+    dst[0] = lo;
+    dst[1] = hi;
 }
 
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint64_t v) {
@@ -593,46 +594,45 @@ struct SampleBuilder {
     uint64_t c;
     int no_dedup, sem;
     uint64_t n_reads = 0, n_bases = 0, n_events = 0, cap = 0;
-    DevBuf<uint64_t> b_hash, b_rf, b_p0, b_p1;  // event arrays (scratch blocks of the ctx cache)
-    uint64_t *hash = nullptr, *recflag = nullptr, *p0 = nullptr, *p1 = nullptr;
+    DevBuf<EventRec> b_ev;  // event array (a scratch block of the ctx cache)
+    EventRec *ev = nullptr;
 
     int reserve(uint64_t need) {
         if (need <= cap) return SYL_OK;
         const uint64_t ncap = std::max<uint64_t>(need, cap * 2);
         cudaStream_t st = ctx->stream;
-        DevBuf<uint64_t> nh, nr, n0, n1;
-        SYL_TRY(nh.alloc(ncap, st)); SYL_TRY(nr.alloc(ncap, st)); SYL_TRY(n0.alloc(ncap, st)); SYL_TRY(n1.alloc(ncap, st));
-        if (n_events) {
-            SYL_CUDA(cudaMemcpyAsync(nh.p, hash, n_events * 8, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaMemcpyAsync(nr.p, recflag, n_events * 8, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaMemcpyAsync(n0.p, p0, n_events * 8, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaMemcpyAsync(n1.p, p1, n_events * 8, cudaMemcpyDeviceToDevice, st));
-        }
-        b_hash.swap(nh); b_rf.swap(nr); b_p0.swap(n0); b_p1.swap(n1);  // the old blocks go back to the cache
-        hash = b_hash.p; recflag = b_rf.p; p0 = b_p0.p; p1 = b_p1.p;
+        DevBuf<EventRec> ne;
+        SYL_TRY(ne.alloc(ncap, st));
+        if (n_events) SYL_CUDA(cudaMemcpyAsync(ne.p, ev, n_events * sizeof(EventRec), cudaMemcpyDeviceToDevice, st));
+        b_ev.swap(ne);  // the old block goes back to the cache
+        ev = b_ev.p;
         cap = ncap;
         return SYL_OK;
     }
 
-    // one batch of reads, device resident; read indices continue from the previous batch
+    // one batch of reads, device resident; read indices continue from the previous batch.
+    // k_seed appends the batch's events (hash, read, pair keys) straight to the event array.
     int add(const uint8_t *d_bases, uint64_t nb, const uint64_t *d_off, uint64_t off_bias, uint64_t nr) {
         cudaStream_t st = ctx->stream;
         if (nr == 0) return SYL_OK;
         uint64_t scap = nb / c + nb / (4 * c) + 65536;
         if (scap > nb) scap = nb + 16;
-        DevBuf<syl_survivor> sv;
-        uint64_t n = 0;
+        uint64_t n = 0, npend = 0;
+        DevBuf<uint32_t> pend;
         for (;;) {
-            SYL_TRY(sv.alloc(scap, st));
-            int rc = seed_device(ctx, d_bases, nb, d_off, off_bias, nr, k, c, sem, /*with_pos=*/0, sv.p, scap, &n);
+            if (scap >= 0xFFFFFFFFull) { set_error("more than 2^32-2 survivor events in one batch"); return SYL_ERR_ARG; }
+            SYL_TRY(reserve(n_events + scap));
+            SYL_TRY(pend.alloc(scap, st));
+            int rc = seed_device_ex(ctx, d_bases, nb, d_off, off_bias, nr, k, c, sem, /*with_pos=*/0, ev + n_events, scap, &n,
+                                    /*emit_events=*/1, n_reads, no_dedup, pend.p, &npend);
             if (rc == SYL_ERR_CAPACITY) { scap = n + 16; continue; }
             if (rc != SYL_OK) return rc;
             break;
         }
-        SYL_TRY(reserve(n_events + n));
-        if (n) {
-            k_events<<<nblk(n, EV_THREADS), EV_THREADS, 0, st>>>(sv.p, n, d_bases, d_off, off_bias, n_reads, no_dedup, hash + n_events,
-                                                    recflag + n_events, p0 + n_events, p1 + n_events);
+        if (npend) {
+            const unsigned grid = (unsigned)std::min<uint64_t>(nblk(npend, EV_THREADS), 4096);
+            k_events_fix<<<grid, EV_THREADS, 0, st>>>(ev + n_events, pend.p, reinterpret_cast<const unsigned long long *>(ctx->d_counters + 1),
+                                                     d_bases, d_off, off_bias, n_reads);
             ctx->launches++;
             SYL_CUDA(cudaGetLastError());
         }
@@ -739,7 +739,11 @@ struct SampleBuilder {
             DevBuf<uint64_t> uq;
             DevBuf<uint32_t> ct;
             uint64_t U = 0, nd = 0;
-            if ((rc = dedup_sorted(hash, recflag, p0, p1, N, uq, ct, &U, &nd)) != SYL_OK) return fail(rc);
+            DevBuf<uint64_t> e_h, e_rf, e_p0, e_p1;
+            if ((rc = e_h.alloc(N, st)) || (rc = e_rf.alloc(N, st)) || (rc = e_p0.alloc(N, st)) || (rc = e_p1.alloc(N, st))) return fail(rc);
+            k_unpack_events<<<nblk(N, 256), 256, 0, st>>>(ev, N, e_h.p, e_rf.p, e_p0.p, e_p1.p);
+            ctx->launches++;
+            if ((rc = dedup_sorted(e_h.p, e_rf.p, e_p0.p, e_p1.p, N, uq, ct, &U, &nd)) != SYL_OK) return fail(rc);
             SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8));
             SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4));
             SYL_CUDA(cudaMemcpyAsync(s->hash, uq.p, U * 8, cudaMemcpyDeviceToDevice, st));
@@ -772,7 +776,7 @@ struct SampleBuilder {
         SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, st));
         SYL_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)nbk * 4, st));
         SYL_CUDA(cudaMemsetAsync(d_ndup, 0, 8, st));
-        k_bucket_hist<<<nblk(N, 256), 256, 0, st>>>(hash, N, Mb, nbk, cnt.p);
+        k_bucket_hist<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, cnt.p);
         {   // boff = exclusive scan of cnt (nbk >= 4096 entries): local scans, scan of block totals, add back
             const uint32_t nblk1 = nbk / 1024;
             DevBuf<uint32_t> btot, boff2;
@@ -782,7 +786,7 @@ struct SampleBuilder {
             k_scan_add<<<nblk1, 1024, 0, st>>>(boff.p, nbk, boff2.p);
             ctx->launches += 2;
         }
-        k_scatter_events<<<nblk(N, 256), 256, 0, st>>>(hash, recflag, p0, p1, N, Mb, nbk, boff.p, cursor.p, part.p);
+        k_scatter_events<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, boff.p, cursor.p, part.p);
         SYL_CUDA(cudaFuncSetAttribute(k_group_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
         k_group_ranges<<<nblk(ng, 256), 256, 0, st>>>(boff.p, nbk, ng, g_bf.p, g_be.p);
         k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, no_dedup, st_hash.p, st_cnt.p,

@@ -60,12 +60,13 @@ struct SeedMeta {
     long long rel[SEED_THREADS];      // rec_off[r] - tile_start (may be very negative)
     int s0[SEED_THREADS];             // first valid window start inside the tile (tile-relative)
     int cnt[SEED_THREADS];            // number of valid window starts inside the tile
+    int len[SEED_THREADS];            // record length (saturated), for the pair-key rule
     int rbase[SEED_THREADS + 1];      // exclusive scan of ceil(cnt / SEED_W)
     int warp_tot[SEED_THREADS / 32];
     unsigned int stage_count;
     unsigned int cand_count;
     unsigned long long flush_base;
-    alignas(16) syl_survivor stage[SEED_STAGE];
+    alignas(16) EventRec stage[SEED_STAGE];  // holds syl_survivor (16 B) or EventRec (32 B) entries
     uint32_t cand[SEED_CAND];          // (tile-relative window start << 8) | record slot
     uint16_t run_rec[SEED_MAXRUNS];    // run -> record slot + 1 (filled by a max-scan over run starts)
 };
@@ -137,12 +138,35 @@ __global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t 
     tile_rec[t] = (uint32_t)r;
 }
 
+// 16 two-bit fields (the even ones of 32, MSB-first) of x -> 32 bits
+__device__ __forceinline__ uint32_t even_fields(uint64_t x) {
+    x &= 0xCCCCCCCCCCCCCCCCull;
+    x = (x | (x << 2)) & 0xF0F0F0F0F0F0F0F0ull;
+    x = (x | (x << 4)) & 0xFF00FF00FF00FF00ull;
+    x = (x | (x << 8)) & 0xFFFF0000FFFF0000ull;
+    x = (x | (x << 16)) & 0xFFFFFFFF00000000ull;
+    return (uint32_t)(x >> 32);
+}
+
+// 32 consecutive bases (64 bits, MSB-first) of the forward stream starting at tile-relative base q
+__device__ __forceinline__ uint64_t fw64(const SeedSmem &S, uint32_t q) {
+    const uint32_t bitpos = 32u + 2u * q, w = bitpos >> 5, sh = bitpos & 31u;
+    const uint32_t a = S.fw[w], b = S.fw[w + 1], c = S.fw[w + 2];
+    return ((uint64_t)__funnelshift_l(b, a, sh) << 32) | __funnelshift_l(c, b, sh);
+}
+
 // Exact re-derivation of one candidate window: k-mer halves from the packed streams at an arbitrary
 // position, full 64-bit hash, threshold test, survivor staged in shared memory.
-template <int K>
+// EMIT == 0: 16-byte syl_survivor (hash, record, position).
+// EMIT == 1: 32-byte EventRec for the read-sketch post-pass, including pair_kmer_single's keys
+//            (src/sketch.rs:624-656) taken straight from the packed stream when the read's first 32
+//            bases and the 32 bases from its middle are inside the staged tile (99 % of 150 bp
+//            reads); otherwise the event is flagged EV_PENDING and k_events_fix fills the keys.
+template <int K, int EMIT>
 __device__ __forceinline__ void seed_resolve(const SeedSmem &S, SeedMeta &M, uint32_t pw, int j, uint64_t rc, uint64_t thr,
-                                             syl_survivor *__restrict__ out, uint64_t cap,
-                                             unsigned long long *__restrict__ g_count) {
+                                             void *__restrict__ out, uint64_t cap,
+                                             unsigned long long *__restrict__ g_count, uint64_t rec_base, int no_dedup,
+                                             uint32_t *__restrict__ pend) {
     constexpr uint32_t PAD = 64 - 2 * K;
     constexpr uint32_t HI_MASK = (1u << (32 - PAD)) - 1u;
     const uint32_t bitpos = 32u + 2u * pw - PAD;
@@ -153,27 +177,58 @@ __device__ __forceinline__ void seed_resolve(const SeedSmem &S, SeedMeta &M, uin
     const uint32_t c0 = S.cw[cq], c1 = S.cw[cq + 1], c2 = S.cw[cq + 2];
     const uint64_t rr = ((uint64_t)(__funnelshift_r(c1, c2, csh) & HI_MASK) << 32) | __funnelshift_r(c0, c1, csh);
     const uint64_t h = mm_hash64(f < rr ? f : rr);  // src/seeding.rs:131-137
-    if (h < thr) {                                  // src/seeding.rs:139
+    if (h >= thr) return;                           // src/seeding.rs:139
+    const unsigned int idx = atomicAdd(&M.stage_count, 1u);
+    if (EMIT == 0) {
         syl_survivor sv;
         sv.hash = h;
         sv.rec = (uint32_t)(rc + (uint64_t)j);
         sv.pos = (uint32_t)((long long)pw - M.rel[j] + (K - 1));
-        const unsigned int idx = atomicAdd(&M.stage_count, 1u);
         if (idx < (unsigned)SEED_STAGE) {
-            M.stage[idx] = sv;
+            reinterpret_cast<syl_survivor *>(M.stage)[idx] = sv;
         } else {
             const unsigned long long gi = atomicAdd(g_count, 1ull);
-            if (gi < cap) out[gi] = sv;
+            if (gi < cap) reinterpret_cast<syl_survivor *>(out)[gi] = sv;
+        }
+    } else {
+        EventRec ev;
+        ev.hash = h;
+        const int L = M.len[j];
+        const bool has_pair = !no_dedup && L <= 400 && L >= 66;  // src/sketch.rs:923, :627
+        ev.recflag = ((rec_base + rc + (uint64_t)j) << 1) | (has_pair ? 0ull : NO_PAIR);
+        ev.p0 = 0;
+        ev.p1 = 0;
+        if (has_pair) {
+            const long long st = M.rel[j];  // read start, tile-relative
+            const long long mid = st + (L >> 1);
+            if (st >= 0 && mid + 32 <= (long long)SEED_NCHUNK16 * 16) {
+                const uint64_t a = fw64(S, (uint32_t)st), b = fw64(S, (uint32_t)mid);
+                const uint32_t kf = even_fields(a), kg = even_fields(a << 2);  // s[0,2,..,30] / s[1,3,..,31]
+                const uint32_t kr = even_fields(b), kt = even_fields(b << 2);
+                ev.p0 = ((uint64_t)kf << 32) | kr;  // doublepairs.0 = [kmer_f, kmer_r]
+                ev.p1 = ((uint64_t)kg << 32) | kt;  // doublepairs.1 = [kmer_g, kmer_t]
+            } else {
+                ev.recflag |= EV_PENDING;
+            }
+        }
+        if (idx < (unsigned)SEED_STAGE) {
+            M.stage[idx] = ev;
+        } else {
+            const unsigned long long gi = atomicAdd(g_count, 1ull);
+            if (gi < cap) {
+                reinterpret_cast<EventRec *>(out)[gi] = ev;
+                if (ev.recflag & EV_PENDING) pend[atomicAdd(g_count + 1, 1ull)] = (uint32_t)gi;
+            }
         }
     }
 }
 
-template <int K, int VAR>
+template <int K, int VAR, int EMIT>
 __global__ void __launch_bounds__(SEED_THREADS, SEED_MINB_CFG)
 k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__restrict__ rec_off, uint64_t off_bias,
        const uint32_t *__restrict__ tile_rec, uint64_t thr, int sem, int with_pos,
-       syl_survivor *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count,
-       const ShiftMul smul) {
+       void *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count,
+       const ShiftMul smul, uint64_t rec_base, int no_dedup, uint32_t *__restrict__ pend) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SeedSmem &S = *reinterpret_cast<SeedSmem *>(smem_raw);
     SeedMeta &M = *reinterpret_cast<SeedMeta *>(S.asc);
@@ -276,6 +331,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
             M.rel[tid] = (long long)a - (long long)T0;
             M.s0[tid] = (int)(lo - T0);
             M.cnt[tid] = cnt;
+            M.len[tid] = L > 0x7FFFFFFFull ? 0x7FFFFFFF : (int)L;
             runs = (cnt + SEED_W - 1) / SEED_W;
         }
         // block-wide exclusive scan of runs
@@ -378,7 +434,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
                 if (ci < (unsigned)SEED_CAND) {
                     M.cand[ci] = ((uint32_t)(p + i) << 8) | (uint32_t)j;
                 } else {  // list full (tiny c): resolve inline
-                    seed_resolve<K>(S, M, (uint32_t)(p + i), j, rc, thr, out, cap, g_count);
+                    seed_resolve<K, EMIT>(S, M, (uint32_t)(p + i), j, rc, thr, out, cap, g_count, rec_base, no_dedup, pend);
                 }
             }
         }
@@ -387,7 +443,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
             const unsigned int nc = min(M.cand_count, (unsigned)SEED_CAND);
             for (unsigned int ci = tid; ci < nc; ci += SEED_THREADS) {
                 const uint32_t e = M.cand[ci];
-                seed_resolve<K>(S, M, e >> 8, (int)(e & 255u), rc, thr, out, cap, g_count);
+                seed_resolve<K, EMIT>(S, M, e >> 8, (int)(e & 255u), rc, thr, out, cap, g_count, rec_base, no_dedup, pend);
             }
         }
         __syncthreads();  // table is rewritten by the next chunk
@@ -400,8 +456,16 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
     __syncthreads();
     if (staged) {
         const unsigned long long base = M.flush_base;
-        for (unsigned int i = tid; i < staged; i += SEED_THREADS)
-            if (base + i < cap) out[base + i] = M.stage[i];
+        for (unsigned int i = tid; i < staged; i += SEED_THREADS) {
+            if (base + i >= cap) continue;
+            if (EMIT == 0) reinterpret_cast<syl_survivor *>(out)[base + i] = reinterpret_cast<const syl_survivor *>(M.stage)[i];
+            else {
+                const EventRec ev = M.stage[i];
+                reinterpret_cast<EventRec *>(out)[base + i] = ev;
+                // reads cut by the tile edge: pair keys are filled in by k_events_fix
+                if (ev.recflag & EV_PENDING) pend[atomicAdd(g_count + 1, 1ull)] = (uint32_t)(base + i);
+            }
+        }
     }
 }
 
@@ -409,10 +473,28 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
 // number of survivors even when it exceeds cap (then SYL_ERR_CAPACITY).
 // d_rec_off[i] - off_bias is the start of record i inside d_bases (off_bias lets a caller pass a
 // slice of a larger offset array unchanged).
+// emit_events: d_out is an EventRec array (read-sketch path: rec_base = index of the batch's first
+// read, no_dedup as in sketch_sequences_needle) instead of a syl_survivor array; d_pend (cap
+// entries, cap < 2^32) receives the indices of the events whose pair keys are still missing.
+int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
+                   uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
+                   uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
+                   uint32_t *d_pend, uint64_t *n_pend);
+
 int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                 uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
                 uint64_t cap, uint64_t *n_out) {
+    return seed_device_ex(ctx, d_bases, n_bases, d_rec_off, off_bias, n_rec, k, c, sem, with_pos, d_out, cap, n_out, 0, 0, 0,
+                          nullptr, nullptr);
+}
+
+int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
+                   uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
+                   uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
+                   uint32_t *d_pend, uint64_t *n_pend) {
     *n_out = 0;
+    if (n_pend) *n_pend = 0;
+    if (emit_events && (!d_pend || !n_pend || cap >= 0xFFFFFFFFull)) { set_error("event emission needs a pending list and cap < 2^32"); return SYL_ERR_ARG; }
     if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
     if (!(k == 21 || k == 31)) {
         set_error("k must be 21 or 31 (the reference panics otherwise, src/avx2_seeding.rs:46-52)");
@@ -435,7 +517,7 @@ int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const ui
         k_tile_first_rec<<<(unsigned)nb, bs, 0, st>>>(d_rec_off, off_bias, n_rec, n_tiles, tile_rec.p);
         ctx->launches++;
     }
-    SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint64_t), st));
+    SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint64_t), st));  // [0] survivors, [1] pending events
     const uint64_t thr = fmh_threshold(c);
     const size_t smem = sizeof(SeedSmem);
     static const int variant = []() {
@@ -444,28 +526,29 @@ int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const ui
         return v < 0 ? 0 : (v > 2 ? 2 : v);
     }();
     using kern_t = void (*)(const uint8_t *, uint64_t, const uint64_t *, uint64_t, const uint32_t *, uint64_t, int, int,
-                            syl_survivor *, uint64_t, unsigned long long *, const ShiftMul);
+                            void *, uint64_t, unsigned long long *, const ShiftMul, uint64_t, int, uint32_t *);
     // VAR 1/2 (xor-shifts on the FMA pipe via IMAD.HI) measured 3-8 % slower on B200: IMAD.HI and
     // IMAD.WIDE occupy the fmaheavy pipe for 4 cycles, which then becomes the limiter. Kept as a
     // compile-time option (-DSEED_ALL_VARIANTS) for future tuning.
 #ifdef SEED_ALL_VARIANTS
-    static const kern_t table[2][3] = {{k_seed<31, 0>, k_seed<31, 1>, k_seed<31, 2>},
-                                       {k_seed<21, 0>, k_seed<21, 1>, k_seed<21, 2>}};
-    kern_t kern = table[k == 31 ? 0 : 1][variant];
+    static const kern_t table[2][3] = {{k_seed<31, 0, 0>, k_seed<31, 1, 0>, k_seed<31, 2, 0>},
+                                       {k_seed<21, 0, 0>, k_seed<21, 1, 0>, k_seed<21, 2, 0>}};
+    kern_t kern = emit_events ? (k == 31 ? k_seed<31, 0, 1> : k_seed<21, 0, 1>) : table[k == 31 ? 0 : 1][variant];
 #else
     (void)variant;
-    kern_t kern = k == 31 ? k_seed<31, 0> : k_seed<21, 0>;
+    kern_t kern = emit_events ? (k == 31 ? k_seed<31, 0, 1> : k_seed<21, 0, 1>)
+                              : (k == 31 ? k_seed<31, 0, 0> : k_seed<21, 0, 0>);
 #endif
     const ShiftMul smul = {1u << 8, 1u << 18, 1u << 4};
     SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev0, st));
     kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
         d_bases, n_bases, d_rec_off, off_bias, tile_rec.p, thr, sem, with_pos, d_out, cap,
-        reinterpret_cast<unsigned long long *>(ctx->d_counters), smul);
+        reinterpret_cast<unsigned long long *>(ctx->d_counters), smul, rec_base, no_dedup, d_pend);
     if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev1, st));
     ctx->launches++;
     SYL_CUDA(cudaGetLastError());
-    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SYL_CUDA(cudaStreamSynchronize(st));
     if (ctx->timing) {
         float ms = 0.f;
@@ -475,6 +558,7 @@ int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const ui
         ctx->seed_bases += n_bases;
     }
     *n_out = ctx->h_counters[0];
+    if (n_pend) *n_pend = ctx->h_counters[1];
     if (*n_out > cap) {
         set_error("survivor buffer too small");
         return SYL_ERR_CAPACITY;
