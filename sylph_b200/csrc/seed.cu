@@ -30,6 +30,9 @@ constexpr int SEED_THREADS = 256;
 #ifndef SEED_TILE_CFG
 #define SEED_TILE_CFG 32768
 #endif
+#ifndef SEED_CANON_MODE
+#define SEED_CANON_MODE 3  // 0 integer compare; 1 FP64 compare + SEL; 2 FP64 compare + predicated IMAD moves; 3 = 2 + candidate bit by predicated IMAD
+#endif
 #ifndef SEED_MINB_CFG
 #define SEED_MINB_CFG 4
 #endif
@@ -74,7 +77,7 @@ static_assert(sizeof(SeedMeta) <= SEED_ASC_BYTES, "meta must fit in the dead ASC
 
 // Multipliers 2^(32-s) for the three xor-shift distances, passed as kernel parameters so that
 // ptxas cannot strength-reduce "mul.hi by a power of two" back into an ALU-pipe shift.
-struct ShiftMul { uint32_t m24, m14, m28; };  // = 1<<8, 1<<18, 1<<4
+struct ShiftMul { uint32_t m24, m14, m28, one, zero; };  // = 1<<8, 1<<18, 1<<4, 1, 0 (opaque to ptxas)
 
 // 64-bit multiply by a 32-bit constant as IMAD.WIDE + IMAD (2 FMA-pipe instructions)
 __device__ __forceinline__ void mul64c(uint32_t lo, uint32_t hi, uint32_t c, uint32_t &plo, uint32_t &phi) {
@@ -419,11 +422,34 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
                 const uint32_t f_lo = __funnelshift_l(F[jb + 2], F[jb + 1], sft);
                 const uint32_t r_lo = __funnelshift_r(G[jb], G[jb + 1], sft);
                 const uint32_t r_hi = __funnelshift_r(G[jb + 1], G[jb + 2], sft) & HI_MASK;
+                // canonical k-mer = min(forward, reverse complement), src/seeding.rs:131-136.  Both are
+                // < 2^62, so as IEEE doubles they are finite, non-negative and ordered like the
+                // integers: ONE compare on the FP64 pipe replaces the two-instruction 64-bit integer
+                // compare on the ALU pipe, which is this loop's limiter.
+                uint32_t c_lo, c_hi;
+#if SEED_CANON_MODE == 0
                 const uint64_t f = ((uint64_t)f_hi << 32) | f_lo, rr = ((uint64_t)r_hi << 32) | r_lo;
-                const uint64_t canon = f < rr ? f : rr;  // src/seeding.rs:131-136
-                const uint32_t hh = hash_hi32<VAR>((uint32_t)canon, (uint32_t)(canon >> 32), smul);
+                const uint64_t canon = f < rr ? f : rr;
+                c_lo = (uint32_t)canon; c_hi = (uint32_t)(canon >> 32);
+#elif SEED_CANON_MODE == 1  // FP64 compare, SEL on the ALU pipe
+                asm("{\n\t.reg .pred p;\n\t.reg .f64 a, b;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\t"
+                    "setp.lt.f64 p, a, b;\n\tselp.b32 %0, %2, %4, p;\n\tselp.b32 %1, %3, %5, p;\n\t}"
+                    : "=r"(c_lo), "=r"(c_hi) : "r"(f_lo), "r"(f_hi), "r"(r_lo), "r"(r_hi));
+#else
+                c_lo = r_lo; c_hi = r_hi;
+                asm("{\n\t.reg .pred p;\n\t.reg .f64 a, b;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\t"
+                    "setp.lt.f64 p, a, b;\n\t@p mad.lo.u32 %0, %2, %6, %7;\n\t@p mad.lo.u32 %1, %3, %6, %7;\n\t}"
+                    : "+r"(c_lo), "+r"(c_hi) : "r"(f_lo), "r"(f_hi), "r"(r_lo), "r"(r_hi), "r"(smul.one), "r"(smul.zero));
+#endif
+                const uint32_t hh = hash_hi32<VAR>(c_lo, c_hi, smul);
+#if SEED_CANON_MODE >= 3
+                // candidate bit set by a predicated IMAD (FMA pipe): the bits are distinct, so add == or
+                asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+                    : "+r"(cand) : "r"(hh), "r"(thr_hi), "r"(smul.one), "r"(1u << i));
+#else
                 asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
                     : "+r"(cand) : "r"(hh), "r"(thr_hi), "r"(1u << i));
+#endif
             }
             if (n < SEED_W) cand &= (1u << n) - 1u;  // n >= 1
             // candidates go to a CTA-wide list and are re-derived exactly by all threads afterwards
@@ -539,7 +565,7 @@ int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const
     kern_t kern = emit_events ? (k == 31 ? k_seed<31, 0, 1> : k_seed<21, 0, 1>)
                               : (k == 31 ? k_seed<31, 0, 0> : k_seed<21, 0, 0>);
 #endif
-    const ShiftMul smul = {1u << 8, 1u << 18, 1u << 4};
+    const ShiftMul smul = {1u << 8, 1u << 18, 1u << 4, 1u, 0u};
     SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev0, st));
     kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
