@@ -303,11 +303,15 @@ def bench_sketch(args, ctx, rank, world, local):
     ho.copy_(off)
     torch.cuda.synchronize()
     hb_np, ho_np = hb.numpy(), ho.numpy().view(np.uint64)
+    # result buffers: pinned and reused across steps, as a caller that sketches file after file would
+    out_cap = int(n_bases // C * 2 + 65536)
+    oh = torch.empty(out_cap, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    oc = torch.empty(out_cap, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
     e2e_state = {}
 
     def step_e2e():
         s = ctx.sketch_sequences(hb_np, ho_np, k=K, c=C)
-        h, c = s.download()
+        h, c = s.download(oh, oc)
         e2e_state["n"] = len(h)
         s.free()
 

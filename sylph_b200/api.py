@@ -287,13 +287,21 @@ class Sample:
     def num_dup_removed(self):
         return int(_lib.lib().syl_sample_num_dup_removed(self._h))
 
-    def download(self):
+    def download(self, hash_out=None, count_out=None):
+        """-> (hash u64[n] ascending, count u32[n]).  hash_out / count_out: optional caller buffers
+        (e.g. views of pinned memory, reused across calls) with room for n entries; the returned
+        arrays are then views of them."""
         n = len(self)
-        h = np.empty(n, dtype=np.uint64)
-        c = np.empty(n, dtype=np.uint32)
-        _lib.check(_lib.lib().syl_sample_download(self.ctx._h, self._h, h.ctypes.data_as(C.c_void_p),
-                                                  c.ctypes.data_as(C.c_void_p)))
-        return h, c
+        if hash_out is None:
+            hash_out = np.empty(n, dtype=np.uint64)
+        if count_out is None:
+            count_out = np.empty(n, dtype=np.uint32)
+        if hash_out.dtype != np.uint64 or count_out.dtype != np.uint32 or hash_out.size < n or count_out.size < n \
+                or not hash_out.flags.c_contiguous or not count_out.flags.c_contiguous:
+            raise ValueError("download buffers must be contiguous uint64 / uint32 arrays with >= %d entries" % n)
+        _lib.check(_lib.lib().syl_sample_download(self.ctx._h, self._h, hash_out.ctypes.data_as(C.c_void_p),
+                                                  count_out.ctypes.data_as(C.c_void_p)))
+        return hash_out[:n], count_out[:n]
 
     def free(self):
         if self._h:

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libsylph_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "sylph_b200.h")
-SOURCES = ["api.cu", "seed.cu", "sample.cu", "genome.cu", "contain.cu"]
+SOURCES = ["api.cu", "seed.cu", "seed_k31_sv.cu", "seed_k31_ev.cu", "seed_k21_sv.cu", "seed_k21_ev.cu", "sample.cu", "genome.cu", "contain.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -46,6 +46,10 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
+    if os.path.getmtime(os.path.abspath(__file__)) > t:  # source list / flags changed
+        return True
+    if any(not os.path.exists(os.path.join(OBJ, s[:-3] + ".o")) for s in _sources()):
+        return True
     return _headers_mtime() > t or any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in _sources())
 
 

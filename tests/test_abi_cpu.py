@@ -68,7 +68,7 @@ def test_sass_is_blackwell_native():
     if not os.path.exists(cuobjdump):
         pytest.skip("no cuobjdump")
     build.build()
-    obj = os.path.join(build.OBJ, "seed.o")
+    obj = os.path.join(build.OBJ, "seed_k31_ev.o")  # k_seed<31, events> for the three run lengths
     out = subprocess.run([cuobjdump, "-sass", obj], stdout=subprocess.PIPE, text=True).stdout
     assert "sm_100a" in out or "SM100" in out.upper()
     assert "UBLKCP" in out and "SYNCS" in out

@@ -63,6 +63,17 @@ def test_c_values(ctx, c):
     check(ctx, buf, off, 31, c, 1, True)
 
 
+@pytest.mark.parametrize("L", [46, 50, 54, 56, 58, 60, 62, 100, 150, 250, 300])
+@pytest.mark.parametrize("sem", [1, 0])
+def test_fixed_length_reads_every_run_length(ctx, L, sem):
+    """The launcher picks the run length W in {24, 30, 32} from the mean record length (seed.cu
+    pick_run_length); these lengths reach every instantiated W under both window sets."""
+    rng = np.random.default_rng(1000 + L + sem)
+    buf, off = random_records(rng, [L] * 1500 + [L + 1, L - 1, 3 * L, 7], alphabet=b"ACGTN")
+    check(ctx, buf, off, 31, 7, sem, False)
+    check(ctx, buf, off, 31, 7, sem, True)
+
+
 def test_single_long_contig_tile_boundaries(ctx):
     rng = np.random.default_rng(5)
     for L in (32768, 32768 + 30, 32768 + 31, 2 * 32768 - 1, 3 * 32768 + 123):

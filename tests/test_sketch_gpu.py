@@ -105,6 +105,20 @@ def test_reads_device_resident_and_empty(ctx):
     assert len(e) == 0
 
 
+def test_sample_download_into_pinned_buffers(ctx):
+    import torch
+    from sylph_b200 import synth
+    b, o = synth.reads(20000, n_comm=2, genome_len=100000)
+    s = ctx.sketch_sequences(b.numpy(), o.numpy().astype(np.uint64))
+    h, c = s.download()
+    oh = torch.empty(len(s) + 100, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    oc = torch.empty(len(s) + 100, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    h2, c2 = s.download(oh, oc)
+    assert np.array_equal(h, h2) and np.array_equal(c, c2) and np.shares_memory(h2, oh)
+    with pytest.raises(ValueError):
+        s.download(oh[:10], oc)
+
+
 def test_genomes_ecoli(ctx):
     bufs, coffs, goff = [], [0], [0]
     for name in ("e.coli-EC590.fasta.gz", "e.coli-o157.fasta.gz", "e.coli-K12.fasta.gz"):
