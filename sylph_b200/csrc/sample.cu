@@ -299,13 +299,20 @@ __global__ void k_group_ranges(const uint32_t *__restrict__ boff, uint32_t nbk, 
     g_be[g] = be;
 }
 
+__device__ __forceinline__ uint32_t bucket_of(uint64_t h, uint64_t Mb, uint32_t nbk) {
+    const uint32_t b = (uint32_t)__umul64hi(h, Mb);
+    return b < nbk ? b : nbk - 1;
+}
+
 // One CTA per group (<= GRP_CAP events, consecutive buckets). Shared-memory traffic is what
 // bounds this kernel, so instead of sorting all events (a 128-bit-key bitonic sort was 4x slower)
-// it (1) groups equal hashes with an open-addressing table, (2) orders each k-mer's few events
-// by read index and replays dup_removal_lsh_full_exact, (3) sorts only the resulting unique
-// (hash, count) pairs (about n/3 single-word keys) with a bitonic network.
+// it (1) groups equal hashes with an open-addressing table, (2) replays
+// dup_removal_lsh_full_exact on each k-mer's first events in read order, (3) orders the resulting
+// unique (hash, count) pairs: the group's buckets are already monotone in the hash, so a pair's
+// position is its bucket's offset plus its rank among the ~10 pairs of the same bucket (a bitonic
+// sort of the pairs remains for groups spanning more than GRP_LB buckets).
 constexpr int GRP_SLOTS = 2048;  // table slots (load factor <= 0.5)
-constexpr int GRP_SHORT = 8;     // k-mers with up to this many events: one thread each; longer: one warp each
+constexpr int GRP_LB = 512;      // most buckets per group for the bucket-rank output ordering (else bitonic sort)
 constexpr int GRP_SELECT_STEPS = 64;  // selection steps before a duplicate-heavy k-mer goes to the generic path
 
 struct GroupSmem {
@@ -315,17 +322,17 @@ struct GroupSmem {
     uint64_t p1[GRP_CAP];              //  8 KB  second pair key per event
     uint16_t scnt[GRP_SLOTS];          //  4 KB  events per slot, then fill cursor, then the k-mer's count
     uint16_t soff[GRP_SLOTS + 2];      //  4 KB  exclusive scan of scnt
-    uint16_t ev_slot[GRP_CAP];         //  2 KB
+    uint16_t ev_slot[GRP_CAP];         //  2 KB  slot per event | after the member fill: 2 x GRP_LB bucket counters / offsets
     uint16_t member[GRP_CAP];          //  2 KB  event indices grouped by slot
     uint16_t occ[GRP_CAP];             //  2 KB  occupied slots, compacted
     uint32_t wtot[GRP_THREADS / 32], wocc[GRP_THREADS / 32];
-    uint32_t e0, e1, overflow, dups, nuniq, nlong;
-    uint16_t longs[GRP_CAP / 2];      //  1 KB  slots of k-mers with more than GRP_SHORT events
+    uint32_t e0, e1, overflow, dups, nuniq, nlong, lb_n, bf;
+    uint16_t longs[GRP_CAP / 2];      //  1 KB  slots of k-mers that need the warp-cooperative replay
 };
 
 __global__ void __launch_bounds__(GRP_THREADS)
 k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ boff, const uint32_t *__restrict__ g_bf,
-              const uint32_t *__restrict__ g_be, uint32_t cap,
+              const uint32_t *__restrict__ g_be, uint32_t cap, uint64_t Mb, uint32_t nbk,
               int no_dedup, uint64_t *__restrict__ st_hash, uint32_t *__restrict__ st_cnt,
               uint32_t *__restrict__ g_nuniq, uint32_t *__restrict__ g_e0, uint32_t *__restrict__ g_n,
               uint8_t *__restrict__ g_fallback, unsigned long long *__restrict__ n_dup) {
@@ -336,13 +343,15 @@ k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ bo
     if (tid == 0) {
         S.e0 = boff[g_bf[g]];  // boff[nbk] = N
         S.e1 = boff[g_be[g]];
+        S.bf = g_bf[g];
+        S.lb_n = g_be[g] - g_bf[g];
         S.overflow = 0;
         S.dups = 0;
         S.nlong = 0;
     }
     for (int i = tid; i < GRP_SLOTS; i += GRP_THREADS) { S.ht[i] = 0xFFFFFFFFFFFFFFFFull; S.scnt[i] = 0; }
     __syncthreads();
-    const uint32_t e0 = S.e0, n = S.e1 - S.e0;
+    const uint32_t e0 = S.e0, n = S.e1 - S.e0, bf = S.bf;
     if (tid == 0) { g_e0[g] = e0; g_n[g] = n; g_nuniq[g] = 0; g_fallback[g] = 0; }
     if (n == 0) return;
     if (n > cap) { if (tid == 0) g_fallback[g] = 1; return; }
@@ -403,45 +412,74 @@ k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ bo
     }
     __syncthreads();
     // (2) replay dup_removal_lsh_full_exact (src/sketch.rs:690-731) per k-mer; the count lands in scnt.
-    //     Short segments (<= GRP_SHORT events): one thread each (insertion sort by read index).
-    //     Longer ones are queued and taken by whole warps: the lanes hold the segment's events and
-    //     hand out the next event in read order with a warp min-reduction, so only the events up
-    //     to c == 4 are ever touched (afterwards every event counts).
+    //     One thread per k-mer, registers only: a single pass over the k-mer's events keeps the four
+    //     smallest (read index, event) keys; those four are replayed in order.  The dedup set at any
+    //     point is simply "every pair key of the earlier paired events", so membership is a compare
+    //     against the earlier events' keys and nothing has to be inserted.  Four counted events reach
+    //     MAX_DEDUP_COUNT (src/constants.rs:14), after which every event counts.  Only a k-mer that
+    //     has more than four events AND a duplicate among the first four needs more; it is queued
+    //     for the warp-cooperative path below.
+    //     The thread also counts its k-mer into its bucket (local index) for the output ordering.
+    const uint32_t lb_n = S.lb_n;
+    uint16_t *lb_cnt = S.ev_slot, *lb_off = S.ev_slot + GRP_LB;  // ev_slot is dead: 2 x GRP_LB u16
+    if (lb_n <= (uint32_t)GRP_LB) {
+        for (int i = tid; i < GRP_LB; i += GRP_THREADS) { lb_cnt[i] = 0; }
+        __syncthreads();
+    }
     uint32_t my_dups = 0;
     for (uint32_t u = tid; u < nu; u += GRP_THREADS) {
         const uint32_t sl = S.occ[u];
         const uint32_t a0 = S.soff[sl], len = S.soff[sl + 1] - a0;
+        if (lb_n <= (uint32_t)GRP_LB) {
+            const uint32_t lb = bucket_of(S.ht[sl], Mb, nbk) - bf;
+            atomicAdd(reinterpret_cast<unsigned int *>(lb_cnt) + (lb >> 1), (lb & 1) ? 0x10000u : 1u);
+        }
         uint32_t c = 0;
         if (no_dedup || len == 1) {
             c = len;  // a first occurrence is never a duplicate (c == 0)
-        } else if (len > (uint32_t)GRP_SHORT) {
-            const uint32_t li = atomicAdd(&S.nlong, 1u);
-            S.longs[li] = (uint16_t)sl;  // at most n / (GRP_SHORT+1) < GRP_CAP/2 entries
-            continue;
         } else {
-            uint16_t ord[GRP_SHORT];
-            for (uint32_t e = 0; e < len; e++) {  // insertion sort by (read index << 1 | no_pair)
-                const uint16_t m = S.member[a0 + e];
-                const uint64_t key = S.rf[m];
-                uint32_t q = e;
-                while (q > 0 && S.rf[ord[q - 1]] > key) { ord[q] = ord[q - 1]; q--; }
-                ord[q] = m;
-            }
-            uint64_t D[2 * GRP_SHORT];
-            uint32_t nset = 0;
+            constexpr uint64_t INF = 0xFFFFFFFFFFFFFFFFull;
+            uint64_t k0 = INF, k1 = INF, k2 = INF, k3 = INF;  // (recflag << 10 | event) ascending
             for (uint32_t e = 0; e < len; e++) {
-                if (c >= 4u) { c += len - e; break; }  // MAX_DEDUP_COUNT (src/constants.rs:14)
-                const uint32_t m = ord[e];
-                if (S.rf[m] & NO_PAIR) { c++; continue; }
-                const uint64_t ka = S.p0[m], kb = S.p1[m];
-                bool ret = false, found = false;
-                for (uint32_t q = 0; q < nset; q++) found |= (D[q] == ka);
-                if (found) ret = c > 0; else D[nset++] = ka;
-                found = false;
-                for (uint32_t q = 0; q < nset; q++) found |= (D[q] == kb);
-                if (found) ret = ret || c > 0; else D[nset++] = kb;
-                if (ret) my_dups++; else c++;
+                const uint32_t m = S.member[a0 + e];
+                uint64_t key = (S.rf[m] << 10) | m;
+                if (key < k3) {
+                    k3 = key;
+                    if (k3 < k2) { const uint64_t t = k2; k2 = k3; k3 = t; }
+                    if (k2 < k1) { const uint64_t t = k1; k1 = k2; k2 = t; }
+                    if (k1 < k0) { const uint64_t t = k0; k0 = k1; k1 = t; }
+                }
             }
+            const uint64_t ks[4] = {k0, k1, k2, k3};
+            uint64_t A[4], B[4];
+            bool paired[4];
+            uint32_t dups = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                paired[j] = false;
+                A[j] = B[j] = 0;
+                if (ks[j] == INF) continue;  // len < 4
+                const uint32_t m = (uint32_t)ks[j] & 1023u;
+                if ((ks[j] >> 10) & NO_PAIR) { c++; continue; }
+                const uint64_t ka = S.p0[m], kb = S.p1[m];
+                bool found = (kb == ka);
+#pragma unroll
+                for (int i = 0; i < j; i++)
+                    found |= paired[i] && (ka == A[i] || ka == B[i] || kb == A[i] || kb == B[i]);
+                paired[j] = true; A[j] = ka; B[j] = kb;
+                // found on the SECOND key only because it equals the first does not make a duplicate
+                // of an earlier read, but sketch.rs:704-722 still returns true when cur > 0
+                if (found && c > 0) dups++; else c++;
+            }
+            if (len > 4u) {
+                if (c >= 4u) c += len - 4u;
+                else {  // a duplicate among the first four: replay the whole k-mer cooperatively
+                    const uint32_t li = atomicAdd(&S.nlong, 1u);
+                    S.longs[li] = (uint16_t)sl;
+                    continue;
+                }
+            }
+            my_dups += dups;
         }
         S.scnt[sl] = (uint16_t)c;  // c <= len <= GRP_CAP
     }
@@ -488,7 +526,48 @@ k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ bo
     if (my_dups) atomicAdd(&S.dups, my_dups);
     __syncthreads();
     if (S.overflow) { if (tid == 0) g_fallback[g] = 1; return; }
-    // (3) unique pairs into the (now dead) rf / p0 arrays, sorted by hash with a bitonic network
+    // (3) output order.  Bucket-rank path: lb_cnt holds the k-mers per bucket (counted in (2)).
+    if (lb_n <= (uint32_t)GRP_LB) {
+        uint16_t *list = S.member;  // event grouping is dead: k-mer slots ordered by bucket
+        {   // exclusive scan of lb_cnt (GRP_LB = 2 per thread) -> lb_off, counters reset as cursors
+            constexpr int PER = GRP_LB / GRP_THREADS;
+            uint32_t loc[PER], tot = 0;
+#pragma unroll
+            for (int e = 0; e < PER; e++) { loc[e] = lb_cnt[tid * PER + e]; tot += loc[e]; }
+            uint32_t inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            if (lane == 31) S.wtot[wid] = inc;
+            __syncthreads();
+            uint32_t base = inc - tot;
+#pragma unroll
+            for (int w = 0; w < GRP_THREADS / 32; w++) if (w < wid) base += S.wtot[w];
+#pragma unroll
+            for (int e = 0; e < PER; e++) { lb_off[tid * PER + e] = (uint16_t)base; base += loc[e]; lb_cnt[tid * PER + e] = 0; }
+            __syncthreads();
+        }
+        for (uint32_t u = tid; u < nu; u += GRP_THREADS) {
+            const uint32_t sl = S.occ[u];
+            const uint32_t lb = bucket_of(S.ht[sl], Mb, nbk) - bf;
+            const unsigned int old = atomicAdd(reinterpret_cast<unsigned int *>(lb_cnt) + (lb >> 1), (lb & 1) ? 0x10000u : 1u);
+            list[lb_off[lb] + ((lb & 1) ? (old >> 16) : (old & 0xFFFFu))] = (uint16_t)sl;
+        }
+        __syncthreads();
+        for (uint32_t u = tid; u < nu; u += GRP_THREADS) {
+            const uint32_t sl = S.occ[u];
+            const unsigned long long h = S.ht[sl];
+            const uint32_t lb = bucket_of(h, Mb, nbk) - bf;
+            const uint32_t q0 = lb_off[lb], q1 = q0 + ((lb & 1) ? (reinterpret_cast<unsigned int *>(lb_cnt)[lb >> 1] >> 16)
+                                                                : (reinterpret_cast<unsigned int *>(lb_cnt)[lb >> 1] & 0xFFFFu));
+            uint32_t r = 0;
+            for (uint32_t q = q0; q < q1; q++) r += (S.ht[list[q]] < h) ? 1u : 0u;
+            st_hash[e0 + q0 + r] = h;
+            st_cnt[e0 + q0 + r] = S.scnt[sl];
+        }
+        if (tid == 0) { g_nuniq[g] = nu; if (S.dups) atomicAdd(n_dup, (unsigned long long)S.dups); }
+        return;
+    }
+    // Bitonic path: unique pairs into the (now dead) rf / p0 arrays, sorted by hash
     uint64_t *uh = S.rf;
     uint32_t *uc = reinterpret_cast<uint32_t *>(S.p0);
     uint32_t P = 32;
@@ -789,7 +868,7 @@ struct SampleBuilder {
         k_scatter_events<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, boff.p, cursor.p, part.p);
         SYL_CUDA(cudaFuncSetAttribute(k_group_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
         k_group_ranges<<<nblk(ng, 256), 256, 0, st>>>(boff.p, nbk, ng, g_bf.p, g_be.p);
-        k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, no_dedup, st_hash.p, st_cnt.p,
+        k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, Mb, nbk, no_dedup, st_hash.p, st_cnt.p,
                                                                    g_nuniq.p, g_e0.p, g_n.p, g_fb.p, d_ndup);
         k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
         k_fallback_sizes<<<nblk(ng, 256), 256, 0, st>>>(g_n.p, g_fb.p, ng, fsz.p);
