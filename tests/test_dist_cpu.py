@@ -1,5 +1,5 @@
 """CPU suite: the N>1 host logic (sharding, variable-length all-gather, row merge, survivor-db
-gather) over gloo with world_size 2.  Compute kernels are not involved (no GPU here)."""
+gather) over gloo with world_size 2 and 3.  Compute kernels are not involved (no GPU here)."""
 import os
 import socket
 
@@ -42,11 +42,21 @@ def _worker(rank, world, port, q):
                "gn_size": np.array([10 + rank, 20 + rank], dtype=np.uint64)}
         gid = np.array([50 * rank + 1, 50 * rank + 9], dtype=np.uint64)
         m, ids = D.gather_survivor_genomes(sub, gid)
-        assert ids.tolist() == [1, 9, 51, 59]
-        assert m["kmer_off"].tolist() == [0, 3, 4, 8, 11]
-        assert m["tracked_off"].tolist() == [0, 1, 1, 3, 3]
-        assert m["kmers"].tolist() == [0, 1, 2, 3, 100, 101, 102, 103, 104, 105, 106]
-        assert m["gn_size"].tolist() == [10, 20, 11, 21]
+        e_ids, e_koff, e_toff, e_km, e_gn = [], [0], [0], [], []
+        for r in range(world):  # what the concatenation in rank order must look like
+            e_ids += [50 * r + 1, 50 * r + 9]
+            e_koff += [e_koff[-1] + 3 + r, e_koff[-1] + 3 + r + 1 + 2 * r]
+            e_toff += [e_toff[-1] + r + 1, e_toff[-1] + r + 1]
+            e_km += list(range(100 * r, 100 * r + 4 + 3 * r))
+            e_gn += [10 + r, 20 + r]
+        assert ids.tolist() == e_ids
+        assert m["kmer_off"].tolist() == e_koff
+        assert m["tracked_off"].tolist() == e_toff
+        assert m["kmers"].tolist() == e_km
+        assert m["gn_size"].tolist() == e_gn
+        if world == 2:  # literal pins
+            assert ids.tolist() == [1, 9, 51, 59] and m["kmer_off"].tolist() == [0, 3, 4, 8, 11]
+            assert m["kmers"].tolist() == [0, 1, 2, 3, 100, 101, 102, 103, 104, 105, 106]
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
@@ -65,15 +75,16 @@ def test_shard_range():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_gloo_world2_gather_and_merge():
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_gather_and_merge(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
