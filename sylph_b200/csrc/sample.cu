@@ -26,7 +26,7 @@ namespace syl {
 int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                    uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
                    uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
-                   uint32_t *d_pend, uint64_t *n_pend);
+                   uint32_t *d_pend, uint64_t *n_pend, uint32_t *d_bucket_cnt, uint64_t Mb, uint32_t nbk);
 
 }  // namespace syl
 
@@ -266,7 +266,7 @@ __global__ void k_scatter_events(const EventRec *__restrict__ ev, uint64_t n,
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
-    const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+    const uint4 lo = __ldcs(src), hi = __ldcs(src + 1);  // read once: keep L2 for the scattered writes
     const uint64_t h = ((uint64_t)lo.y << 32) | lo.x;
     uint32_t b = (uint32_t)__umul64hi(h, Mb);
     if (b >= nbk) b = nbk - 1;
@@ -358,7 +358,7 @@ k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ bo
     // (1) stage the events, group equal hashes: slot per event, events per slot
     for (uint32_t i = tid; i < n; i += GRP_THREADS) {
         const uint4 *src = reinterpret_cast<const uint4 *>(part + e0 + i);
-        const uint4 a = src[0], b = src[1];
+        const uint4 a = __ldcs(src), b = __ldcs(src + 1);  // read once
         const unsigned long long h = ((unsigned long long)a.y << 32) | a.x;
         S.rf[i] = ((uint64_t)a.w << 32) | a.z;
         S.p0[i] = ((uint64_t)b.y << 32) | b.x;
@@ -675,6 +675,27 @@ struct SampleBuilder {
     uint64_t n_reads = 0, n_bases = 0, n_events = 0, cap = 0;
     DevBuf<EventRec> b_ev;  // event array (a scratch block of the ctx cache)
     EventRec *ev = nullptr;
+    // Post-pass buckets: fixed before the first batch from the expected number of events, so that
+    // k_seed can fill the bucket histogram while it flushes the events.
+    uint64_t expect_bases = 0, expect_reads = 0;
+    uint32_t nbk = 0;
+    uint64_t Mb = 0;
+    DevBuf<uint32_t> cnt;
+    bool hist_valid = true;  // false after a capacity retry (partial counts of the failed attempt)
+
+    int plan_buckets() {
+        if (nbk) return SYL_OK;
+        const uint64_t win = expect_bases > expect_reads * (uint64_t)(k - 1) ? expect_bases - expect_reads * (uint64_t)(k - 1) : 0;
+        const uint64_t n_exp = win / c;
+        nbk = 4096;
+        while (nbk < n_exp / 32 && nbk < (1u << 22)) nbk <<= 1;
+        const uint64_t thr = fmh_threshold(c);
+        unsigned __int128 mb = ((unsigned __int128)nbk << 64) / ((unsigned __int128)thr + 1);
+        Mb = mb > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)mb;
+        SYL_TRY(cnt.alloc(nbk, ctx->stream));
+        SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, ctx->stream));
+        return SYL_OK;
+    }
 
     int reserve(uint64_t need) {
         if (need <= cap) return SYL_OK;
@@ -698,13 +719,14 @@ struct SampleBuilder {
         if (scap > nb) scap = nb + 16;
         uint64_t n = 0, npend = 0;
         DevBuf<uint32_t> pend;
+        SYL_TRY(plan_buckets());
         for (;;) {
             if (scap >= 0xFFFFFFFFull) { set_error("more than 2^32-2 survivor events in one batch"); return SYL_ERR_ARG; }
             SYL_TRY(reserve(n_events + scap));
             SYL_TRY(pend.alloc(scap, st));
             int rc = seed_device_ex(ctx, d_bases, nb, d_off, off_bias, nr, k, c, sem, /*with_pos=*/0, ev + n_events, scap, &n,
-                                    /*emit_events=*/1, n_reads, no_dedup, pend.p, &npend);
-            if (rc == SYL_ERR_CAPACITY) { scap = n + 16; continue; }
+                                    /*emit_events=*/1, n_reads, no_dedup, pend.p, &npend, cnt.p, Mb, nbk);
+            if (rc == SYL_ERR_CAPACITY) { scap = n + 16; hist_valid = false; continue; }
             if (rc != SYL_OK) return rc;
             break;
         }
@@ -833,18 +855,13 @@ struct SampleBuilder {
             *out = s;
             return SYL_OK;
         }
-        // ---- primary path: bucket partition + CTA-local sort/dedup
-        uint32_t nbk = 4096;
-        while (nbk < N / 32 && nbk < (1u << 22)) nbk <<= 1;
-        const uint64_t thr = fmh_threshold(c);
-        unsigned __int128 mb = ((unsigned __int128)nbk << 64) / ((unsigned __int128)thr + 1);
-        const uint64_t Mb = mb > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)mb;
+        // ---- primary path: bucket partition + CTA-local sort/dedup (nbk, Mb, cnt: plan_buckets)
         const uint32_t ng = (uint32_t)(N / GRP_T + 1);
-        DevBuf<uint32_t> cnt, boff, cursor, st_cnt, g_nuniq, g_e0, g_n, uoff, fsz, foff, g_bf, g_be, g_src;
+        DevBuf<uint32_t> boff, cursor, st_cnt, g_nuniq, g_e0, g_n, uoff, fsz, foff, g_bf, g_be, g_src;
         DevBuf<uint64_t> st_hash;
         DevBuf<uint8_t> g_fb;
         DevBuf<EventRec> part;
-        if ((rc = cnt.alloc(nbk, st)) || (rc = boff.alloc((uint64_t)nbk + 1, st)) || (rc = cursor.alloc(nbk, st)) ||
+        if ((rc = boff.alloc((uint64_t)nbk + 1, st)) || (rc = cursor.alloc(nbk, st)) ||
             (rc = part.alloc(N, st)) || (rc = st_hash.alloc(N, st)) || (rc = st_cnt.alloc(N, st)) ||
             (rc = g_nuniq.alloc(ng, st)) || (rc = g_e0.alloc(ng, st)) || (rc = g_n.alloc(ng, st)) ||
             (rc = g_fb.alloc(ng, st)) || (rc = uoff.alloc((uint64_t)ng + 1, st)) || (rc = fsz.alloc(ng, st)) ||
@@ -852,10 +869,13 @@ struct SampleBuilder {
             (rc = g_src.alloc(ng, st)))
             return fail(rc);
         unsigned long long *d_ndup = reinterpret_cast<unsigned long long *>(ctx->d_counters + 2);
-        SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, st));
         SYL_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)nbk * 4, st));
         SYL_CUDA(cudaMemsetAsync(d_ndup, 0, 8, st));
-        k_bucket_hist<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, cnt.p);
+        if (!hist_valid) {  // recount: a retried batch left partial counts behind
+            SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, st));
+            k_bucket_hist<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, cnt.p);
+            ctx->launches++;
+        }
         {   // boff = exclusive scan of cnt (nbk >= 4096 entries): local scans, scan of block totals, add back
             const uint32_t nblk1 = nbk / 1024;
             DevBuf<uint32_t> btot, boff2;
@@ -873,7 +893,7 @@ struct SampleBuilder {
         k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
         k_fallback_sizes<<<nblk(ng, 256), 256, 0, st>>>(g_n.p, g_fb.p, ng, fsz.p);
         k_scan_u32<<<1, 1024, 0, st>>>(fsz.p, ng, foff.p);
-        ctx->launches += 7;
+        ctx->launches += 6;
         SYL_CUDA(cudaGetLastError());
         SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 1, uoff.p + ng, 4, cudaMemcpyDeviceToHost, st));
         SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, foff.p + ng, 4, cudaMemcpyDeviceToHost, st));
@@ -931,6 +951,8 @@ int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bas
     SYL_CUDA(cudaSetDevice(ctx->device));
     syl::tl_ctx = ctx;
     SampleBuilder b{ctx, k, c, no_dedup, sem};
+    b.expect_bases = n_bases;
+    b.expect_reads = n_reads;
     cudaStream_t st = ctx->stream;
     if (mem == SYL_MEM_DEVICE) {
         SYL_TRY(b.add(bases, n_bases, rec_off, 0, n_reads));

@@ -74,19 +74,19 @@ static int pick_run_length(uint64_t mean_len, int k, int sem, int with_pos) {
 int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                    uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
                    uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
-                   uint32_t *d_pend, uint64_t *n_pend);
+                   uint32_t *d_pend, uint64_t *n_pend, uint32_t *d_bucket_cnt, uint64_t Mb, uint32_t nbk);
 
 int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                 uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
                 uint64_t cap, uint64_t *n_out) {
     return seed_device_ex(ctx, d_bases, n_bases, d_rec_off, off_bias, n_rec, k, c, sem, with_pos, d_out, cap, n_out, 0, 0, 0,
-                          nullptr, nullptr);
+                          nullptr, nullptr, nullptr, 0, 0);
 }
 
 int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
                    uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
                    uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
-                   uint32_t *d_pend, uint64_t *n_pend) {
+                   uint32_t *d_pend, uint64_t *n_pend, uint32_t *d_bucket_cnt, uint64_t Mb, uint32_t nbk) {
     *n_out = 0;
     if (n_pend) *n_pend = 0;
     if (emit_events && (!d_pend || !n_pend || cap >= 0xFFFFFFFFull)) { set_error("event emission needs a pending list and cap < 2^32"); return SYL_ERR_ARG; }
@@ -126,7 +126,8 @@ int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const
     if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev0, st));
     kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
         d_bases, n_bases, d_rec_off, off_bias, tile_rec.p, thr, sem, with_pos, d_out, cap,
-        reinterpret_cast<unsigned long long *>(ctx->d_counters), smul, rec_base, no_dedup, d_pend);
+        reinterpret_cast<unsigned long long *>(ctx->d_counters), smul, rec_base, no_dedup, d_pend,
+        BucketHist{emit_events ? d_bucket_cnt : nullptr, Mb, nbk});
     if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev1, st));
     ctx->launches++;
     SYL_CUDA(cudaGetLastError());

@@ -56,6 +56,20 @@ static_assert(sizeof(SeedMeta) <= SEED_ASC_BYTES, "meta must fit in the dead ASC
 
 // Multipliers 2^(32-s) for the three xor-shift distances, passed as kernel parameters so that
 // ptxas cannot strength-reduce "mul.hi by a power of two" back into an ALU-pipe shift.
+// Histogram of the emitted events over the post-pass's hash buckets (sample.cu), filled while the
+// events are flushed so that the post-pass does not have to re-read them for it.
+struct BucketHist {
+    uint32_t *cnt;  // nullptr: off
+    uint64_t Mb;    // bucket = min(mulhi(hash, Mb), nbk - 1)
+    uint32_t nbk;
+    __device__ __forceinline__ void add(uint64_t h) const {
+        if (cnt) {
+            const uint32_t b = (uint32_t)__umul64hi(h, Mb);
+            atomicAdd(&cnt[b < nbk ? b : nbk - 1], 1u);
+        }
+    }
+};
+
 struct ShiftMul { uint32_t m24, m14, m28, one, zero; };  // = 1<<8, 1<<18, 1<<4, 1, 0 (opaque to ptxas)
 
 // 64-bit multiply by a 32-bit constant as IMAD.WIDE + IMAD (2 FMA-pipe instructions)
@@ -127,7 +141,7 @@ template <int K, int EMIT>
 __device__ __forceinline__ void seed_resolve(const SeedSmem &S, SeedMeta &M, uint32_t pw, int j, uint64_t rc, uint64_t thr,
                                              void *__restrict__ out, uint64_t cap,
                                              unsigned long long *__restrict__ g_count, uint64_t rec_base, int no_dedup,
-                                             uint32_t *__restrict__ pend) {
+                                             uint32_t *__restrict__ pend, const BucketHist bh) {
     constexpr uint32_t PAD = 64 - 2 * K;
     constexpr uint32_t HI_MASK = (1u << (32 - PAD)) - 1u;
     const uint32_t bitpos = 32u + 2u * pw - PAD;
@@ -179,6 +193,7 @@ __device__ __forceinline__ void seed_resolve(const SeedSmem &S, SeedMeta &M, uin
             if (gi < cap) {
                 reinterpret_cast<EventRec *>(out)[gi] = ev;
                 if (ev.recflag & EV_PENDING) pend[atomicAdd(g_count + 1, 1ull)] = (uint32_t)gi;
+                bh.add(ev.hash);
             }
         }
     }
@@ -189,7 +204,7 @@ __global__ void __launch_bounds__(SEED_THREADS, SEED_MINB_CFG)
 k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__restrict__ rec_off, uint64_t off_bias,
        const uint32_t *__restrict__ tile_rec, uint64_t thr, int sem, int with_pos,
        void *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count,
-       const ShiftMul smul, uint64_t rec_base, int no_dedup, uint32_t *__restrict__ pend) {
+       const ShiftMul smul, uint64_t rec_base, int no_dedup, uint32_t *__restrict__ pend, const BucketHist bh) {
     static_assert(W >= SEED_W_MIN && W <= SEED_W_MAX, "run length");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SeedSmem &S = *reinterpret_cast<SeedSmem *>(smem_raw);
@@ -419,7 +434,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
                 if (ci < (unsigned)SEED_CAND) {
                     M.cand[ci] = ((uint32_t)(p + i) << 8) | (uint32_t)j;
                 } else {  // list full (tiny c): resolve inline
-                    seed_resolve<K, EMIT>(S, M, (uint32_t)(p + i), j, rc, thr, out, cap, g_count, rec_base, no_dedup, pend);
+                    seed_resolve<K, EMIT>(S, M, (uint32_t)(p + i), j, rc, thr, out, cap, g_count, rec_base, no_dedup, pend, bh);
                 }
             }
         }
@@ -428,7 +443,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
             const unsigned int nc = min(M.cand_count, (unsigned)SEED_CAND);
             for (unsigned int ci = tid; ci < nc; ci += SEED_THREADS) {
                 const uint32_t e = M.cand[ci];
-                seed_resolve<K, EMIT>(S, M, e >> 8, (int)(e & 255u), rc, thr, out, cap, g_count, rec_base, no_dedup, pend);
+                seed_resolve<K, EMIT>(S, M, e >> 8, (int)(e & 255u), rc, thr, out, cap, g_count, rec_base, no_dedup, pend, bh);
             }
         }
         __syncthreads();  // table is rewritten by the next chunk
@@ -449,6 +464,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
                 reinterpret_cast<EventRec *>(out)[base + i] = ev;
                 // reads cut by the tile edge: pair keys are filled in by k_events_fix
                 if (ev.recflag & EV_PENDING) pend[atomicAdd(g_count + 1, 1ull)] = (uint32_t)(base + i);
+                bh.add(ev.hash);
             }
         }
     }
@@ -456,7 +472,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
 
 
 using seed_kern_t = void (*)(const uint8_t *, uint64_t, const uint64_t *, uint64_t, const uint32_t *, uint64_t, int, int,
-                             void *, uint64_t, unsigned long long *, const ShiftMul, uint64_t, int, uint32_t *);
+                             void *, uint64_t, unsigned long long *, const ShiftMul, uint64_t, int, uint32_t *, const BucketHist);
 
 // One translation unit per (K, EMIT) instantiates the three run lengths and exports a getter, so
 // the twelve kernels compile in parallel.

@@ -105,6 +105,21 @@ def test_reads_device_resident_and_empty(ctx):
     assert len(e) == 0
 
 
+def test_reads_homopolymers_overflow_the_event_estimate(ctx):
+    """mm_hash64(AAA..A) = 0.468 * 2^64 < 2^64 / 2: with c = 2 every window of a poly-A / poly-T read
+    survives, so the batch emits far more events than the n_bases / c sizing assumes.  Exercises the
+    capacity retry of the event buffer (and the recount of the bucket histogram after it), one k-mer
+    with ~10^6 events (generic path for its group) and reads whose pair keys are all identical."""
+    from tests.util import flatten
+    rng = np.random.default_rng(99)
+    seqs = [b"A" * 150] * 5000 + [b"T" * 150] * 4000 + rand_seqs(rng, [150] * 3000) + [b"A" * 60, b"T" * 401, b"C" * 150]
+    order = rng.permutation(len(seqs))
+    buf, off = flatten([seqs[i] for i in order])
+    n, nd = check_reads(ctx, buf, off, k=31, c=2)
+    assert n > 1000 and nd > 500000
+    check_reads(ctx, buf, off, k=31, c=2, no_dedup=True)
+
+
 def test_sample_download_into_pinned_buffers(ctx):
     import torch
     from sylph_b200 import synth
