@@ -203,6 +203,66 @@ __device__ __forceinline__ bool ani_from_lambda_dev(double lambda, double k, uin
     return true;
 }
 
+// Everything get_stats derives from (n hits, median, sum and count of the kept coverages, histogram of
+// the kept values 1..16) for one (sample, genome) pair; one lane.  src/contain.rs:690-814.
+__device__ __forceinline__ void stats_emit(uint32_t sample_idx, uint64_t g, uint32_t n, uint32_t gl, uint32_t median, uint32_t sum,
+                                           uint32_t nz, const uint32_t *hist, const uint32_t *lost, uint32_t genome_base,
+                                           const StatParams &P, int pass2, syl_ani_row *__restrict__ rows, uint64_t rows_cap,
+                                           uint32_t *__restrict__ boot_rows, uint32_t *__restrict__ hist_out, uint64_t boot_cap,
+                                           unsigned long long *__restrict__ n_rows, unsigned long long *__restrict__ n_boot) {
+    const double k = (double)P.k;
+    const uint64_t nfull = (uint64_t)(gl - n) + nz;
+    const double naive_ani = pow((double)n / (double)gl, 1. / k);
+    const double geq1_mean = (double)sum / (double)n;  // :690 divides by covs.len()
+    uint32_t status;
+    double lam = 0.;
+    if ((double)median > 2.) {
+        status = SYL_LAMBDA_HIGH;
+    } else {
+        RatioOut r = ratio_lambda_hist(hist, nz, P.min_count_correct);
+        status = r.ok ? SYL_LAMBDA_VALUE : SYL_LAMBDA_LOW;
+        lam = r.lambda;
+    }
+    double final_cov;
+    if (status == SYL_LAMBDA_VALUE) final_cov = lam;
+    else if ((double)median < 15.) final_cov = geq1_mean;
+    else final_cov = P.mean_coverage ? geq1_mean : (double)median;
+    double est = 0.;
+    const bool has_lambda = status == SYL_LAMBDA_VALUE;
+    const bool has_est = has_lambda && ani_from_lambda_dev(final_cov, k, nz, nfull, &est);
+    const double final_ani = (!has_lambda || !has_est || P.no_adj) ? naive_ani : est;
+    if (final_ani < P.min_ani) return;  // :746-764
+
+    syl_ani_row r;
+    r.sample = sample_idx;
+    r.genome = genome_base + (uint32_t)g;
+    r.lambda_status = status;
+    r.ci_valid = 0;
+    r.contain = n;
+    r.glen = gl;
+    r.kmers_lost = pass2 ? (int64_t)lost[g] : -1;
+    r.naive_ani = naive_ani;
+    r.final_est_ani = final_ani;
+    r.final_est_cov = final_cov;
+    r.mean_cov = geq1_mean;
+    r.median_cov = (double)median;
+    r.lambda = has_lambda ? lam : 0.;
+    r.ci[0] = r.ci[1] = r.ci[2] = r.ci[3] = 0.;
+    r.rel_abund = 0.;
+    r.seq_abund = 0.;
+    r.reserved = 0.;
+    const unsigned long long ri = atomicAdd(n_rows, 1ull);  // compact output; the host orders rows
+    if (ri >= rows_cap) return;
+    rows[ri] = r;
+    if (!P.no_ci && has_lambda) {
+        const unsigned long long bi = atomicAdd(n_boot, 1ull);
+        if (bi < boot_cap) {
+            boot_rows[bi] = (uint32_t)ri;
+            for (int v = 0; v < 17; v++) hist_out[bi * 17 + v] = v == 0 ? (uint32_t)(gl - n) : hist[v];
+        }
+    }
+}
+
 constexpr int STAT_WARPS = 4;
 
 __global__ void __launch_bounds__(STAT_WARPS * 32)
@@ -289,57 +349,134 @@ k_stats(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, cons
     __syncwarp();
     if (lane != 0) return;
 
-    const double k = (double)P.k;
-    const uint64_t nfull = (uint64_t)(gl - n) + nz;
-    const double naive_ani = pow((double)n / (double)gl, 1. / k);
-    const double geq1_mean = (double)sum / (double)n;  // :690 divides by covs.len()
-    uint32_t status;
-    double lam = 0.;
-    if ((double)median > 2.) {
-        status = SYL_LAMBDA_HIGH;
-    } else {
-        RatioOut r = ratio_lambda_hist(hist, nz, P.min_count_correct);
-        status = r.ok ? SYL_LAMBDA_VALUE : SYL_LAMBDA_LOW;
-        lam = r.lambda;
-    }
-    double final_cov;
-    if (status == SYL_LAMBDA_VALUE) final_cov = lam;
-    else if ((double)median < 15.) final_cov = geq1_mean;
-    else final_cov = P.mean_coverage ? geq1_mean : (double)median;
-    double est = 0.;
-    const bool has_lambda = status == SYL_LAMBDA_VALUE;
-    const bool has_est = has_lambda && ani_from_lambda_dev(final_cov, k, nz, nfull, &est);
-    const double final_ani = (!has_lambda || !has_est || P.no_adj) ? naive_ani : est;
-    if (final_ani < P.min_ani) return;  // :746-764
+    stats_emit(sample_idx, g, n, gl, median, sum, nz, hist, lost, genome_base, P, pass2, rows, rows_cap, boot_rows, hist_out,
+               boot_cap, n_rows, n_boot);
+}
 
-    syl_ani_row r;
-    r.sample = sample_idx;
-    r.genome = genome_base + (uint32_t)g;
-    r.lambda_status = status;
-    r.ci_valid = 0;
-    r.contain = n;
-    r.glen = gl;
-    r.kmers_lost = pass2 ? (int64_t)lost[g] : -1;
-    r.naive_ani = naive_ani;
-    r.final_est_ani = final_ani;
-    r.final_est_cov = final_cov;
-    r.mean_cov = geq1_mean;
-    r.median_cov = (double)median;
-    r.lambda = has_lambda ? lam : 0.;
-    r.ci[0] = r.ci[1] = r.ci[2] = r.ci[3] = 0.;
-    r.rel_abund = 0.;
-    r.seq_abund = 0.;
-    r.reserved = 0.;
-    const unsigned long long ri = atomicAdd(n_rows, 1ull);  // compact output; the host orders rows
-    if (ri >= rows_cap) return;
-    rows[ri] = r;
-    if (!P.no_ci && has_lambda) {
-        const unsigned long long bi = atomicAdd(n_boot, 1ull);
-        if (bi < boot_cap) {
-            boot_rows[bi] = (uint32_t)ri;
-            for (int v = 0; v < 17; v++) hist_out[bi * 17 + v] = v == 0 ? (uint32_t)(gl - n) : hist[v];
+
+// ---- histogram formulation of one get_stats pass ------------------------------------------------
+// get_stats only needs, per (sample, genome), the multiset of the hit k-mers' sample counts: its
+// median, the sum / number of the values below the Poisson cut-off and how many are 1, 2, .., 16.
+// All of that follows from a histogram of the values, which the join can accumulate directly:
+// ONE probe pass per get_stats pass (the CSR formulation probes twice: count, then fill) and a
+// k_stats that reads 1 KB per pair instead of selecting a median from a value list.  Values
+// >= COV_BINS (a genome covered 256x or deeper) are only counted in `ovf`; if there are any, the
+// caller falls back to the CSR formulation for this pass.
+constexpr uint32_t COV_BINS = 256;
+
+template <bool PASS2>
+__global__ void k_join_hist(const SampleView *__restrict__ views, uint64_t G,
+                            const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gid,
+                            const uint32_t *__restrict__ bstart, uint64_t M, uint64_t NB, uint64_t maxkey,
+                            const uint8_t *__restrict__ survivor, const double *__restrict__ ani1,
+                            uint32_t *__restrict__ cnt, uint32_t *__restrict__ lost, uint32_t *__restrict__ chist,
+                            unsigned long long *__restrict__ ovf) {
+    const SampleView sv = views[blockIdx.y];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n) return;
+    const uint64_t row = (uint64_t)blockIdx.y * G;
+    if (PASS2) { survivor += row; ani1 += row; lost += row; }
+    cnt += row;
+    chist += row * COV_BINS;
+    const uint64_t key = sv.hash[i];
+    const uint32_t c = sv.count[i];
+    if (key > maxkey || c == 0) return;  // count 0: src/contain.rs:634-636
+    const uint64_t b = bucket_of(key, M, NB);
+    uint32_t lo = bstart[b];
+    const uint32_t hi = bstart[b + 1];
+    while (lo < hi && keys[lo] < key) lo++;
+    if (lo >= hi || keys[lo] != key) return;
+    uint32_t winner = 0xFFFFFFFFu;
+    if (PASS2) {
+        double best = -1.0;
+        for (uint32_t j = lo; j < hi && keys[j] == key; j++) {
+            const uint32_t g = gid[j] >> 1;
+            if (!survivor[g]) continue;
+            const double a = ani1[g];
+            if (a > best || (a == best && g < winner)) { best = a; winner = g; }
         }
     }
+    for (uint32_t e = lo; e < hi && keys[e] == key; e++) {
+        const uint32_t gv = gid[e];
+        if (gv & 1u) continue;  // tracked k-mers only take part in the winner decision
+        const uint32_t g = gv >> 1;
+        if (PASS2) {
+            if (!survivor[g]) continue;
+            if (g != winner) { atomicAdd(&lost[g], 1u); continue; }
+        }
+        atomicAdd(&cnt[g], 1u);
+        if (c < COV_BINS) atomicAdd(&chist[(uint64_t)g * COV_BINS + c], 1u);
+        else atomicAdd(ovf, 1ull);
+    }
+}
+
+// one warp per (sample, genome); lane l owns the bins [8l, 8l+8)
+__global__ void __launch_bounds__(STAT_WARPS * 32)
+k_stats_hist(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ chist,
+             const uint32_t *__restrict__ glen, const uint32_t *__restrict__ lost, uint64_t n_genomes, uint64_t n_pairs,
+             uint32_t genome_base, StatParams P, int pass2, syl_ani_row *__restrict__ rows, uint64_t rows_cap,
+             uint32_t *__restrict__ boot_rows, uint32_t *__restrict__ hist_out, uint64_t boot_cap,
+             unsigned long long *__restrict__ n_rows, unsigned long long *__restrict__ n_boot) {
+    __shared__ uint32_t s_hist[STAT_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t pair = (uint64_t)blockIdx.x * STAT_WARPS + w;
+    if (pair >= n_pairs) return;
+    const uint32_t sample_idx = (uint32_t)(pair / n_genomes);
+    const uint64_t g = pair - (uint64_t)sample_idx * n_genomes;
+    const uint32_t n = cnt[pair];
+    const uint32_t gl = glen[g];
+    if (n == 0) return;                                   // covs.is_empty() :654
+    if ((double)gl < P.min_number_kmers) return;          // :627
+    if (lost) lost += (uint64_t)sample_idx * n_genomes;
+    const uint4 *hp = reinterpret_cast<const uint4 *>(chist + pair * COV_BINS + 8 * lane);
+    const uint4 h0 = hp[0], h1 = hp[1];
+    const uint32_t h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    uint32_t tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) tot += h[q];
+    uint32_t incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    // median = value of rank n/2 (0-based) in ascending order (:659-660)
+    const uint32_t kth = n / 2, excl = incl - tot;
+    uint32_t med = 0;
+    if (kth >= excl && kth < incl) {
+        uint32_t acc = excl;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (kth >= acc && kth < acc + h[q]) med = 8 * lane + q;
+            acc += h[q];
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) med |= __shfl_xor_sync(0xffffffffu, med, d);  // exactly one lane holds it
+    const uint32_t median = med;
+    const uint32_t max_cov = median < 30u ? c_pois_cut[median] : 0xFFFFFFFFu;  // f64::MAX
+    uint32_t sum = 0, nz = 0;  // u32 sum wraps like iter().sum::<u32>() in a release build
+    uint32_t *hist = s_hist[w];
+    hist[lane] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t v = 8 * lane + q;
+        if (v <= max_cov) {
+            sum += v * h[q];
+            nz += h[q];
+            if (v >= 1 && v <= 16u) hist[v] = h[q];
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        nz += __shfl_xor_sync(0xffffffffu, nz, d);
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    stats_emit(sample_idx, g, n, gl, median, sum, nz, hist, lost, genome_base, P, pass2, rows, rows_cap, boot_rows, hist_out,
+               boot_cap, n_rows, n_boot);
 }
 
 // ---- bootstrap (src/contain.rs:849-898) -------------------------------------------------------
@@ -526,7 +663,8 @@ __global__ void k_mark_survivors(const syl_ani_row *__restrict__ rows, uint64_t 
 // Scratch for one syl_query / syl_profile call: dense per-(sample, genome) tables + compact outputs
 struct ContainScratch {
     DevBuf<SampleView> views;
-    DevBuf<uint32_t> cnt, cursor, lost, boot_rows, hist, covs, reject;
+    DevBuf<uint32_t> cnt, cursor, lost, boot_rows, hist, covs, reject, chist;
+    bool use_hist = false;  // per-pair coverage histograms fit (COV_BINS x 4 B per pair)
     DevBuf<uint64_t> off;
     DevBuf<uint8_t> survivor, tmp, res_ok;
     DevBuf<double> ani1, res_ani, res_lambda;
@@ -573,6 +711,9 @@ static int scratch_init(syl_ctx *ctx, const syl_db *db, const syl_sample *const 
     SYL_TRY(S.boot_rows.alloc(S.boot_cap, st));
     SYL_TRY(S.hist.alloc(S.boot_cap * 17, st));
     SYL_TRY(S.covs.alloc(1 << 16, st));
+    static const bool force_csr = getenv("SYL_CONTAIN_CSR") != nullptr;  // testing: always take the CSR formulation
+    S.use_hist = !force_csr && S.P * COV_BINS * 4 <= (8ull << 30);
+    if (S.use_hist) SYL_TRY(S.chist.alloc(S.P * COV_BINS, st));
     cub::DeviceScan::ExclusiveSum(nullptr, S.tmp_bytes, S.cnt.p, S.off.p, (int)S.P, st);
     SYL_TRY(S.tmp.alloc(S.tmp_bytes, st));
     return SYL_OK;
@@ -585,55 +726,95 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
     cudaStream_t st = ctx->stream;
     const uint64_t G = S.G, NP = S.P;
     rows_out.clear();
-    SYL_CUDA(cudaMemsetAsync(S.cnt.p, 0, NP * 4, st));
-    SYL_CUDA(cudaMemsetAsync(S.cursor.p, 0, NP * 4, st));
-    if (pass2) SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, NP * 4, st));
     const dim3 jgrid(nblk(std::max<uint64_t>(S.max_n, 1), 128), (unsigned)S.S);
     const bool have = S.max_n && db->N;
-    if (have) {
-        if (!pass2)
-            k_join<false, false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
-                                                        nullptr, nullptr, S.cnt.p, nullptr, nullptr, nullptr, nullptr);
-        else
-            k_join<true, false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
-                                                       S.survivor.p, S.ani1.p, S.cnt.p, nullptr, nullptr, nullptr, S.lost.p);
-        ctx->launches++;
-    }
-    size_t tb = S.tmp_bytes;
-    SYL_CUDA(cub::DeviceScan::ExclusiveSum(S.tmp.p, tb, S.cnt.p, S.off.p, (int)NP, st));
-    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 10, S.off.p + (NP - 1), 8, cudaMemcpyDeviceToHost, st));
-    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 11, S.cnt.p + (NP - 1), 4, cudaMemcpyDeviceToHost, st));
-    SYL_CUDA(cudaStreamSynchronize(st));
-    const uint64_t H = ctx->h_counters[10] + (uint32_t)ctx->h_counters[11];
-    if (H > S.covs.n) SYL_TRY(S.covs.alloc(H + H / 2 + 1024, st));
-    if (H) {
-        if (!pass2)
-            k_join<false, true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
-                                                       nullptr, nullptr, nullptr, S.off.p, S.cursor.p, S.covs.p, nullptr);
-        else
-            k_join<true, true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
-                                                      S.survivor.p, S.ani1.p, nullptr, S.off.p, S.cursor.p, S.covs.p, nullptr);
-        ctx->launches++;
-    }
-    unsigned long long *d_n = reinterpret_cast<unsigned long long *>(ctx->d_counters + 12);  // [12] rows, [13] boot rows
+    unsigned long long *d_n = reinterpret_cast<unsigned long long *>(ctx->d_counters + 12);  // [12] rows, [13] boot rows, [15] overflow
+    unsigned long long *d_ovf = reinterpret_cast<unsigned long long *>(ctx->d_counters + 15);
     uint64_t n_rows = 0, n_boot = 0;
-    for (;;) {
-        SYL_CUDA(cudaMemsetAsync(d_n, 0, 16, st));
-        k_stats<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.cnt.p, S.off.p, S.covs.p, db->glen, pass2 ? S.lost.p : nullptr,
-                                                                  G, NP, db->genome_base, P, pass2 ? 1 : 0, S.rows.p, S.rows_cap,
-                                                                  S.boot_rows.p, S.hist.p, S.boot_cap, d_n, d_n + 1);
-        ctx->launches++;
-        SYL_CUDA(cudaGetLastError());
-        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 12, d_n, 16, cudaMemcpyDeviceToHost, st));
-        SYL_CUDA(cudaStreamSynchronize(st));
-        n_rows = ctx->h_counters[12];
-        n_boot = ctx->h_counters[13];
-        if (n_rows <= S.rows_cap && n_boot <= S.boot_cap) break;
-        S.rows_cap = std::max(S.rows_cap, n_rows);  // rare: more rows than the first guess, redo with room
+    bool done = false;
+    auto grow_rows = [&]() -> int {  // rare: more rows than the first guess, redo the statistics with room
+        S.rows_cap = std::max(S.rows_cap, n_rows);
         S.boot_cap = std::max(S.boot_cap, n_boot);
         SYL_TRY(S.rows.alloc(S.rows_cap, st));
         SYL_TRY(S.boot_rows.alloc(S.boot_cap, st));
         SYL_TRY(S.hist.alloc(S.boot_cap * 17, st));
+        return SYL_OK;
+    };
+    if (S.use_hist) {
+        // histogram formulation: one probe pass, statistics from the per-pair count histograms
+        SYL_CUDA(cudaMemsetAsync(S.cnt.p, 0, NP * 4, st));
+        if (pass2) SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, NP * 4, st));
+        SYL_CUDA(cudaMemsetAsync(S.chist.p, 0, NP * COV_BINS * 4, st));
+        SYL_CUDA(cudaMemsetAsync(d_ovf, 0, 8, st));
+        if (have) {
+            if (!pass2)
+                k_join_hist<false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                          nullptr, nullptr, S.cnt.p, nullptr, S.chist.p, d_ovf);
+            else
+                k_join_hist<true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                         S.survivor.p, S.ani1.p, S.cnt.p, S.lost.p, S.chist.p, d_ovf);
+            ctx->launches++;
+        }
+        for (;;) {
+            SYL_CUDA(cudaMemsetAsync(d_n, 0, 16, st));
+            k_stats_hist<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.cnt.p, S.chist.p, db->glen, pass2 ? S.lost.p : nullptr,
+                                                                           G, NP, db->genome_base, P, pass2 ? 1 : 0, S.rows.p, S.rows_cap,
+                                                                           S.boot_rows.p, S.hist.p, S.boot_cap, d_n, d_n + 1);
+            ctx->launches++;
+            SYL_CUDA(cudaGetLastError());
+            SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 12, d_n, 32, cudaMemcpyDeviceToHost, st));
+            SYL_CUDA(cudaStreamSynchronize(st));
+            if (ctx->h_counters[15]) break;  // coverage >= COV_BINS somewhere: CSR formulation below
+            n_rows = ctx->h_counters[12];
+            n_boot = ctx->h_counters[13];
+            if (n_rows <= S.rows_cap && n_boot <= S.boot_cap) { done = true; break; }
+            SYL_TRY(grow_rows());
+        }
+    }
+    if (!done) {
+        // CSR formulation: count the hits per pair, scan, scatter the counts, select the median
+        SYL_CUDA(cudaMemsetAsync(S.cnt.p, 0, NP * 4, st));
+        SYL_CUDA(cudaMemsetAsync(S.cursor.p, 0, NP * 4, st));
+        if (pass2) SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, NP * 4, st));
+        if (have) {
+            if (!pass2)
+                k_join<false, false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                            nullptr, nullptr, S.cnt.p, nullptr, nullptr, nullptr, nullptr);
+            else
+                k_join<true, false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                           S.survivor.p, S.ani1.p, S.cnt.p, nullptr, nullptr, nullptr, S.lost.p);
+            ctx->launches++;
+        }
+        size_t tb = S.tmp_bytes;
+        SYL_CUDA(cub::DeviceScan::ExclusiveSum(S.tmp.p, tb, S.cnt.p, S.off.p, (int)NP, st));
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 10, S.off.p + (NP - 1), 8, cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 11, S.cnt.p + (NP - 1), 4, cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaStreamSynchronize(st));
+        const uint64_t H = ctx->h_counters[10] + (uint32_t)ctx->h_counters[11];
+        if (H > S.covs.n) SYL_TRY(S.covs.alloc(H + H / 2 + 1024, st));
+        if (H) {
+            if (!pass2)
+                k_join<false, true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                           nullptr, nullptr, nullptr, S.off.p, S.cursor.p, S.covs.p, nullptr);
+            else
+                k_join<true, true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
+                                                          S.survivor.p, S.ani1.p, nullptr, S.off.p, S.cursor.p, S.covs.p, nullptr);
+            ctx->launches++;
+        }
+        for (;;) {
+            SYL_CUDA(cudaMemsetAsync(d_n, 0, 16, st));
+            k_stats<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.cnt.p, S.off.p, S.covs.p, db->glen, pass2 ? S.lost.p : nullptr,
+                                                                      G, NP, db->genome_base, P, pass2 ? 1 : 0, S.rows.p, S.rows_cap,
+                                                                      S.boot_rows.p, S.hist.p, S.boot_cap, d_n, d_n + 1);
+            ctx->launches++;
+            SYL_CUDA(cudaGetLastError());
+            SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 12, d_n, 16, cudaMemcpyDeviceToHost, st));
+            SYL_CUDA(cudaStreamSynchronize(st));
+            n_rows = ctx->h_counters[12];
+            n_boot = ctx->h_counters[13];
+            if (n_rows <= S.rows_cap && n_boot <= S.boot_cap) break;
+            SYL_TRY(grow_rows());
+        }
     }
     if (n_boot) {
         const uint64_t nb = n_boot * BOOT_ITERS;

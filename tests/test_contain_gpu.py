@@ -156,6 +156,32 @@ def test_uploaded_sketches_and_zero_counts(ctx):
     compare(ctx.profile(db, [smp]), oracle_rows(d, (sh, sc), True), True)
 
 
+@pytest.mark.parametrize("depth", [40, 250, 255, 256, 700])
+def test_deep_coverage_uploaded_sample(ctx, depth):
+    """Coverage around the 256-bin limit of the per-pair count histograms: up to 255 the histogram
+    formulation of get_stats answers, from 256 on the call falls back to the CSR formulation
+    (contain.cu COV_BINS); medians >= 30 take the no-cutoff branch (src/contain.rs:664)."""
+    rng = np.random.default_rng(1000 + depth)
+    kmers = np.unique(rng.integers(1, 2**57, size=9000, dtype=np.uint64))[:8000]
+    koff = np.array([0, 3000, 5500, 8000], dtype=np.uint64)
+    tracked = np.zeros(0, np.uint64)
+    toff = np.zeros(4, np.uint64)
+    gs = np.array([600000, 500000, 500000], dtype=np.uint64)
+    g = ctx.upload_genomes(kmers, koff, tracked, toff, gs)
+    # genome 0 deep, genome 1 shallow (lambda / bootstrap branch), genome 2 absent
+    sh = np.concatenate([kmers[:2900], kmers[3000:4200]])
+    sc = np.concatenate([rng.poisson(depth, size=2900), rng.poisson(0.7, size=1200)]).astype(np.uint32)
+    if depth >= 250:
+        sc[:5] = [255, 256, 257, 100000, 255]
+    smp = ctx.upload_sample(sh, sc)
+    db = ctx.build_db(g)
+    d = dict(kmers=kmers, kmer_off=koff, tracked=tracked, tracked_off=toff, gn_size=gs)
+    exp = oracle_rows(d, (sh, sc), False)
+    assert len(exp) >= 1 and exp[0].median_cov >= 30
+    compare(sort_query_rows(ctx.query(db, [smp])), exp, False)
+    compare(ctx.profile(db, [smp]), oracle_rows(d, (sh, sc), True), True)
+
+
 def test_k21_scalar_semantics_end_to_end(ctx):
     """k = 21 with the scalar window set (what sylph computes on non-x86): sketches, query and profile."""
     from oracle import oracle as O
