@@ -364,19 +364,68 @@ k_stats(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, cons
 // caller falls back to the CSR formulation for this pass.
 constexpr uint32_t COV_BINS = 256;
 
+// The genome ids of one k-mer's equal range [lo, e) -> hit counters / count histograms of one sample.
+// PASS2: the k-mer belongs to the pass-1 survivor with the best pass-1 ANI (lowest genome on ties,
+// tracked k-mers take part in the decision); other survivors lose it (src/contain.rs:410-430, :641-646).
+template <bool PASS2>
+__device__ __forceinline__ void join_range(const uint32_t *__restrict__ gid, uint32_t lo, uint32_t e, uint32_t c,
+                                           const uint8_t *__restrict__ survivor, const double *__restrict__ ani1,
+                                           uint8_t *__restrict__ touched, uint32_t *__restrict__ lost,
+                                           uint32_t *__restrict__ chist, unsigned long long *__restrict__ ovf) {
+    uint32_t winner = 0xFFFFFFFFu;
+    if (PASS2) {
+        double best = -1.0;
+        for (uint32_t j = lo; j < e; j += 4) {
+            uint32_t gq[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) gq[q] = j + q < e ? gid[j + q] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (j + q >= e) continue;
+                const uint32_t g = gq[q] >> 1;
+                if (!survivor[g]) continue;
+                const double a = ani1[g];
+                if (a > best || (a == best && g < winner)) { best = a; winner = g; }
+            }
+        }
+    }
+    for (uint32_t j = lo; j < e; j += 4) {
+        uint32_t gq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) gq[q] = j + q < e ? gid[j + q] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j + q >= e) continue;
+            const uint32_t gv = gq[q];
+            if (gv & 1u) continue;  // tracked k-mers only take part in the winner decision
+            const uint32_t g = gv >> 1;
+            if (PASS2) {
+                if (!survivor[g]) continue;
+                if (g != winner) { atomicAdd(&lost[g], 1u); continue; }
+            }
+            // no per-genome hit counter: the sample's k-mers concentrate on the few genomes that are
+            // present, and a million atomics on a handful of adjacent counters serialise in one L2
+            // slice (measured: 2/3 of this kernel's time).  The hit count is the histogram's total.
+            if (!touched[g]) touched[g] = 1;
+            if (c < COV_BINS) atomicAdd(&chist[(uint64_t)g * COV_BINS + c], 1u);
+            else atomicAdd(ovf, 1ull);
+        }
+    }
+}
+
 template <bool PASS2>
 __global__ void k_join_hist(const SampleView *__restrict__ views, uint64_t G,
-                            const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gid,
+                            const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gid, uint64_t N,
                             const uint32_t *__restrict__ bstart, uint64_t M, uint64_t NB, uint64_t maxkey,
                             const uint8_t *__restrict__ survivor, const double *__restrict__ ani1,
-                            uint32_t *__restrict__ cnt, uint32_t *__restrict__ lost, uint32_t *__restrict__ chist,
-                            unsigned long long *__restrict__ ovf) {
+                            uint8_t *__restrict__ touched, uint32_t *__restrict__ lost, uint32_t *__restrict__ chist,
+                            unsigned long long *__restrict__ ovf, uint2 *__restrict__ hits, uint64_t hits_stride) {
     const SampleView sv = views[blockIdx.y];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sv.n) return;
     const uint64_t row = (uint64_t)blockIdx.y * G;
     if (PASS2) { survivor += row; ani1 += row; lost += row; }
-    cnt += row;
+    touched += row;
     chist += row * COV_BINS;
     const uint64_t key = sv.hash[i];
     const uint32_t c = sv.count[i];
@@ -384,35 +433,57 @@ __global__ void k_join_hist(const SampleView *__restrict__ views, uint64_t G,
     const uint64_t b = bucket_of(key, M, NB);
     uint32_t lo = bstart[b];
     const uint32_t hi = bstart[b + 1];
-    while (lo < hi && keys[lo] < key) lo++;
+    // A k-mer shared by many genomes has a long equal range, and a thread walking it one dependent
+    // load at a time holds its whole warp for range x DRAM latency.  Keys and genome ids are
+    // therefore fetched four at a time (independent loads; reads past the bucket stay inside the
+    // arrays, which hold N entries).
+    const uint32_t n4 = (uint32_t)N;
+    for (;;) {  // first position with keys[lo] >= key
+        if (lo >= hi) return;  // (hits is zero-filled by the caller)
+        uint64_t kq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) kq[q] = lo + q < n4 ? keys[lo + q] : 0xFFFFFFFFFFFFFFFFull;
+        int adv = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) adv += (lo + q < hi && kq[q] < key) ? 1 : 0;  // keys ascend: a prefix
+        lo += adv;
+        if (adv < 4) break;
+    }
     if (lo >= hi || keys[lo] != key) return;
-    uint32_t winner = 0xFFFFFFFFu;
-    if (PASS2) {
-        double best = -1.0;
-        for (uint32_t j = lo; j < hi && keys[j] == key; j++) {
-            const uint32_t g = gid[j] >> 1;
-            if (!survivor[g]) continue;
-            const double a = ani1[g];
-            if (a > best || (a == best && g < winner)) { best = a; winner = g; }
-        }
+    uint32_t e = lo;  // end of the equal range
+    for (;;) {
+        uint64_t kq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) kq[q] = e + q < n4 ? keys[e + q] : 0xFFFFFFFFFFFFFFFFull;
+        int adv = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) adv += (e + q < hi && kq[q] == key) ? 1 : 0;
+        e += adv;
+        if (adv < 4) break;
     }
-    for (uint32_t e = lo; e < hi && keys[e] == key; e++) {
-        const uint32_t gv = gid[e];
-        if (gv & 1u) continue;  // tracked k-mers only take part in the winner decision
-        const uint32_t g = gv >> 1;
-        if (PASS2) {
-            if (!survivor[g]) continue;
-            if (g != winner) { atomicAdd(&lost[g], 1u); continue; }
-        }
-        atomicAdd(&cnt[g], 1u);
-        if (c < COV_BINS) atomicAdd(&chist[(uint64_t)g * COV_BINS + c], 1u);
-        else atomicAdd(ovf, 1ull);
-    }
+    if (hits) hits[(uint64_t)blockIdx.y * hits_stride + i] = make_uint2(lo, e - lo);  // equal range in the db, for pass 2
+    join_range<PASS2>(gid, lo, e, c, survivor, ani1, touched, lost, chist, ovf);
+}
+
+// Pass 2 over the equal ranges recorded by pass 1: no directory / key look-ups, only the genome ids.
+__global__ void k_join2_hits(const SampleView *__restrict__ views, uint64_t G, const uint32_t *__restrict__ gid,
+                             const uint2 *__restrict__ hits, uint64_t hits_stride,
+                             const uint8_t *__restrict__ survivor, const double *__restrict__ ani1,
+                             uint8_t *__restrict__ touched, uint32_t *__restrict__ lost, uint32_t *__restrict__ chist,
+                             unsigned long long *__restrict__ ovf) {
+    const SampleView sv = views[blockIdx.y];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n) return;
+    const uint2 h = hits[(uint64_t)blockIdx.y * hits_stride + i];
+    if (h.y == 0) return;
+    const uint64_t row = (uint64_t)blockIdx.y * G;
+    join_range<true>(gid, h.x, h.x + h.y, sv.count[i], survivor + row, ani1 + row, touched + row, lost + row,
+                     chist + row * COV_BINS, ovf);
 }
 
 // one warp per (sample, genome); lane l owns the bins [8l, 8l+8)
 __global__ void __launch_bounds__(STAT_WARPS * 32)
-k_stats_hist(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ chist,
+k_stats_hist(const uint8_t *__restrict__ touched, const uint32_t *__restrict__ chist,
              const uint32_t *__restrict__ glen, const uint32_t *__restrict__ lost, uint64_t n_genomes, uint64_t n_pairs,
              uint32_t genome_base, StatParams P, int pass2, syl_ani_row *__restrict__ rows, uint64_t rows_cap,
              uint32_t *__restrict__ boot_rows, uint32_t *__restrict__ hist_out, uint64_t boot_cap,
@@ -423,9 +494,8 @@ k_stats_hist(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ chis
     if (pair >= n_pairs) return;
     const uint32_t sample_idx = (uint32_t)(pair / n_genomes);
     const uint64_t g = pair - (uint64_t)sample_idx * n_genomes;
-    const uint32_t n = cnt[pair];
+    if (!touched[pair]) return;                           // covs.is_empty() :654
     const uint32_t gl = glen[g];
-    if (n == 0) return;                                   // covs.is_empty() :654
     if ((double)gl < P.min_number_kmers) return;          // :627
     if (lost) lost += (uint64_t)sample_idx * n_genomes;
     const uint4 *hp = reinterpret_cast<const uint4 *>(chist + pair * COV_BINS + 8 * lane);
@@ -440,6 +510,7 @@ k_stats_hist(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ chis
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
+    const uint32_t n = __shfl_sync(0xffffffffu, incl, 31);  // number of hit k-mers
     // median = value of rank n/2 (0-based) in ascending order (:659-660)
     const uint32_t kth = n / 2, excl = incl - tot;
     uint32_t med = 0;
@@ -665,8 +736,10 @@ struct ContainScratch {
     DevBuf<SampleView> views;
     DevBuf<uint32_t> cnt, cursor, lost, boot_rows, hist, covs, reject, chist;
     bool use_hist = false;  // per-pair coverage histograms fit (COV_BINS x 4 B per pair)
+    DevBuf<uint2> hits;     // [sample][max_n] equal range of every sample key in the db (recorded by pass 1 for pass 2)
+    bool hits_valid = false;
     DevBuf<uint64_t> off;
-    DevBuf<uint8_t> survivor, tmp, res_ok;
+    DevBuf<uint8_t> survivor, tmp, res_ok, touched;
     DevBuf<double> ani1, res_ani, res_lambda;
     DevBuf<syl_ani_row> rows;
     size_t tmp_bytes = 0;
@@ -713,7 +786,8 @@ static int scratch_init(syl_ctx *ctx, const syl_db *db, const syl_sample *const 
     SYL_TRY(S.covs.alloc(1 << 16, st));
     static const bool force_csr = getenv("SYL_CONTAIN_CSR") != nullptr;  // testing: always take the CSR formulation
     S.use_hist = !force_csr && S.P * COV_BINS * 4 <= (8ull << 30);
-    if (S.use_hist) SYL_TRY(S.chist.alloc(S.P * COV_BINS, st));
+    if (S.use_hist) { SYL_TRY(S.chist.alloc(S.P * COV_BINS, st)); SYL_TRY(S.touched.alloc(S.P, st)); }
+    if (S.use_hist && need_pass2 && S.max_n) SYL_TRY(S.hits.alloc(S.S * S.max_n, st));
     cub::DeviceScan::ExclusiveSum(nullptr, S.tmp_bytes, S.cnt.p, S.off.p, (int)S.P, st);
     SYL_TRY(S.tmp.alloc(S.tmp_bytes, st));
     return SYL_OK;
@@ -742,22 +816,27 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
     };
     if (S.use_hist) {
         // histogram formulation: one probe pass, statistics from the per-pair count histograms
-        SYL_CUDA(cudaMemsetAsync(S.cnt.p, 0, NP * 4, st));
+        SYL_CUDA(cudaMemsetAsync(S.touched.p, 0, NP, st));
         if (pass2) SYL_CUDA(cudaMemsetAsync(S.lost.p, 0, NP * 4, st));
         SYL_CUDA(cudaMemsetAsync(S.chist.p, 0, NP * COV_BINS * 4, st));
         SYL_CUDA(cudaMemsetAsync(d_ovf, 0, 8, st));
         if (have) {
+            if (!pass2 && S.hits.p) SYL_CUDA(cudaMemsetAsync(S.hits.p, 0, S.S * S.max_n * sizeof(uint2), st));
             if (!pass2)
-                k_join_hist<false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
-                                                          nullptr, nullptr, S.cnt.p, nullptr, S.chist.p, d_ovf);
+                k_join_hist<false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->N, db->bstart, db->M, db->NB, db->maxkey,
+                                                          nullptr, nullptr, S.touched.p, nullptr, S.chist.p, d_ovf, S.hits.p, S.max_n);
+            else if (S.hits_valid)
+                k_join2_hits<<<jgrid, 128, 0, st>>>(S.views.p, G, db->gid, S.hits.p, S.max_n, S.survivor.p, S.ani1.p, S.touched.p,
+                                                    S.lost.p, S.chist.p, d_ovf);
             else
-                k_join_hist<true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->bstart, db->M, db->NB, db->maxkey,
-                                                         S.survivor.p, S.ani1.p, S.cnt.p, S.lost.p, S.chist.p, d_ovf);
+                k_join_hist<true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->N, db->bstart, db->M, db->NB, db->maxkey,
+                                                         S.survivor.p, S.ani1.p, S.touched.p, S.lost.p, S.chist.p, d_ovf, nullptr, 0);
+            if (!pass2) S.hits_valid = S.hits.p != nullptr;
             ctx->launches++;
         }
         for (;;) {
             SYL_CUDA(cudaMemsetAsync(d_n, 0, 16, st));
-            k_stats_hist<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.cnt.p, S.chist.p, db->glen, pass2 ? S.lost.p : nullptr,
+            k_stats_hist<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.touched.p, S.chist.p, db->glen, pass2 ? S.lost.p : nullptr,
                                                                            G, NP, db->genome_base, P, pass2 ? 1 : 0, S.rows.p, S.rows_cap,
                                                                            S.boot_rows.p, S.hist.p, S.boot_cap, d_n, d_n + 1);
             ctx->launches++;
