@@ -59,11 +59,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        """index: one GPU index, a list of them (one nvidia-smi process samples them all; the median /
+        union is reported), or None = no sampling in this process."""
+        self.rows, self.proc = [], None
+        self.index = None if index is None else ",".join(str(i) for i in (index if isinstance(index, (list, tuple)) else [index]))
 
     def start(self):
+        if self.index is None:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -76,6 +81,8 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.index is None:
+            return {}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -248,7 +255,8 @@ def bench_sketch(args, ctx, rank, world, local):
     # clocks are sampled from before the warm-up to the end of the timed region: nvidia-smi needs ~100 ms to
     # start and its first query can stall the GPU, so neither may fall inside the (tens of ms) timed region;
     # the warm-up keeps the same load running for >= 0.5 s so that the samples are taken under load
-    clocks = ClockSampler(local)
+    # N > 1: rank 0's single nvidia-smi process samples all N GPUs (N polling processes perturb the launch path)
+    clocks = ClockSampler(local if world == 1 else (list(range(world)) if rank == 0 else None))
     clocks.start()
     # ... and until the device has settled: a freshly started process on an idle GPU shows sporadic
     # 30-500 ms stalls in its first seconds (clock ramp / driver housekeeping, also seen with no sampler);
@@ -410,6 +418,13 @@ def bench_pairs(args, ctx, rank, world, local, reads):
                       "rows_per_step": int(len(st["rows"])), "db_build_s": t_db,
                       "collective": "all_gather of survivor sketches and of result rows (NCCL)" if world > 1 else "none"},
            "e2e_note": "syl_profile returns rows in host memory: the D2H of the result rows is inside the timed region"}
+    jpath = os.path.join(ROOT, "profiles", "r01_k_join_traffic.json")
+    if os.path.exists(jpath):  # the probe kernel's DRAM traffic and time from the committed ncu capture (not live)
+        j = json.load(open(jpath))
+        peak, peak_src = measured_peak_hbm()
+        out["probe_kernel_ncu"] = {"kernel": j["kernel"], "bound": "hbm", "achieved": j["achieved_GBps"], "peak": peak,
+                                   "unit": "GB/s", "frac": j["achieved_GBps"] / peak, "traffic": j["dram_bytes_read"] + j["dram_bytes_write"],
+                                   "peak_source": peak_src, "source": j["source"], "note": j["note"]}
     if d is not None:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
