@@ -17,8 +17,10 @@
 // (keys are uniform hashes, so bucket = mulhi(key, M) is a perfect interpolation) and walks
 // the equal range.  Work per sample = |sample| short probes + #hits, independent of how many
 // genomes the database holds, and the database is never streamed.  The per-genome statistics
-// are functions of the multiset of hit counts, computed by one warp per genome (exact radix
-// select for the median, no histogram range limit).  In pass 2 the winner of a k-mer is the
+// are functions of the multiset of hit counts: the join accumulates a 256-bin histogram of the
+// counts per (sample, genome) pair and one warp per pair derives everything from it (a count
+// >= 256 anywhere sends the pass through the CSR formulation instead: count, scan, scatter,
+// exact radix select for the median — no range limit).  In pass 2 the winner of a k-mer is the
 // best pass-1 ANI inside that k-mer's equal range — a purely local decision, so no global
 // k-mer -> winner map is ever materialised.
 #include <cub/cub.cuh>

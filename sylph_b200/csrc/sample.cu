@@ -7,10 +7,13 @@
 // The reference walks reads in file order and keeps ONE global exact set S of (kmer, pair-key)
 // plus the count map.  S is keyed by the k-mer, so the state of different k-mers never
 // interacts; only the order of the events OF ONE k-mer matters, and that order is read order.
-// Device formulation: every survivor becomes an event (hash, read index, p0, p1); events are
-// sorted by (hash, read index) with two stable LSD radix sorts; one thread then replays the
-// state machine of one k-mer over its (contiguous) event segment.  Within one read the order of
-// repeated k-mers is irrelevant (identical events; the second is a duplicate either way).
+// Device formulation: every survivor is an event (hash, read index, p0, p1), written by the
+// seeding kernel itself; the events are partitioned by hash bucket, a CTA groups the events of
+// ~25 consecutive buckets by k-mer in shared memory and one thread replays the state machine
+// of one k-mer over its first events in read order (after four counted events every further
+// event counts).  Groups that do not fit take the generic path: two stable LSD radix sorts by
+// (hash, read index) and one thread per (contiguous) k-mer segment.  Within one read the order
+// of repeated k-mers is irrelevant (identical events; the second is a duplicate either way).
 #include <cub/cub.cuh>
 
 #include <chrono>
@@ -176,7 +179,6 @@ __global__ void k_copy_len(const uint32_t *__restrict__ len, uint32_t *__restric
 constexpr int GRP_THREADS = 256;
 constexpr int GRP_CAP = 1024;   // most events one CTA handles in shared memory
 constexpr int GRP_T = 768;      // group span in event offsets: typical n ~ 800, leaving room for k-mers with ~200 events
-constexpr int GRP_SET = 16;     // dedup-set entries kept per k-mer before falling back
 
 __global__ void k_bucket_hist(const EventRec *__restrict__ ev, uint64_t n, uint64_t Mb, uint32_t nbk,
                               uint32_t *__restrict__ cnt) {
@@ -488,7 +490,7 @@ k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ bo
         const uint32_t sl = S.longs[li];
         const uint32_t a0 = S.soff[sl], len = S.soff[sl + 1] - a0;
         uint32_t c = 0, done = 0, nset = 0;
-        uint64_t last_key = 0, dset = 0;  // lane q (< GRP_SET) keeps dedup-set entry q in `dset`
+        uint64_t last_key = 0, dset = 0;  // lane q keeps dedup-set entry q in `dset` (32 entries, then the group falls back)
         uint32_t last_m = 0;
         bool first = true;
         while (done < len) {
