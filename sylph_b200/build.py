@@ -68,6 +68,20 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     os.makedirs(OBJ, exist_ok=True)
+    # one builder at a time (torchrun starts N ranks that all import the package): the others wait
+    # on the lock and then find the library up to date
+    import fcntl
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return SO
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     nvcc = _nvcc()
     hm = _headers_mtime()
     jobs, objs = [], []
@@ -78,7 +92,9 @@ def build(force=False, verbose=False):
             jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(lambda c: _run(c, verbose), jobs))
-    _run([nvcc, "-shared", "-o", SO] + objs, verbose)
+    tmp = SO + ".tmp.%d" % os.getpid()
+    _run([nvcc, "-shared", "-o", tmp] + objs, verbose)
+    os.replace(tmp, SO)  # atomic: a process that already mapped the old file keeps it
     return SO
 
 
