@@ -268,3 +268,48 @@ def get_stats(genome_kmers, sample, k=31, min_number_kmers=50.0, min_count_corre
         ci = bootstrap_interval(full, k, min_count_correct)
     return dict(naive_ani=naive, final_est_ani=final_ani, final_est_cov=final_cov, mean_cov=geq1, median_cov=float(median),
                 contain=len(covs), glen=n, status=status, lam=lam, ci=ci, kmers_lost=lost if winner is not None else None)
+
+
+def contain_sample(genomes, sample, k=31, pseudotax=False, min_number_kmers=50.0, min_count_correct=3.0,
+                   minimum_ani=None, redundant_ani=99.0, no_ci=False):
+    """Inner body of contain() for one sample (src/contain.rs:284-334), written from the reference
+    source only.  genomes: list of dict(kmers=[..], tracked=[..], gn_size=int); sample: dict hash->count.
+    Pass-1 results are taken in genome-index order (the reference's order is thread-timing dependent).
+    -> list of dicts (get_stats fields + genome, rel_abund, seq_abund) in output order."""
+    min_ani = minimum_ani / 100.0 if minimum_ani is not None else (0.95 if pseudotax else 0.90)  # :746-748
+    kw = dict(k=k, min_number_kmers=min_number_kmers, min_count_correct=min_count_correct, min_ani=min_ani, no_ci=no_ci)
+    res = []
+    for gi, g in enumerate(genomes):  # :286-292
+        r = get_stats(g["kmers"], sample, **kw)
+        if r is not None:
+            r["genome"] = gi
+            res.append(r)
+    if pseudotax:
+        # winner_table (:410-430): first entry wins ties, a later genome needs a strictly larger ANI
+        winner = {}
+        for r in res:
+            g = genomes[r["genome"]]
+            for km in list(g["kmers"]) + list(g.get("tracked", [])):
+                v = winner.get(km)
+                if v is None or r["final_est_ani"] > v[0]:
+                    winner[km] = (r["final_est_ani"], r["genome"])
+        wmap = {km: v[1] for km, v in winner.items()}
+        res2 = []
+        for r in res:  # :302-307
+            r2 = get_stats(genomes[r["genome"]]["kmers"], sample, winner=wmap, genome_id=r["genome"], **kw)
+            if r2 is not None:
+                r2["genome"] = r["genome"]
+                res2.append(r2)
+        # derep_if_reassign_threshold (:353-375)
+        old = {r["genome"]: r for r in res}
+        thr = (redundant_ani / 100.0) ** k
+        res = [r for r in res2 if float(old[r["genome"]]["contain"] - r["contain"]) < thr * r["glen"]]
+        total_cov = sum(r["final_est_cov"] for r in res)  # :319-326
+        total_seq = sum(r["final_est_cov"] * genomes[r["genome"]]["gn_size"] for r in res)
+        for r in res:
+            r["rel_abund"] = r["final_est_cov"] / total_cov * 100.0
+            r["seq_abund"] = r["final_est_cov"] * genomes[r["genome"]]["gn_size"] / total_seq * 100.0
+        res.sort(key=lambda r: -r["rel_abund"])  # stable, :329-331
+    else:
+        res.sort(key=lambda r: -r["final_est_ani"])  # :332-334
+    return res

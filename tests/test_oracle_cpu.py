@@ -148,6 +148,76 @@ def test_get_stats_vs_pyref():
                 assert np.allclose(list(r.ci), e["ci"], rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("pseudotax", [False, True])
+def test_contain_sample_vs_pyref(pseudotax):
+    """query / profile body (pass 1, winner table, pass 2, derep, abundances, output order) of the C
+    oracle against the independent Python restatement, on k-mer sets with close relatives so that
+    k-mers are reassigned and a redundant genome is dropped."""
+    rng = np.random.default_rng(77 + int(pseudotax))
+    pool = np.unique(rng.integers(1, 2**57, size=30000, dtype=np.uint64))
+    rng.shuffle(pool)
+    base = [pool[0:3000], pool[3000:5500], pool[5500:8000], pool[8000:10000]]
+    genomes = [
+        dict(kmers=base[0], tracked=pool[20000:20050], gn_size=600000),
+        dict(kmers=np.concatenate([base[0][:2700], pool[10000:10300]]), tracked=base[0][2700:2760], gn_size=590000),  # 90 % relative of 0
+        dict(kmers=base[1], tracked=pool[20100:20120], gn_size=500000),
+        dict(kmers=np.concatenate([base[1][:2490], pool[10300:10310]]), tracked=np.zeros(0, np.uint64), gn_size=500000),  # ~identical to 2
+        dict(kmers=base[2], tracked=pool[20200:20230], gn_size=450000),   # low coverage: lambda branch
+        dict(kmers=base[3], tracked=np.zeros(0, np.uint64), gn_size=400000),  # absent
+        dict(kmers=pool[12000:12040], tracked=np.zeros(0, np.uint64), gn_size=8000),  # fewer than min_number_kmers
+        dict(kmers=np.concatenate([pool[13000:15000], base[0][2000:2600]]), tracked=pool[20300:20310], gn_size=520000),  # shares 600 k-mers with 0, survives
+    ]
+    sample = {}
+    for km in base[0]:
+        c = int(rng.poisson(6.0))
+        if c:
+            sample[int(km)] = c
+    for km in base[1]:
+        c = int(rng.poisson(35.0))  # median >= 30: no Poisson cut-off
+        if c:
+            sample[int(km)] = c
+    for km in base[2]:
+        c = int(rng.poisson(0.6))
+        if c:
+            sample[int(km)] = c
+    for km in pool[13000:15000]:
+        c = int(rng.poisson(4.0))
+        if c:
+            sample[int(km)] = c
+    for km in pool[10300:10310]:
+        sample[int(km)] = 30
+    for km in pool[25000:26000]:
+        sample[int(km)] = int(rng.integers(1, 4))
+    sample[int(base[0][5])] = 0  # a zero count is skipped (src/contain.rs:634-636)
+    exp = R.contain_sample([dict(kmers=g["kmers"].tolist(), tracked=g["tracked"].tolist(), gn_size=g["gn_size"]) for g in genomes],
+                           sample, pseudotax=pseudotax)
+    kmers = np.concatenate([g["kmers"] for g in genomes])
+    koff = np.cumsum([0] + [len(g["kmers"]) for g in genomes]).astype(np.uint64)
+    tracked = np.concatenate([g["tracked"] for g in genomes]).astype(np.uint64)
+    toff = np.cumsum([0] + [len(g["tracked"]) for g in genomes]).astype(np.uint64)
+    gs = np.array([g["gn_size"] for g in genomes], dtype=np.uint64)
+    sh = np.array(list(sample.keys()), dtype=np.uint64)
+    sc = np.array(list(sample.values()), dtype=np.uint32)
+    got = O.contain_sample(O.default_params(pseudotax=pseudotax), kmers, koff, tracked, toff, gs, O.Sample(sh, sc))
+    assert [r.genome for r in got] == [e["genome"] for e in exp]
+    assert len(exp) >= 3
+    if pseudotax:
+        ids = [e["genome"] for e in exp]
+        assert 0 in ids and 7 in ids and 1 not in ids and (2 in ids) != (3 in ids)  # relatives dereplicated
+        assert any(e["kmers_lost"] >= 500 for e in exp)
+    for r, e in zip(got, exp):
+        assert r.contain == e["contain"] and r.glen == e["glen"] and r.median_cov == e["median_cov"]
+        assert ["LOW", "HIGH", "LAMBDA"][r.lambda_status] == e["status"]
+        assert r.kmers_lost == (e["kmers_lost"] if pseudotax else -1)
+        for f in ("naive_ani", "final_est_ani", "final_est_cov", "mean_cov"):
+            assert abs(getattr(r, f) - e[f]) < 1e-12, f
+        assert bool(r.ci_valid) == (e["ci"] is not None)
+        if e["ci"]:
+            assert np.allclose(list(r.ci), e["ci"], rtol=0, atol=1e-12)
+        if pseudotax:
+            assert abs(r.rel_abund - e["rel_abund"]) < 1e-9 and abs(r.seq_abund - e["seq_abund"]) < 1e-9
+
+
 @pytest.fixture(scope="module")
 def config1():
     db = []
