@@ -1,0 +1,37 @@
+"""CPU suite: the parts of bench.py that need no GPU — the reference arm's JSON line (bench contract)
+and the helpers around it."""
+import json
+import os
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--reads", "40000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "bases/s sketched" and d["unit"] == "bases/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_clock_sampler_degrades_without_nvidia_smi():
+    sys.path.insert(0, REPO)
+    import bench
+    c = bench.ClockSampler([0, 1])
+    assert c.index == "0,1"
+    c.start()
+    out = c.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    off = bench.ClockSampler(None)
+    off.start()
+    assert off.stop() == {}
