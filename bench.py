@@ -33,6 +33,21 @@ K, C = 31, 200
 GENOME_LEN = 4_000_000
 
 
+def sketch_config(args):
+    """The `config` object of the sketch workload: identical in our arm and in the reference arm."""
+    n_bases = args.reads * READ_LEN
+    return {"workload": "sketch 1 Gbp synthetic 150 bp SE reads k=31 c=200 (BASELINE.json configs[1])",
+            "reads_per_gpu": args.reads, "read_len": READ_LEN, "k": K, "c": C, "sem": "avx2-lane",
+            "l2": "inputs (%.2f GB per step) are larger than L2; no flush needed" % (n_bases / 1e9)}
+
+
+def profile_config(args, world):
+    n_samples = args.samples or (1 if world == 1 else 16)
+    return {"workload": "profile %d sample sketch(es) vs %d synthetic 4 Mbp genome sketches per GPU (BASELINE.json configs[%d])"
+                        % (n_samples, args.genomes, 2 if world == 1 else 3),
+            "genomes_per_gpu": args.genomes, "samples": n_samples, "reads_per_sample": args.reads, "k": K, "c": C}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,7 +213,11 @@ def cpu_sketch_baseline(host_bases, host_off, n_reads_sample, repeats=1):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port: no Rust toolchain in the image)."""
+    """--impl reference: the reference's CPU path (oracle port: no Rust toolchain in the image) on the host
+    cores, same config / metric / unit as our arm.  sketch: every step sketches ALL reads of the workload
+    (AVX2-intrinsic seeding over all cores + the sequential dedup).  profile: every step is the oracle's
+    `profile` of the sample against all genomes over all cores (the db is sketched on the GPU when there
+    is one — database construction is not part of the timed path in either arm)."""
     import numpy as np
     import torch
     rank = int(os.environ.get("RANK", 0))
@@ -207,20 +226,38 @@ def run_reference(args):
     from sylph_b200 import synth
     from oracle import oracle as O
     cores = os.cpu_count() or 1
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    b, o = synth.reads(args.reads, READ_LEN, device=dev)
+    b, o = b.cpu().numpy(), o.cpu().numpy().astype(np.uint64)
     if args.workload == "sketch":
-        n_sample = min(args.reads, 1_000_000)  # 150 Mbases per step
-        dev = "cuda" if torch.cuda.is_available() else "cpu"
-        if dev == "cpu":
-            n_sample = min(n_sample, 100_000)
-        b, o = synth.reads(n_sample, READ_LEN, device=dev)
-        b, o = b.cpu().numpy(), o.cpu().numpy().astype(np.uint64)
         fn = lambda: O.sketch_reads(b, o, k=K, c=C, sem=O.SEM_AVX2_INTRIN, nthreads=cores)
         units, unit, metric = len(b), "bases/s", "bases/s sketched"
-        sample = "%d of %d reads per step (%d bases)" % (n_sample, args.reads, len(b))
-        cfg = {"workload": "sketch 1 Gbp synthetic 150 bp SE reads k=31 c=200 (BASELINE.json configs[1])",
-               "reads": args.reads, "read_len": READ_LEN, "k": K, "c": C}
+        sample = "all %d reads per step (%d bases), %d OpenMP threads" % (args.reads, len(b), cores)
+        cfg = sketch_config(args)
     else:
-        raise SystemExit("--impl reference --workload profile: use the default run's pairs.cpu_baseline")
+        cfg = profile_config(args, 1)
+        G = args.genomes
+        h, c, _, _ = O.sketch_reads(b, o, k=K, c=C, sem=O.SEM_AVX2_INTRIN, nthreads=cores)
+        if dev == "cuda":
+            import sylph_b200
+            ctx = sylph_b200.Context(0)
+            g = synth.sketch_db_range(ctx, 0, G)
+            d = g.download()
+            g.free()
+            ctx.close()
+        else:  # no GPU (CPU test of this arm): the oracle sketches the genomes itself
+            km, tr, gs, ko, to = [], [], [], [0], [0]
+            for i in range(G):
+                gb, _ = synth.db_chunk(i, i + 1, GENOME_LEN)
+                a, t, n = O.sketch_genome(gb.numpy(), np.array([0, GENOME_LEN], np.uint64), k=K, c=C)
+                km.append(a); tr.append(t); gs.append(n); ko.append(ko[-1] + len(a)); to.append(to[-1] + len(t))
+            d = dict(kmers=np.concatenate(km), kmer_off=np.array(ko, np.uint64), tracked=np.concatenate(tr),
+                     tracked_off=np.array(to, np.uint64), gn_size=np.array(gs, np.uint64))
+        smp = O.Sample(h, c)
+        p = O.default_params(pseudotax=True)
+        fn = lambda: O.contain_sample(p, d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"], smp, nthreads=cores)
+        units, unit, metric = float(G), "pairs/s", "(sample x genome) containment pairs/s"
+        sample = "all %d pairs per step: oracle profile (2 x get_stats + winner table), %d OpenMP threads" % (G, cores)
     for _ in range(args.warmup):
         fn()
     t = time.perf_counter()
@@ -291,7 +328,8 @@ def bench_sketch(args, ctx, rank, world, local):
     surv_buf = torch.empty(int(n_bases / C * 1.3 + 65536) * 2, dtype=torch.int64, device="cuda")
     n_surv = ctx.extract_markers_batch(bases, off, k=K, c=C, out=surv_buf)
     del surv_buf
-    alg_bytes = n_bases + 32 * n_surv  # 1 B per base read + one 32-byte event (hash, read, pair keys) per survivor written
+    alg_bytes = n_bases + 8 * n_surv   # 1 B per base read + 8 B per survivor written
+    model_bytes = n_bases + 32 * n_surv  # what this kernel really writes: one 32-byte event (hash, read, pair keys) per survivor
     peak, peak_src = measured_peak_hbm()
     k_ms = kms / max(klaunch, 1)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
@@ -302,7 +340,7 @@ def bench_sketch(args, ctx, rank, world, local):
     roofline = {"kernel": "k_seed<31, events, W=30>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": k_ms, "kernel_share_of_step": kms / ms if ms else None,
-                "algorithmic_bytes_per_launch": alg_bytes,
+                "algorithmic_bytes_per_launch": alg_bytes, "traffic_model_bytes_per_launch": model_bytes,
                 "note": "integer-issue bound: ~33 SASS instructions per window, 18.4 of them on the ALU pipe (1 warp "
                         "instruction / 2 cycles) and 12.4 IMADs on the FMA pipe; ncu: ALU pipe 75 % active, fmaheavy 59 %, "
                         "DRAM 9 %; see DESIGN.md 4.1 and profiles/"}
@@ -339,46 +377,51 @@ def bench_sketch(args, ctx, rank, world, local):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_sketch_baseline(hb_np, ho_np, min(n_reads, 2_000_000))
     line = {"metric": "bases/s sketched", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "sketch 1 Gbp synthetic 150 bp SE reads k=31 c=200 (BASELINE.json configs[1])",
-                       "reads_per_gpu": n_reads, "read_len": READ_LEN, "k": K, "c": C, "sem": "avx2-lane",
-                       "l2": "inputs (%.2f GB per step) are larger than L2; no flush needed" % (n_bases / 1e9),
-                       "sketch_entries": state["n"], "survivors": int(n_surv)},
+            "warmup": n_w, "warmup_requested": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": sketch_config(args), "workload_stats": {"sketch_entries": state["n"], "survivors": int(n_surv)},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
     if cpu:
         line["cpu_baseline"] = cpu
     return line, (bases, off)
 
 
-def build_db(ctx, g0, g1, chunk=125):
-    from sylph_b200 import synth
-    parts = []
-    for a in range(g0, g1, chunk):
-        b = min(g1, a + chunk)
-        bases, off = synth.db_chunk(a, b, GENOME_LEN, device="cuda")
-        import torch
-        goff = torch.arange(b - a + 1, dtype=torch.int64, device="cuda")
-        parts.append(ctx.sketch_genomes(bases, off, goff, k=K, c=C))
-        del bases
-    g = ctx.concat_genomes(parts)
-    for p in parts:
-        p.free()
-    return g
+def rows_equal_oracle(rows, exp, tol=1e-6):
+    """Field-by-field comparison of syl_profile rows with the oracle's rows (same order): integers exact,
+    floats within `tol` relative — the same bar as tests/test_contain_gpu.py::compare. -> (ok, first difference)"""
+    if len(rows) != len(exp):
+        return False, "row count %d != %d" % (len(rows), len(exp))
+    for i, (r, e) in enumerate(zip(rows, exp)):
+        for f in ("genome", "contain", "glen", "lambda_status", "kmers_lost", "ci_valid"):
+            if int(r[f]) != int(getattr(e, f)):
+                return False, "row %d %s: %s != %s" % (i, f, r[f], getattr(e, f))
+        for f in ("naive_ani", "final_est_ani", "final_est_cov", "mean_cov", "median_cov", "rel_abund", "seq_abund"):
+            x, y = float(r[f]), float(getattr(e, f))
+            if abs(x - y) > tol * max(1.0, abs(y)):
+                return False, "row %d %s: %r != %r" % (i, f, x, y)
+        if e.ci_valid:
+            for j in range(4):
+                if abs(float(r["ci"][j]) - e.ci[j]) > tol * max(1.0, abs(e.ci[j])):
+                    return False, "row %d ci[%d]" % (i, j)
+    return True, None
+
+
+PAIR_KERNELS = {"join": "k_join_hist<pass 1>", "join2": "k_join2_hits", "stats": "k_stats_hist", "boot": "k_boot_iter"}
 
 
 def bench_pairs(args, ctx, rank, world, local, reads):
     """BASELINE.json configs[2] (N=1) / configs[3] shape (N>1: genome-sharded db, replicated samples)."""
     import numpy as np
     import torch
-    from sylph_b200 import synth
+    from sylph_b200 import _lib, synth
     n_samples = args.samples or (1 if world == 1 else 16)
     G = args.genomes
     t0 = time.perf_counter()
-    genomes = build_db(ctx, rank * G, (rank + 1) * G)
+    genomes = synth.sketch_db_range(ctx, rank * G, (rank + 1) * G, GENOME_LEN, k=K, c=C)
     db = ctx.build_db(genomes, genome_base=rank * G)
     torch.cuda.synchronize()
     t_db = time.perf_counter() - t0
+    db_keys = int(_lib.lib().syl_genomes_total_kmers(genomes._h))
     samples = []
     bases, off = reads
     for si in range(n_samples):
@@ -403,28 +446,37 @@ def bench_pairs(args, ctx, rank, world, local, reads):
 
     for _ in range(args.warmup):
         step()
+    ctx.enable_timing(True)
+    for kname in PAIR_KERNELS:
+        ctx.kernel_time(kname, reset=True)
     l0 = ctx.launches
     ms, wall = timed(step, args.steps, world)
     launches = ctx.launches - l0
+    per_step = {kname: ctx.kernel_time(kname, reset=True)[0] / args.steps for kname in PAIR_KERNELS}
+    ctx.enable_timing(False)
     pairs = float(n_samples) * G * world
     value = pairs * args.steps / (ms * 1e-3)
     d = genomes.download() if (rank == 0 and world == 1 and not args.no_cpu) else None
-    nk_total = sum_over_ranks(float(int(np.sum([len(s) for s in samples]))), 1)
     out = {"metric": "(sample x genome) containment pairs/s", "value": value, "unit": "pairs/s", "ms_per_step": ms / args.steps,
            "wall_ms_per_step": wall / args.steps, "steps": args.steps, "gpu_launches": int(launches),
-           "config": {"workload": "profile %d sample sketch(es) vs %d synthetic 4 Mbp genome sketches per GPU "
-                                  "(BASELINE.json configs[%d])" % (n_samples, G, 2 if world == 1 else 3),
-                      "genomes_per_gpu": G, "samples": n_samples, "sample_keys": int(nk_total),
-                      "rows_per_step": int(len(st["rows"])), "db_build_s": t_db,
-                      "collective": "all_gather of survivor sketches and of result rows (NCCL)" if world > 1 else "none"},
+           "config": profile_config(args, world),
+           "workload_stats": {"sample_keys": int(np.sum([len(s) for s in samples])), "rows_per_step": int(len(st["rows"])),
+                              "db_build_s": t_db, "db_keys_per_gpu": db_keys,
+                              "collective": "all_gather of survivor sketches and of result rows (NCCL)" if world > 1 else "none"},
            "e2e_note": "syl_profile returns rows in host memory: the D2H of the result rows is inside the timed region"}
-    jpath = os.path.join(ROOT, "profiles", "r01_k_join_traffic.json")
-    if os.path.exists(jpath):  # the probe kernel's DRAM traffic and time from the committed ncu capture (not live)
-        j = json.load(open(jpath))
-        peak, peak_src = measured_peak_hbm()
-        out["probe_kernel_ncu"] = {"kernel": j["kernel"], "bound": "hbm", "achieved": j["achieved_GBps"], "peak": peak,
-                                   "unit": "GB/s", "frac": j["achieved_GBps"] / peak, "traffic": j["dram_bytes_read"] + j["dram_bytes_write"],
-                                   "peak_source": peak_src, "source": j["source"], "note": j["note"]}
+    # live roofline of the step's dominant kernel: CUDA events recorded inside the library around every launch
+    peak, peak_src = measured_peak_hbm()
+    dom = max(per_step, key=lambda kname: per_step[kname])
+    alg_bytes = 8.0 * db_keys + 64.0 * G * n_samples  # 8 B x |G| per pair (db streamed once for all samples) + 64 B per row
+    ach = alg_bytes / (per_step[dom] * 1e-3) / 1e9 if per_step[dom] else None
+    out["kernels_ms_per_step"] = per_step
+    out["roofline"] = {"kernel": PAIR_KERNELS[dom], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                       "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
+                       "kernel_ms": per_step[dom], "kernel_share_of_step": per_step[dom] / (ms / args.steps),
+                       "algorithmic_bytes_per_launch": alg_bytes,
+                       "note": "SURVEY §8(d) byte model of a genome-streaming probe loop (8 B x |G| per pair); this implementation "
+                               "probes a sorted db index with the sample keys and never streams the db, so this is an equivalent "
+                               "bandwidth that is not bounded by HBM (DESIGN.md 4.4)"}
     if d is not None:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
@@ -437,14 +489,12 @@ def bench_pairs(args, ctx, rank, world, local, reads):
         out["cpu_baseline"] = {"value": G / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
                                "sample": "all %d pairs of the same db/sample, oracle profile (2 x get_stats + winner table) over %d OpenMP threads" % (G, cores),
                                "rows": len(res)}
-        assert len(res) == len(st["rows"]), (len(res), len(st["rows"]))
-        kbytes = 8.0 * float(d["kmer_off"][-1])
-        out["roofline_equiv"] = {
-            "streaming_bytes_per_step": kbytes + 64.0 * G,
-            "equiv_GBps": (kbytes + 64.0 * G) / (ms / args.steps * 1e-3) / 1e9,
-            "note": "SURVEY §8(d) counts 8 B x |G| per pair for a genome-streaming probe loop; this implementation "
-                    "probes a sorted db index with the sample keys instead and never streams the db, so the "
-                    "equivalent bandwidth may exceed the HBM peak; see DESIGN.md"}
+        mine = st["rows"][st["rows"]["sample"] == 0]
+        ok, why = rows_equal_oracle(mine, res)
+        out["parity_checked"] = bool(ok)
+        out["parity_detail"] = ("all %d profile rows of sample 0 equal the oracle's field by field (ints exact, floats 1e-6)" % len(res)) if ok else why
+        if not ok:
+            raise SystemExit("bench: profile rows differ from the oracle: " + str(why))
     for s in samples:
         s.free()
     db.free()

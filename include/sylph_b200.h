@@ -71,6 +71,20 @@ uint64_t syl_ctx_launch_count(const syl_ctx *ctx);
  * accumulated milliseconds, launches and bases since the last reset (and resets when asked). */
 int syl_ctx_enable_timing(syl_ctx *ctx, int on);
 int syl_ctx_seed_kernel_time(syl_ctx *ctx, double *total_ms, uint64_t *launches, uint64_t *bases, int reset);
+/* The same for the other kernels of the two paths (bench.py's live roofline figures): accumulated
+ * CUDA-event milliseconds and launches of kernel class `which` since the last reset. Syncs the ctx stream. */
+enum {
+    SYL_KERNEL_SEED = 0,        /* k_seed (all variants) */
+    SYL_KERNEL_GROUP_DEDUP = 1, /* read-sketch post-pass: k_group_dedup */
+    SYL_KERNEL_JOIN = 2,        /* containment pass 1 probe: k_join_hist<pass 1> */
+    SYL_KERNEL_JOIN2 = 3,       /* containment pass 2: k_join2_hits / k_join_hist<pass 2> */
+    SYL_KERNEL_STATS = 4,       /* k_stats_hist / k_stats */
+    SYL_KERNEL_BOOT = 5,        /* bootstrap: k_boot_iter (+ k_boot_seq, k_boot_final) */
+    SYL_KERNEL_GENOME_POST = 6, /* genome-sketch post-pass (everything after k_seed) */
+    SYL_KERNEL_PACK = 7,        /* ASCII -> 2-bit packing on the device (unused by the host-packed path) */
+    SYL_KERNEL_COUNT = 8
+};
+int syl_ctx_kernel_time(syl_ctx *ctx, int which, double *total_ms, uint64_t *launches, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * (1) Seeding — replaces extract_markers / extract_markers_positions over a whole batch

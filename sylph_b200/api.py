@@ -92,6 +92,14 @@ class Context:
         _lib.check(_lib.lib().syl_ctx_seed_kernel_time(self._h, C.byref(ms), C.byref(n), C.byref(b), int(reset)))
         return ms.value, n.value, b.value
 
+    KERNELS = {"seed": 0, "group_dedup": 1, "join": 2, "join2": 3, "stats": 4, "boot": 5, "genome_post": 6, "pack": 7}
+
+    def kernel_time(self, which, reset=True):
+        """-> (total_ms, launches) of kernel class `which` (name in Context.KERNELS) since the last reset."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        _lib.check(_lib.lib().syl_ctx_kernel_time(self._h, self.KERNELS[which], C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
+
     # ---- (1) seeding -------------------------------------------------------------------------
     def extract_markers_batch(self, bases, rec_off, k=31, c=200, sem=SEM_AVX2, with_pos=False, cap=None,
                               out=None):

@@ -154,8 +154,8 @@ void syl_ctx_destroy(syl_ctx *ctx) {
         if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (auto &t : ctx->timed_pending) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -174,21 +174,42 @@ int syl_ctx_enable_timing(syl_ctx *ctx, int on) {
     if (!ctx) { set_error("ctx is NULL"); return SYL_ERR_ARG; }
     SYL_CUDA(cudaSetDevice(ctx->device));
     syl::tl_ctx = ctx;
-    if (on && !ctx->ev0) {
-        SYL_CUDA(cudaEventCreate(&ctx->ev0));
-        SYL_CUDA(cudaEventCreate(&ctx->ev1));
-    }
     ctx->timing = on != 0;
+    return SYL_OK;
+}
+
+// resolve the recorded event pairs into the per-kernel totals (the stream must be idle)
+static int timers_resolve(syl_ctx *ctx) {
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->timed_pending.empty()) return SYL_OK;
+    SYL_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &t : ctx->timed_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess && t.which >= 0 && t.which < SYL_KERNEL_COUNT) {
+            ctx->kernel_ms[t.which] += ms;
+            ctx->kernel_launches[t.which]++;
+        }
+        ctx->event_pool.push_back(t.e0);
+        ctx->event_pool.push_back(t.e1);
+    }
+    ctx->timed_pending.clear();
+    return SYL_OK;
+}
+
+int syl_ctx_kernel_time(syl_ctx *ctx, int which, double *total_ms, uint64_t *launches, int reset) {
+    if (!ctx || which < 0 || which >= SYL_KERNEL_COUNT) { set_error("bad argument"); return SYL_ERR_ARG; }
+    SYL_TRY(timers_resolve(ctx));
+    if (total_ms) *total_ms = ctx->kernel_ms[which];
+    if (launches) *launches = ctx->kernel_launches[which];
+    if (reset) { ctx->kernel_ms[which] = 0.; ctx->kernel_launches[which] = 0; }
     return SYL_OK;
 }
 
 int syl_ctx_seed_kernel_time(syl_ctx *ctx, double *total_ms, uint64_t *launches, uint64_t *bases, int reset) {
     if (!ctx) { set_error("ctx is NULL"); return SYL_ERR_ARG; }
-    if (total_ms) *total_ms = ctx->seed_ms;
-    if (launches) *launches = ctx->seed_launches;
     if (bases) *bases = ctx->seed_bases;
-    if (reset) { ctx->seed_ms = 0.; ctx->seed_launches = 0; ctx->seed_bases = 0; }
-    return SYL_OK;
+    if (reset) ctx->seed_bases = 0;
+    return syl_ctx_kernel_time(ctx, SYL_KERNEL_SEED, total_ms, launches, reset);
 }
 
 int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,

@@ -53,11 +53,15 @@ struct syl_ctx {
     // small persistent scratch: device counters + pinned host mirror
     uint64_t *d_counters = nullptr;  // 16 x u64
     uint64_t *h_counters = nullptr;  // pinned
-    // optional timing of the seeding kernel (syl_ctx_enable_timing)
+    // optional per-kernel timing (syl_ctx_enable_timing): every timed launch is bracketed by a pair of
+    // CUDA events from a pool; the pairs are resolved (cudaEventElapsedTime) when the totals are read
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double seed_ms = 0.;
-    uint64_t seed_launches = 0, seed_bases = 0;
+    struct TimedLaunch { int which; cudaEvent_t e0, e1; };
+    std::vector<TimedLaunch> timed_pending;
+    std::vector<cudaEvent_t> event_pool;
+    double kernel_ms[SYL_KERNEL_COUNT] = {};
+    uint64_t kernel_launches[SYL_KERNEL_COUNT] = {};
+    uint64_t seed_bases = 0;
     // double-buffered H2D staging for host-memory inputs (lazily allocated, reused across calls)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
@@ -74,6 +78,30 @@ struct syl_ctx {
 };
 
 namespace syl {
+// RAII bracket of one timed launch (no-op unless syl_ctx_enable_timing is on)
+struct KernelTimer {
+    syl_ctx *c;
+    int which;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KernelTimer(syl_ctx *ctx, int w) : c(ctx), which(w) {
+        if (!c->timing) return;
+        auto take = [&]() {
+            cudaEvent_t e = nullptr;
+            if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+            else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+            return e;
+        };
+        e0 = take(); e1 = take();
+        if (e0 && e1) cudaEventRecord(e0, c->stream);
+    }
+    void stop() {
+        if (!e0 || !e1) return;
+        cudaEventRecord(e1, c->stream);
+        c->timed_pending.push_back({which, e0, e1});
+        e0 = e1 = nullptr;
+    }
+    ~KernelTimer() { stop(); }
+};
 // ctx whose scratch cache DevBuf uses on this thread (set at every API entry)
 extern thread_local syl_ctx *tl_ctx;
 // device arrays owned by handles: taken from / returned to the owning ctx's block cache

@@ -824,6 +824,7 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
         SYL_CUDA(cudaMemsetAsync(d_ovf, 0, 8, st));
         if (have) {
             if (!pass2 && S.hits.p) SYL_CUDA(cudaMemsetAsync(S.hits.p, 0, S.S * S.max_n * sizeof(uint2), st));
+            KernelTimer kt(ctx, pass2 ? SYL_KERNEL_JOIN2 : SYL_KERNEL_JOIN);
             if (!pass2)
                 k_join_hist<false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->N, db->bstart, db->M, db->NB, db->maxkey,
                                                           nullptr, nullptr, S.touched.p, nullptr, S.chist.p, d_ovf, S.hits.p, S.max_n);
@@ -838,9 +839,11 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
         }
         for (;;) {
             SYL_CUDA(cudaMemsetAsync(d_n, 0, 16, st));
+            KernelTimer kt(ctx, SYL_KERNEL_STATS);
             k_stats_hist<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(S.touched.p, S.chist.p, db->glen, pass2 ? S.lost.p : nullptr,
                                                                            G, NP, db->genome_base, P, pass2 ? 1 : 0, S.rows.p, S.rows_cap,
                                                                            S.boot_rows.p, S.hist.p, S.boot_cap, d_n, d_n + 1);
+            kt.stop();
             ctx->launches++;
             SYL_CUDA(cudaGetLastError());
             SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 12, d_n, 32, cudaMemcpyDeviceToHost, st));
@@ -906,6 +909,7 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
             SYL_TRY(S.reject.alloc(n_boot, st));
         }
         SYL_CUDA(cudaMemsetAsync(S.reject.p, 0, (size_t)n_boot * 4, st));
+        KernelTimer kt(ctx, SYL_KERNEL_BOOT);
         for (uint64_t r0 = 0; r0 < n_boot; r0 += 32768) {  // gridDim.y limit
             const uint32_t nr = (uint32_t)std::min<uint64_t>(32768, n_boot - r0);
             k_boot_iter<<<dim3(BOOT_ITERS, nr), BOOT_THREADS, 0, st>>>(S.hist.p + r0 * 17, P, S.res_ani.p + r0 * BOOT_ITERS,
@@ -915,6 +919,7 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
         }
         k_boot_seq<<<nblk(n_boot, 32), 32, 0, st>>>(S.hist.p, (uint32_t)n_boot, P, S.reject.p, S.res_ani.p, S.res_lambda.p, S.res_ok.p);
         k_boot_final<<<(unsigned)n_boot, 128, 0, st>>>(S.boot_rows.p, (uint32_t)n_boot, S.res_ani.p, S.res_lambda.p, S.res_ok.p, S.rows.p);
+        kt.stop();
         ctx->launches += 2;
         SYL_CUDA(cudaGetLastError());
     }

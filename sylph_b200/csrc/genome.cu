@@ -226,6 +226,7 @@ int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases
     k_contig_genome<<<nblk(n_contigs, 256), 256, 0, st>>>(d_genome_off, n_genomes, n_contigs, cg.p);
     ctx->launches++;
     uint64_t total_kept = 0, total_tracked = 0;
+    KernelTimer kt_post(ctx, SYL_KERNEL_GENOME_POST);
     if (N) {
         k_split<<<nblk(N, 256), 256, 0, st>>>(sv.p, N, key_a.p, hash_a.p);
         // 2. position order: sort by (contig, pos)
@@ -276,6 +277,7 @@ int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases
                                                                total_kept, pseudotax ? total_tracked : 0, d_contig_off,
                                                                out->kmer_off, out->tracked_off, out->gn_size);
     ctx->launches++;
+    kt_post.stop();
     SYL_CUDA(cudaGetLastError());
     if (!pseudotax) SYL_CUDA(cudaMemsetAsync(out->tracked_off, 0, (n_genomes + 1) * 8, st));
     SYL_CUDA(cudaStreamSynchronize(st));

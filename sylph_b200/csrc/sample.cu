@@ -890,8 +890,11 @@ struct SampleBuilder {
         k_scatter_events<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, boff.p, cursor.p, part.p);
         SYL_CUDA(cudaFuncSetAttribute(k_group_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
         k_group_ranges<<<nblk(ng, 256), 256, 0, st>>>(boff.p, nbk, ng, g_bf.p, g_be.p);
-        k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, Mb, nbk, no_dedup, st_hash.p, st_cnt.p,
-                                                                   g_nuniq.p, g_e0.p, g_n.p, g_fb.p, d_ndup);
+        {
+            KernelTimer kt(ctx, SYL_KERNEL_GROUP_DEDUP);
+            k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, Mb, nbk, no_dedup, st_hash.p, st_cnt.p,
+                                                                       g_nuniq.p, g_e0.p, g_n.p, g_fb.p, d_ndup);
+        }
         k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
         k_fallback_sizes<<<nblk(ng, 256), 256, 0, st>>>(g_n.p, g_fb.p, ng, fsz.p);
         k_scan_u32<<<1, 1024, 0, st>>>(fsz.p, ng, foff.p);

@@ -123,23 +123,17 @@ int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const
     const seed_kern_t kern = emit_events ? (k == 31 ? seed_kernels_k31_ev(W) : seed_kernels_k21_ev(W))
                                          : (k == 31 ? seed_kernels_k31_sv(W) : seed_kernels_k21_sv(W));
     SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev0, st));
+    KernelTimer kt(ctx, SYL_KERNEL_SEED);
     kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
         d_bases, n_bases, d_rec_off, off_bias, tile_rec.p, thr, sem, with_pos, d_out, cap,
         reinterpret_cast<unsigned long long *>(ctx->d_counters), smul, rec_base, no_dedup, d_pend,
         BucketHist{emit_events ? d_bucket_cnt : nullptr, Mb, nbk});
-    if (ctx->timing) SYL_CUDA(cudaEventRecord(ctx->ev1, st));
+    kt.stop();
+    if (ctx->timing) ctx->seed_bases += n_bases;
     ctx->launches++;
     SYL_CUDA(cudaGetLastError());
     SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SYL_CUDA(cudaStreamSynchronize(st));
-    if (ctx->timing) {
-        float ms = 0.f;
-        SYL_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        ctx->seed_ms += ms;
-        ctx->seed_launches++;
-        ctx->seed_bases += n_bases;
-    }
     *n_out = ctx->h_counters[0];
     if (n_pend) *n_pend = ctx->h_counters[1];
     if (*n_out > cap) {

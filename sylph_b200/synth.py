@@ -127,3 +127,19 @@ def reads(n_reads, read_len=150, n_comm=64, genome_len=4_000_000, seed=SEED_READ
         buf[r0 * read_len:r1 * read_len] = reads_chunk(r0, r1, read_len, n_comm, genome_len, seed, device, cdf)
     off = torch.arange(n_reads + 1, dtype=torch.int64, device=device) * read_len
     return buf[:total], off
+
+
+def sketch_db_range(ctx, g0, g1, genome_len=4_000_000, k=31, c=200, chunk=125, device="cuda"):
+    """Sketch synthetic genomes [g0, g1) on the device in batches of `chunk` genomes (bases are generated
+    on the device, never cross PCIe: SURVEY §8-d config 5) -> one Genomes handle."""
+    parts = []
+    for a in range(g0, g1, chunk):
+        b = min(g1, a + chunk)
+        bases, off = db_chunk(a, b, genome_len, device=device)
+        goff = torch.arange(b - a + 1, dtype=torch.int64, device=device)
+        parts.append(ctx.sketch_genomes(bases, off, goff, k=k, c=c))
+        del bases
+    g = ctx.concat_genomes(parts)
+    for p in parts:
+        p.free()
+    return g

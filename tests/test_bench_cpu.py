@@ -24,6 +24,26 @@ def test_reference_arm_prints_one_contract_line():
     assert "workload" in d["config"]
 
 
+def test_reference_arm_profile_workload():
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "profile", "--steps", "1",
+                        "--warmup", "1", "--reads", "20000", "--genomes", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=600, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0
+    assert d["config"]["genomes_per_gpu"] == 3 and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_both_arms_share_the_config_object():
+    sys.path.insert(0, REPO)
+    import bench
+
+    class A:
+        reads, genomes, samples = 1000, 7, None
+    assert bench.sketch_config(A) == bench.sketch_config(A) and set(bench.sketch_config(A)) >= {"workload", "reads_per_gpu", "k", "c"}
+    assert bench.profile_config(A, 1)["samples"] == 1 and bench.profile_config(A, 8)["samples"] == 16
+
+
 def test_clock_sampler_degrades_without_nvidia_smi():
     sys.path.insert(0, REPO)
     import bench
