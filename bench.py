@@ -369,9 +369,19 @@ def bench_sketch(args, ctx, rank, world, local):
     e2e_steps = max(1, min(args.steps, 5))
     _, wall_ms = timed(step_e2e, e2e_steps, world)
     e2e_value = total_bases * e2e_steps / (wall_ms * 1e-3)
-    e2e = {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
+    from sylph_b200 import _lib
+    ingest = os.environ.get("SYL_HOST_INGEST", "packed2")
+    if ingest == "ascii":
+        h2d = int(n_bases + 8 * (n_reads + 1))
+        what = "ASCII bases + u64 record offsets copied as they are"
+    else:  # 2-bit words + u32 chunk-relative offsets (one extra offset per 32 Mbase chunk)
+        h2d = int((n_bases + 15) // 16 * 4 + 4 * (n_reads + 1 + n_bases // (32 << 20) + 1))
+        what = ("host ASCII -> 2-bit words by %d packer threads into pinned staging (inside the timed region), "
+                "u32 chunk-relative record offsets" % _lib.lib().syl_pack_threads())
+    e2e = {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": int(12 * e2e_state["n"]), "steps": e2e_steps, "ms_per_step": wall_ms / e2e_steps,
-           "timing": "wall clock bracketed by device syncs, max over ranks"}
+           "timing": "wall clock bracketed by device syncs, max over ranks", "ingest": what,
+           "call": "syl_sketch_reads(SYL_MEM_HOST, ASCII bases, u64 offsets) + syl_sample_download into pinned result buffers"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

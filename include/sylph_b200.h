@@ -109,6 +109,11 @@ int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases
                    const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
                    syl_survivor *out, uint64_t cap, uint64_t *n_out);
 
+/* The same for 2-bit packed input (layout: see syl_sketch_reads_packed2). */
+int syl_seed_batch_packed2(syl_ctx *ctx, int mem, const uint32_t *packed, uint64_t n_bases,
+                           const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
+                           syl_survivor *out, uint64_t cap, uint64_t *n_out);
+
 /* ------------------------------------------------------------------------------------------
  * (2) Sample sketch — replaces sketch_sequences_needle's per-record loop
  *     (src/sketch.rs:917-947: pair_kmer_single :624-656, extract_markers,
@@ -122,6 +127,19 @@ typedef struct syl_sample syl_sample;
 int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
                      const uint64_t *rec_off, uint64_t n_reads, int k, uint64_t c, int no_dedup,
                      int sem, syl_sample **out);
+/* The same for reads that are already 2-bit packed: word w (little-endian u32) holds bases 16w .. 16w+15 of
+ * the flat buffer, base 16w+j in bits [30-2j, 31-2j], codes = BYTE_TO_SEQ (src/types.rs:50-59: A/a 0, C/c 1,
+ * G/g 2, T/t/U/u 3, everything else 0); ceil(n_bases/16) words; rec_off in bases as above.  A FASTQ parser
+ * that packs while it parses ships 4x fewer bytes to the device.  syl_sketch_reads with SYL_MEM_HOST does
+ * this internally (worker threads pack into pinned staging buffers while earlier chunks are copied and
+ * seeded); SYL_PACK_THREADS overrides the worker count (default min(cores, 64)). */
+int syl_sketch_reads_packed2(syl_ctx *ctx, int mem, const uint32_t *packed, uint64_t n_bases,
+                             const uint64_t *rec_off, uint64_t n_reads, int k, uint64_t c, int no_dedup,
+                             int sem, syl_sample **out);
+/* Host-side packer used by the above: exact BYTE_TO_SEQ codes, n_threads <= 0 = default. */
+int syl_pack2(const uint8_t *bases, uint64_t n_bases, uint32_t *words, int n_threads);
+/* Worker threads the host-memory path of syl_sketch_reads packs with (for bench.py's e2e record). */
+int syl_pack_threads(void);
 /* Wrap an existing sketch (e.g. a deserialised .sylsp).  Pairs need not be sorted; hashes must
  * be distinct. */
 int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_t *count,

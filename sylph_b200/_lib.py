@@ -54,7 +54,11 @@ SIGNATURES = {
     "syl_ctx_seed_kernel_time": (_i, [_vp, C.POINTER(C.c_double), _pu64, _pu64, _i]),
     "syl_ctx_kernel_time": (_i, [_vp, _i, C.POINTER(C.c_double), _pu64, _i]),
     "syl_seed_batch": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _vp, _u64, _pu64]),
+    "syl_seed_batch_packed2": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _vp, _u64, _pu64]),
     "syl_sketch_reads": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _pp]),
+    "syl_sketch_reads_packed2": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _pp]),
+    "syl_pack2": (_i, [_vp, _u64, _vp, _i]),
+    "syl_pack_threads": (_i, []),
     "syl_sample_upload": (_i, [_vp, _i, _vp, _vp, _u64, _i, _u64, _pp]),
     "syl_sample_size": (_u64, [_vp]),
     "syl_sample_mean_read_length": (_d, [_vp]),

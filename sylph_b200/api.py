@@ -102,13 +102,18 @@ class Context:
 
     # ---- (1) seeding -------------------------------------------------------------------------
     def extract_markers_batch(self, bases, rec_off, k=31, c=200, sem=SEM_AVX2, with_pos=False, cap=None,
-                              out=None):
+                              out=None, packed_bases=None):
         """Batched extract_markers / extract_markers_positions (src/sketch.rs:53-93).
         Returns a numpy structured array (hash, rec, pos) in unspecified order, or — when `out`
         is a torch CUDA tensor of >= cap*16 bytes — the survivor count (survivors stay on device)."""
         _CTX_STREAM[0] = self._stream
         L = _lib.lib()
-        mem_b, pb, nb, kb = _arg(bases, np.uint8)
+        fn = L.syl_seed_batch
+        if packed_bases is not None:   # `bases` = 2-bit words (see pack2)
+            mem_b, pb, nw, kb = _arg(bases, np.uint32)
+            nb, fn = int(packed_bases), L.syl_seed_batch_packed2
+        else:
+            mem_b, pb, nb, kb = _arg(bases, np.uint8)
         mem_o, po, no, ko = _arg(rec_off, np.uint64)
         if mem_b != mem_o:
             raise ValueError("bases and rec_off must live in the same memory space")
@@ -117,8 +122,8 @@ class Context:
         if out is not None:
             assert mem_b == _lib.MEM_DEVICE and _is_torch(out)
             cap = out.numel() * out.element_size() // 16
-            _lib.check(L.syl_seed_batch(self._h, mem_b, pb, nb, po, n_rec, k, c, sem, int(with_pos),
-                                        C.c_void_p(out.data_ptr()), cap, C.byref(n_out)))
+            _lib.check(fn(self._h, mem_b, pb, nb, po, n_rec, k, c, sem, int(with_pos),
+                          C.c_void_p(out.data_ptr()), cap, C.byref(n_out)))
             return n_out.value
         if cap is None:
             cap = max(1024, int(nb / c * 1.3) + 4096)
@@ -130,8 +135,7 @@ class Context:
             else:
                 hbuf = np.empty(cap, dtype=SURVIVOR_DTYPE)
                 pout = hbuf.ctypes.data_as(C.c_void_p)
-            rc = L.syl_seed_batch(self._h, mem_b, pb, nb, po, n_rec, k, c, sem, int(with_pos), pout, cap,
-                                  C.byref(n_out))
+            rc = fn(self._h, mem_b, pb, nb, po, n_rec, k, c, sem, int(with_pos), pout, cap, C.byref(n_out))
             if rc == _lib.SYL_ERR_CAPACITY:
                 cap = n_out.value + 16
                 continue
@@ -142,15 +146,24 @@ class Context:
             return hbuf[:n].copy()
 
     # ---- (2) sample sketch -------------------------------------------------------------------
-    def sketch_sequences(self, bases, rec_off, k=31, c=200, no_dedup=False, sem=SEM_AVX2):
-        """Batched body of sketch_sequences_needle (src/sketch.rs:897-959) -> Sample."""
+    def sketch_sequences(self, bases, rec_off, k=31, c=200, no_dedup=False, sem=SEM_AVX2, packed_bases=None):
+        """Batched body of sketch_sequences_needle (src/sketch.rs:897-959) -> Sample.
+        packed_bases: `bases` holds 2-bit words (see pack2) for this many bases (syl_sketch_reads_packed2)."""
         _CTX_STREAM[0] = self._stream
         L = _lib.lib()
-        mem_b, pb, nb, kb = _arg(bases, np.uint8)
         mem_o, po, no, ko = _arg(rec_off, np.uint64)
+        h = C.c_void_p()
+        if packed_bases is not None:
+            mem_b, pb, nw, kb = _arg(bases, np.uint32)
+            if nw < (packed_bases + 15) // 16:
+                raise ValueError("packed buffer too short")
+            if mem_b != mem_o:
+                raise ValueError("bases and rec_off must live in the same memory space")
+            _lib.check(L.syl_sketch_reads_packed2(self._h, mem_b, pb, int(packed_bases), po, no - 1, k, c, int(no_dedup), sem, C.byref(h)))
+            return Sample(self, h)
+        mem_b, pb, nb, kb = _arg(bases, np.uint8)
         if mem_b != mem_o:
             raise ValueError("bases and rec_off must live in the same memory space")
-        h = C.c_void_p()
         _lib.check(L.syl_sketch_reads(self._h, mem_b, pb, nb, po, no - 1, k, c, int(no_dedup), sem, C.byref(h)))
         return Sample(self, h)
 
@@ -239,6 +252,15 @@ class Context:
         """`sylph profile`: pass 1, winner table, pass 2, derep, abundances; per sample sorted by rel_abund."""
         params = params or contain_params(pseudotax=True)
         return self._pairs(_lib.lib().syl_profile, db, samples, params, cap)
+
+
+def pack2(bases, threads=0):
+    """Host packer (syl_pack2): ASCII bases (numpy uint8) -> uint32 words, 16 bases per word, base 16w+j in
+    bits [30-2j, 31-2j], exact BYTE_TO_SEQ codes (src/types.rs:50-59)."""
+    a = np.ascontiguousarray(bases, dtype=np.uint8)
+    out = np.zeros((a.size + 15) // 16, dtype=np.uint32)
+    _lib.check(_lib.lib().syl_pack2(a.ctypes.data_as(C.c_void_p), a.size, out.ctypes.data_as(C.c_void_p), int(threads)))
+    return out
 
 
 def contain_params(k=31, pseudotax=False, **kw):

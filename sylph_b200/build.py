@@ -15,11 +15,24 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libsylph_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "sylph_b200.h")
-SOURCES = ["api.cu", "seed.cu", "seed_k31_sv.cu", "seed_k31_ev.cu", "seed_k21_sv.cu", "seed_k21_ev.cu", "sample.cu", "genome.cu", "contain.cu"]
+SOURCES = ["api.cu", "seed.cu", "seed_k31_sv.cu", "seed_k31_ev.cu", "seed_k21_sv.cu", "seed_k21_ev.cu",
+           "seedw_k31_sv.cu", "seedw_k31_ev.cu", "seedw_k21_sv.cu", "seedw_k21_ev.cu",
+           "seedw_k31_sv_p.cu", "seedw_k31_ev_p.cu", "seedw_k21_sv_p.cu", "seedw_k21_ev_p.cu",
+           "sample.cu", "genome.cu", "contain.cu", "host_pack.cpp"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
+
+
+# tuning experiments: extra -D flags and an alternative output name (SYL_BUILD_DEFS="-DSEEDW_TW=2048 -DSEEDW_MINB=4"
+# SYL_BUILD_TAG=tw2048 -> libsylph_b200_tw2048.so, objects under build_tw2048/), loaded with SYLPH_B200_LIB
+EXTRA_NVCC = os.environ.get("SYL_BUILD_DEFS", "").split()
+_TAG = os.environ.get("SYL_BUILD_TAG", "")
+if _TAG:
+    OBJ = os.path.join(HERE, "build_" + _TAG)
+    SO = os.path.join(HERE, "libsylph_b200_%s.so" % _TAG)
 
 
 def _nvcc():
@@ -34,7 +47,7 @@ def _sources():
 
 
 def _headers_mtime():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [HEADER]
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))] + [HEADER]
     return max(os.path.getmtime(h) for h in hs)
 
 
@@ -48,7 +61,7 @@ def needs_build():
     t = os.path.getmtime(SO)
     if os.path.getmtime(os.path.abspath(__file__)) > t:  # source list / flags changed
         return True
-    if any(not os.path.exists(os.path.join(OBJ, s[:-3] + ".o")) for s in _sources()):
+    if any(not os.path.exists(os.path.join(OBJ, os.path.splitext(s)[0] + ".o")) for s in _sources()):
         return True
     return _headers_mtime() > t or any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in _sources())
 
@@ -86,14 +99,17 @@ def _build_locked(force, verbose):
     hm = _headers_mtime()
     jobs, objs = [], []
     for s in _sources():
-        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, os.path.splitext(s)[0] + ".o")
         objs.append(obj)
         if force or _stale(src, obj, hm):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+            if s.endswith(".cpp"):  # host-only code (thread pool, AVX2 packer): plain g++
+                jobs.append([os.environ.get("SYL_CXX", "g++")] + CXX_FLAGS + ["-c", src, "-o", obj])
+            else:
+                jobs.append([nvcc] + NVCC_FLAGS + EXTRA_NVCC + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(lambda c: _run(c, verbose), jobs))
     tmp = SO + ".tmp.%d" % os.getpid()
-    _run([nvcc, "-shared", "-o", tmp] + objs, verbose)
+    _run([nvcc, "-shared", "-o", tmp] + objs + ["-lpthread"], verbose)
     os.replace(tmp, SO)  # atomic: a process that already mapped the old file keeps it
     return SO
 

@@ -58,10 +58,6 @@ void hblock_free(syl_ctx *ctx, void *p) {
 }
 void set_error(const std::string &msg) { g_last_error = msg; }
 
-int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
-                uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
-                uint64_t cap, uint64_t *n_out);
-
 // Stage caller memory on the device if needed. For SYL_MEM_DEVICE the pointer is used as is.
 template <typename T>
 struct Staged {
@@ -122,8 +118,8 @@ int syl_ctx_create(int device, void *stream, syl_ctx **out) {
         uint64_t thresh = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
-    if (cudaMalloc((void **)&ctx->d_counters, 16 * sizeof(uint64_t)) != cudaSuccess ||
-        cudaMallocHost((void **)&ctx->h_counters, 16 * sizeof(uint64_t)) != cudaSuccess) {
+    if (cudaMalloc((void **)&ctx->d_counters, 32 * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMallocHost((void **)&ctx->h_counters, 32 * sizeof(uint64_t)) != cudaSuccess) {
         set_error("ctx scratch allocation failed");
         syl_ctx_destroy(ctx);
         return SYL_ERR_OOM;
@@ -144,6 +140,7 @@ void syl_ctx_destroy(syl_ctx *ctx) {
     }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    syl::ingest_destroy(ctx);
     for (auto &b : ctx->free_blocks) cudaFree(b.first);
     ctx->free_blocks.clear();
     if (syl::tl_ctx == ctx) syl::tl_ctx = nullptr;
@@ -212,29 +209,59 @@ int syl_ctx_seed_kernel_time(syl_ctx *ctx, double *total_ms, uint64_t *launches,
     return syl_ctx_kernel_time(ctx, SYL_KERNEL_SEED, total_ms, launches, reset);
 }
 
-int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
-                   const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
-                   syl_survivor *out, uint64_t cap, uint64_t *n_out) {
-    if (!ctx || !n_out || (!bases && n_bases) || !rec_off || (!out && cap)) {
+static int seed_batch_impl(syl_ctx *ctx, int mem, const uint8_t *bases, const uint32_t *packed, uint64_t n_bases,
+                           const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
+                           syl_survivor *out, uint64_t cap, uint64_t *n_out) {
+    if (!ctx || !n_out || (!bases && !packed && n_bases) || !rec_off || (!out && cap)) {
         set_error("NULL argument");
         return SYL_ERR_ARG;
     }
     SYL_CUDA(cudaSetDevice(ctx->device));
     syl::tl_ctx = ctx;
+    *n_out = 0;
+    cudaStream_t st = ctx->stream;
     Staged<uint8_t> sb;
+    Staged<uint32_t> sp;
     Staged<uint64_t> so;
-    SYL_TRY(sb.init(ctx, mem, bases, n_bases));
+    if (packed) SYL_TRY(sp.init(ctx, mem, packed, (n_bases + 15) / 16));
+    else SYL_TRY(sb.init(ctx, mem, bases, n_bases));
     SYL_TRY(so.init(ctx, mem, rec_off, n_rec + 1));
-    if (mem == SYL_MEM_DEVICE) return seed_device(ctx, sb.p, n_bases, so.p, 0, n_rec, k, c, sem, with_pos, out, cap, n_out);
     DevBuf<syl_survivor> d_out;
-    SYL_TRY(d_out.alloc(cap, ctx->stream));
-    int rc = seed_device(ctx, sb.p, n_bases, so.p, 0, n_rec, k, c, sem, with_pos, d_out.p, cap, n_out);
-    if (rc != SYL_OK) return rc;
-    if (*n_out) {
-        SYL_CUDA(cudaMemcpyAsync(out, d_out.p, *n_out * sizeof(syl_survivor), cudaMemcpyDeviceToHost, ctx->stream));
-        SYL_CUDA(cudaStreamSynchronize(ctx->stream));
+    syl_survivor *dst = out;
+    if (mem != SYL_MEM_DEVICE) {
+        SYL_TRY(d_out.alloc(cap, st));
+        dst = d_out.p;
+    }
+    SeedJob job;
+    job.d_bases = packed ? nullptr : sb.p; job.d_packed = packed ? sp.p : nullptr; job.n_bases = n_bases;
+    job.d_rec_off = so.p; job.off_bias = 0; job.n_rec = n_rec; job.k = k; job.c = c; job.sem = sem; job.with_pos = with_pos;
+    job.d_out = dst; job.cap = cap;
+    job.d_count = reinterpret_cast<unsigned long long *>(ctx->d_counters);
+    job.d_pend_count = job.d_count + 1;
+    SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint64_t), st));
+    SYL_TRY(seed_enqueue(ctx, job));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaStreamSynchronize(st));
+    *n_out = ctx->h_counters[0];
+    if (*n_out > cap) { set_error("survivor buffer too small"); return SYL_ERR_CAPACITY; }
+    if (mem != SYL_MEM_DEVICE && *n_out) {
+        SYL_CUDA(cudaMemcpyAsync(out, d_out.p, *n_out * sizeof(syl_survivor), cudaMemcpyDeviceToHost, st));
+        SYL_CUDA(cudaStreamSynchronize(st));
     }
     return SYL_OK;
+}
+
+int syl_seed_batch(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
+                   const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
+                   syl_survivor *out, uint64_t cap, uint64_t *n_out) {
+    return seed_batch_impl(ctx, mem, bases, nullptr, n_bases, rec_off, n_rec, k, c, sem, with_pos, out, cap, n_out);
+}
+
+int syl_seed_batch_packed2(syl_ctx *ctx, int mem, const uint32_t *packed, uint64_t n_bases,
+                           const uint64_t *rec_off, uint64_t n_rec, int k, uint64_t c, int sem, int with_pos,
+                           syl_survivor *out, uint64_t cap, uint64_t *n_out) {
+    if (!packed && n_bases) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    return seed_batch_impl(ctx, mem, nullptr, packed, n_bases, rec_off, n_rec, k, c, sem, with_pos, out, cap, n_out);
 }
 
 }  // extern "C"

@@ -51,7 +51,7 @@ struct syl_ctx {
     int num_sms = 148;
     uint64_t launches = 0;
     // small persistent scratch: device counters + pinned host mirror
-    uint64_t *d_counters = nullptr;  // 16 x u64
+    uint64_t *d_counters = nullptr;  // 32 x u64
     uint64_t *h_counters = nullptr;  // pinned
     // optional per-kernel timing (syl_ctx_enable_timing): every timed launch is bracketed by a pair of
     // CUDA events from a pool; the pairs are resolved (cudaEventElapsedTime) when the totals are read
@@ -62,7 +62,8 @@ struct syl_ctx {
     double kernel_ms[SYL_KERNEL_COUNT] = {};
     uint64_t kernel_launches[SYL_KERNEL_COUNT] = {};
     uint64_t seed_bases = 0;
-    // double-buffered H2D staging for host-memory inputs (lazily allocated, reused across calls)
+    void *ingest = nullptr;  // HostIngest (sample.cu): packer pool + pinned staging ring of the host-memory read path
+    // double-buffered H2D staging for host-memory ASCII inputs (SYL_HOST_INGEST=ascii; lazily allocated, reused across calls)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     uint8_t *stage_b[2] = {nullptr, nullptr};
@@ -148,6 +149,31 @@ static_assert(sizeof(EventRec) == 32, "EventRec is one 32-byte sector");
 constexpr uint64_t NO_PAIR = 1ull;
 constexpr uint64_t EV_PENDING = 1ull << 63;
 
+// One batch for the seeding kernel (seed.cu: seed_enqueue).  Exactly one of d_bases (ASCII) / d_packed
+// (2-bit words: base 16w+j of the batch in bits [30-2j, 31-2j] of word w) is set.
+struct SeedJob {
+    const uint8_t *d_bases = nullptr;
+    const uint32_t *d_packed = nullptr;
+    uint64_t n_bases = 0;
+    const uint64_t *d_rec_off = nullptr;  // d_rec_off[i] - off_bias = start of record i inside the batch
+    uint64_t off_bias = 0, n_rec = 0;
+    int k = 31;
+    uint64_t c = 200;
+    int sem = SYL_SEM_AVX2, with_pos = 0;
+    void *d_out = nullptr;                // syl_survivor[cap], or EventRec[cap] when emit_events
+    uint64_t cap = 0;
+    int emit_events = 0;
+    uint64_t rec_base = 0;                // index of the batch's first read (events)
+    int no_dedup = 0;
+    uint32_t *d_pend = nullptr;           // indices of events whose pair keys are still missing
+    uint32_t *d_bucket_cnt = nullptr;     // post-pass bucket histogram (events)
+    uint64_t Mb = 0;
+    uint32_t nbk = 0;
+    unsigned long long *d_count = nullptr, *d_pend_count = nullptr;  // running device counters
+};
+int seed_enqueue(syl_ctx *ctx, const SeedJob &job);
+void ingest_destroy(syl_ctx *ctx);
+
 // stream-ordered temporary device buffer (cudaMallocAsync from the device's default pool)
 template <typename T>
 struct DevBuf {
@@ -201,6 +227,16 @@ struct DevBuf {
         n = 0;
     }
 };
+
+// 16 two-bit fields (the even ones of 32, MSB-first) of x -> 32 bits
+__device__ __forceinline__ uint32_t even_fields(uint64_t x) {
+    x &= 0xCCCCCCCCCCCCCCCCull;
+    x = (x | (x << 2)) & 0xF0F0F0F0F0F0F0F0ull;
+    x = (x | (x << 4)) & 0xFF00FF00FF00FF00ull;
+    x = (x | (x << 8)) & 0xFFFF0000FFFF0000ull;
+    x = (x | (x << 16)) & 0xFFFFFFFF00000000ull;
+    return (uint32_t)(x >> 32);
+}
 
 // ---- the reference's arithmetic, device side ------------------------------------------------
 

@@ -1,0 +1,184 @@
+// host_pack.cpp — exact BYTE_TO_SEQ (src/types.rs:50-59) 2-bit packing on the host + the worker pool
+// that feeds the pinned staging ring of syl_sketch_reads (host-memory inputs).  Compiled by g++ (no
+// CUDA in here); AVX2 path selected at run time, scalar table path otherwise.
+#include "host_pack.hpp"
+
+#include <immintrin.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace syl {
+
+namespace {
+
+struct Lut {
+    uint8_t t[256];
+    Lut() {
+        memset(t, 0, sizeof(t));
+        t[1] = 1; t[2] = 2; t[3] = 3;
+        t['C'] = t['c'] = 1;
+        t['G'] = t['g'] = 2;
+        t['T'] = t['t'] = t['U'] = t['u'] = 3;
+    }
+};
+const Lut g_lut;
+
+inline uint32_t pack16_scalar(const uint8_t *p) {
+    uint32_t w = 0;
+    for (int j = 0; j < 16; j++) w = (w << 2) | g_lut.t[p[j]];
+    return w;
+}
+
+void pack2_scalar(const uint8_t *bases, uint64_t n, uint32_t *words) {
+    const uint64_t full = n / 16;
+    for (uint64_t w = 0; w < full; w++) words[w] = pack16_scalar(bases + 16 * w);
+    if (n % 16) {
+        uint8_t tmp[16] = {0};
+        memcpy(tmp, bases + 16 * full, n % 16);
+        words[full] = pack16_scalar(tmp);
+    }
+}
+
+// 32 bases -> 2 words.  Byte class by two nibble tables ANDed together: bit a = {C,c}, b = {0x01},
+// c = {G,g}, d = {0x02}, e = {T,t,U,u}, f = {0x03}; code bit 0 = a|b|e|f, code bit 1 = c|d|e|f.
+__attribute__((target("avx2"))) void pack2_avx2(const uint8_t *bases, uint64_t n, uint32_t *words) {
+    const __m256i lo_tab = _mm256_setr_epi8(0, 0x02, 0x08, 0x21, 0x10, 0x10, 0, 0x04, 0, 0, 0, 0, 0, 0, 0, 0,
+                                            0, 0x02, 0x08, 0x21, 0x10, 0x10, 0, 0x04, 0, 0, 0, 0, 0, 0, 0, 0);
+    // hi nibble 0: b,d,f ; 4,6: a,c ; 5,7: e
+    const __m256i hi_tab = _mm256_setr_epi8(0x2A, 0, 0, 0, 0x05, 0x10, 0x05, 0x10, 0, 0, 0, 0, 0, 0, 0, 0,
+                                            0x2A, 0, 0, 0, 0x05, 0x10, 0x05, 0x10, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i nib = _mm256_set1_epi8(0x0F);
+    const __m256i m_b0 = _mm256_set1_epi8(0x33);  // a|b|e|f  (0x01|0x02|0x10|0x20)
+    const __m256i m_b1 = _mm256_set1_epi8(0x3C);  // c|d|e|f  (0x04|0x08|0x10|0x20)
+    const __m256i zero = _mm256_setzero_si256();
+    const __m256i one = _mm256_set1_epi8(1), two = _mm256_set1_epi8(2);
+    const __m256i w41 = _mm256_set1_epi16(0x0104);      // bytes (4, 1): c0*4 + c1
+    const __m256i w161 = _mm256_set1_epi32(0x00010010);  // words (16, 1): p0*16 + p1
+    const __m256i gather = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                            12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const uint64_t full = n / 32;
+    for (uint64_t i = 0; i < full; i++) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(bases + 32 * i));
+        const __m256i lo = _mm256_and_si256(v, nib);
+        const __m256i hi = _mm256_and_si256(_mm256_srli_epi16(v, 4), nib);
+        const __m256i m = _mm256_and_si256(_mm256_shuffle_epi8(lo_tab, lo), _mm256_shuffle_epi8(hi_tab, hi));
+        const __m256i b0 = _mm256_andnot_si256(_mm256_cmpeq_epi8(_mm256_and_si256(m, m_b0), zero), one);
+        const __m256i b1 = _mm256_andnot_si256(_mm256_cmpeq_epi8(_mm256_and_si256(m, m_b1), zero), two);
+        const __m256i code = _mm256_or_si256(b0, b1);                   // one 2-bit code per byte
+        const __m256i p2 = _mm256_maddubs_epi16(code, w41);            // 16-bit lanes: c0*4 + c1
+        const __m256i p4 = _mm256_madd_epi16(p2, w161);                // 32-bit lanes: 4 bases, MSB-first, in the low byte
+        const __m256i g = _mm256_shuffle_epi8(p4, gather);            // low dword of each 128-bit half = one word
+        words[2 * i] = (uint32_t)_mm256_extract_epi32(g, 0);
+        words[2 * i + 1] = (uint32_t)_mm256_extract_epi32(g, 4);
+    }
+    if (n % 32) pack2_scalar(bases + 32 * full, n % 32, words + 2 * full);
+}
+
+bool have_avx2() {
+    static const bool v = __builtin_cpu_supports("avx2") && getenv("SYL_PACK_SCALAR") == nullptr;
+    return v;
+}
+
+}  // namespace
+
+void pack2_range(const uint8_t *bases, uint64_t n_bases, uint32_t *words) {
+    if (have_avx2()) pack2_avx2(bases, n_bases, words);
+    else pack2_scalar(bases, n_bases, words);
+}
+
+int default_pack_threads() {
+    if (const char *e = getenv("SYL_PACK_THREADS")) {
+        const int v = atoi(e);
+        if (v > 0) return std::min(v, 512);
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    if (!hc) hc = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): share the host's cores
+        const int lw = atoi(e);
+        if (lw > 1) hc = std::max(1u, hc / (unsigned)lw);
+    }
+    // the packer is memory-bound well before all cores of a big host are busy
+    return (int)std::max(1u, std::min(hc, 64u));
+}
+
+PackPool::PackPool(int n_threads) {
+    for (int i = 0; i < std::max(1, n_threads); i++) workers_.emplace_back([this]() { worker(); });
+}
+
+PackPool::~PackPool() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+}
+
+void PackPool::start(const std::vector<PackItem> *items, std::vector<std::atomic<uint32_t>> *remaining,
+                     std::atomic<int64_t> *gate_chunk) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        items_ = items;
+        remaining_ = remaining;
+        gate_ = gate_chunk;
+        next_.store(0, std::memory_order_relaxed);
+        active_.store((int)workers_.size(), std::memory_order_relaxed);
+        generation_++;
+    }
+    cv_.notify_all();
+}
+
+static inline void cpu_relax() {
+#if defined(__x86_64__)
+    _mm_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
+void PackPool::worker() {
+    uint64_t seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&]() { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+        }
+        const std::vector<PackItem> &items = *items_;
+        for (;;) {
+            const uint64_t i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= items.size()) break;
+            const PackItem &it = items[i];
+            int spins = 0;
+            while (gate_->load(std::memory_order_acquire) < (int64_t)it.chunk) {  // staging buffer not free yet
+                if (++spins > 64) { std::this_thread::yield(); spins = 0; } else cpu_relax();
+            }
+            if (it.src) {
+                pack2_range(it.src, it.n, it.dst);
+            } else {
+                for (uint64_t j = 0; j < it.off_n; j++) it.off_dst[j] = (uint32_t)(it.off_src[j] - it.off_base);
+            }
+            (*remaining_)[it.chunk].fetch_sub(1, std::memory_order_release);
+        }
+        active_.fetch_sub(1, std::memory_order_release);
+    }
+}
+
+void PackPool::wait_chunk(uint32_t c) {
+    int spins = 0;
+    while ((*remaining_)[c].load(std::memory_order_acquire) != 0) {
+        if (++spins > 256) { std::this_thread::yield(); spins = 0; } else cpu_relax();
+    }
+}
+
+void PackPool::finish() {
+    int spins = 0;
+    while (active_.load(std::memory_order_acquire) != 0) {
+        if (++spins > 256) { std::this_thread::yield(); spins = 0; } else cpu_relax();
+    }
+}
+
+}  // namespace syl

@@ -18,31 +18,24 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
-
-namespace syl {
-
-int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
-                   uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
-                   uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
-                   uint32_t *d_pend, uint64_t *n_pend, uint32_t *d_bucket_cnt, uint64_t Mb, uint32_t nbk);
-
-}  // namespace syl
+#include "host_pack.hpp"
 
 namespace syl {
 
 // pair_kmer_single (src/sketch.rs:624-656): four 16-base keys sampled at even/odd offsets from
 // the read start and from the middle.  len > 400 (src/sketch.rs:923) or len < 66 (:627) => None.
-// k_seed computes the keys itself from its packed tile whenever the read's first 32 bases and the
-// 32 bases from its middle are inside the tile; k_events_fix below handles the reads cut by a tile
-// edge (about 1 % of 150 bp reads).  One thread per such event: the 32 bytes a key pair is drawn
-// from are fetched as nine aligned 32-bit words and realigned with funnel shifts; even / odd bytes
-// are separated with PRMT and mapped through four pre-shifted copies of the exact BYTE_TO_SEQ
-// table in shared memory.
+// The seeding kernel computes the keys itself from its packed tile whenever the read's first 32 bases
+// and the 32 bases from its middle are inside the tile; k_events_fix below handles the reads cut by a
+// tile edge.  One thread per such event.  ASCII input: the 32 bytes a key pair is drawn from are
+// fetched as nine aligned 32-bit words and realigned with funnel shifts; even / odd bytes are
+// separated with PRMT and mapped through four pre-shifted copies of the exact BYTE_TO_SEQ table in
+// shared memory.  2-bit input: three words, one funnel extract, even / odd fields compressed.
 constexpr int EV_THREADS = 128;
 
 __device__ __forceinline__ void load32_unaligned(const uint8_t *p, uint32_t x[8]) {
@@ -70,34 +63,63 @@ __device__ __forceinline__ uint32_t pack16(const uint32_t x[8], uint32_t sel, co
     return out;
 }
 
+// 32 bases starting at base `a` of a 2-bit packed buffer of n_words words -> 64 bits, MSB-first
+__device__ __forceinline__ uint64_t packed64(const uint32_t *__restrict__ packed, uint64_t n_words, uint64_t a) {
+    const uint64_t w = a >> 4;
+    const uint32_t sh = (uint32_t)(a & 15u) * 2u;
+    const uint32_t v0 = __ldg(packed + w), v1 = w + 1 < n_words ? __ldg(packed + w + 1) : 0u,
+                   v2 = w + 2 < n_words ? __ldg(packed + w + 2) : 0u;
+    return ((uint64_t)__funnelshift_l(v1, v0, sh) << 32) | __funnelshift_l(v2, v1, sh);
+}
+
+// events pend[*p_begin .. *p_end) (indices into ev) belong to the batch (bases | packed, rec_off, off_bias)
+template <bool PACKED>
 __global__ void __launch_bounds__(EV_THREADS)
-k_events_fix(EventRec *__restrict__ ev, const uint32_t *__restrict__ pend, const unsigned long long *__restrict__ n_pend,
-             const uint8_t *__restrict__ bases, const uint64_t *__restrict__ rec_off, uint64_t off_bias, uint64_t rec_base) {
+k_events_fix(EventRec *__restrict__ ev, const uint32_t *__restrict__ pend, const unsigned long long *__restrict__ p_begin,
+             const unsigned long long *__restrict__ p_end, uint64_t ev_cap, const uint8_t *__restrict__ bases,
+             const uint32_t *__restrict__ packed, uint64_t n_words, const uint64_t *__restrict__ rec_off, uint64_t off_bias,
+             uint64_t rec_base) {
     __shared__ uint8_t lut[4][256];
-    for (int i = threadIdx.x; i < 256; i += EV_THREADS) {
-        const uint32_t code = byte_to_seq((uint32_t)i);
-        lut[0][i] = (uint8_t)(code << 6);
-        lut[1][i] = (uint8_t)(code << 4);
-        lut[2][i] = (uint8_t)(code << 2);
-        lut[3][i] = (uint8_t)code;
+    if (!PACKED) {
+        for (int i = threadIdx.x; i < 256; i += EV_THREADS) {
+            const uint32_t code = byte_to_seq((uint32_t)i);
+            lut[0][i] = (uint8_t)(code << 6);
+            lut[1][i] = (uint8_t)(code << 4);
+            lut[2][i] = (uint8_t)(code << 2);
+            lut[3][i] = (uint8_t)code;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const uint64_t n = *n_pend;
-    for (uint64_t i = (uint64_t)blockIdx.x * EV_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * EV_THREADS) {
-        EventRec *e = ev + pend[i];
+    const uint64_t i0 = *p_begin, i1 = *p_end;
+    for (uint64_t i = i0 + (uint64_t)blockIdx.x * EV_THREADS + threadIdx.x; i < i1; i += (uint64_t)gridDim.x * EV_THREADS) {
+        const uint32_t ei = pend[i];
+        if (ei >= ev_cap) continue;
+        EventRec *e = ev + ei;
         const uint64_t rf = e->recflag & ~EV_PENDING;
         const uint64_t rec = (rf >> 1) - rec_base;
         const uint64_t a = rec_off[rec] - off_bias;
         const uint64_t L = rec_off[rec + 1] - off_bias - a;
-        uint32_t x[8];
-        load32_unaligned(bases + a, x);
-        const uint32_t f = pack16(x, 0x6420, lut), g = pack16(x, 0x7531, lut);
-        load32_unaligned(bases + a + L / 2, x);
-        const uint32_t r = pack16(x, 0x6420, lut), t = pack16(x, 0x7531, lut);
+        uint32_t f, g, r, t;
+        if (!PACKED) {
+            uint32_t x[8];
+            load32_unaligned(bases + a, x);
+            f = pack16(x, 0x6420, lut); g = pack16(x, 0x7531, lut);
+            load32_unaligned(bases + a + L / 2, x);
+            r = pack16(x, 0x6420, lut); t = pack16(x, 0x7531, lut);
+        } else {
+            const uint64_t x = packed64(packed, n_words, a), y = packed64(packed, n_words, a + L / 2);
+            f = even_fields(x); g = even_fields(x << 2);
+            r = even_fields(y); t = even_fields(y << 2);
+        }
         e->recflag = rf;
         e->p0 = ((uint64_t)f << 32) | r;  // doublepairs.0 = [kmer_f, kmer_r]
         e->p1 = ((uint64_t)g << 32) | t;  // doublepairs.1 = [kmer_g, kmer_t]
     }
+}
+
+__global__ void k_off32_to_64(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 
 __global__ void k_unpack_events(const EventRec *__restrict__ ev, uint64_t n, uint64_t *__restrict__ hash,
@@ -262,20 +284,23 @@ __global__ void k_scan_add(uint32_t *__restrict__ out, uint64_t n, const uint32_
     if (i == n - 1) out[n] = block_off[gridDim.x];  // total
 }
 
-__global__ void k_scatter_events(const EventRec *__restrict__ ev, uint64_t n,
+// n events (device-side count, clamped to the array capacity) -> bucket order
+__global__ void k_scatter_events(const EventRec *__restrict__ ev, const unsigned long long *__restrict__ d_n, uint64_t ev_cap,
                                  uint64_t Mb, uint32_t nbk, const uint32_t *__restrict__ boff,
                                  uint32_t *__restrict__ cursor, EventRec *__restrict__ part) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
-    const uint4 lo = __ldcs(src), hi = __ldcs(src + 1);  // read once: keep L2 for the scattered writes
-    const uint64_t h = ((uint64_t)lo.y << 32) | lo.x;
-    uint32_t b = (uint32_t)__umul64hi(h, Mb);
-    if (b >= nbk) b = nbk - 1;
-    const uint32_t pos = boff[b] + atomicAdd(&cursor[b], 1u);
-    uint4 *dst = reinterpret_cast<uint4 *>(part + pos);
-    dst[0] = lo;
-    dst[1] = hi;
+    const uint64_t n = *d_n < ev_cap ? *d_n : ev_cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
+        const uint4 lo = __ldcs(src), hi = __ldcs(src + 1);  // read once: keep L2 for the scattered writes
+        const uint64_t h = ((uint64_t)lo.y << 32) | lo.x;
+        uint32_t b = (uint32_t)__umul64hi(h, Mb);
+        if (b >= nbk) b = nbk - 1;
+        const uint64_t pos = (uint64_t)boff[b] + atomicAdd(&cursor[b], 1u);
+        if (pos >= ev_cap) continue;  // only after an overflow (the whole sample is redone then)
+        uint4 *dst = reinterpret_cast<uint4 *>(part + pos);
+        dst[0] = lo;
+        dst[1] = hi;
+    }
 }
 
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint64_t v) {
@@ -334,7 +359,7 @@ struct GroupSmem {
 
 __global__ void __launch_bounds__(GRP_THREADS)
 k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ boff, const uint32_t *__restrict__ g_bf,
-              const uint32_t *__restrict__ g_be, uint32_t cap, uint64_t Mb, uint32_t nbk,
+              const uint32_t *__restrict__ g_be, uint32_t cap, uint32_t ev_cap, uint64_t Mb, uint32_t nbk,
               int no_dedup, uint64_t *__restrict__ st_hash, uint32_t *__restrict__ st_cnt,
               uint32_t *__restrict__ g_nuniq, uint32_t *__restrict__ g_e0, uint32_t *__restrict__ g_n,
               uint8_t *__restrict__ g_fallback, unsigned long long *__restrict__ n_dup) {
@@ -353,7 +378,8 @@ k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ bo
     }
     for (int i = tid; i < GRP_SLOTS; i += GRP_THREADS) { S.ht[i] = 0xFFFFFFFFFFFFFFFFull; S.scnt[i] = 0; }
     __syncthreads();
-    const uint32_t e0 = S.e0, n = S.e1 - S.e0, bf = S.bf;
+    const uint32_t e0 = S.e0, bf = S.bf;
+    const uint32_t n = S.e1 <= ev_cap ? S.e1 - S.e0 : 0u;  // past the capacity only after an overflow (sample is redone)
     if (tid == 0) { g_e0[g] = e0; g_n[g] = n; g_nuniq[g] = 0; g_fallback[g] = 0; }
     if (n == 0) return;
     if (n > cap) { if (tid == 0) g_fallback[g] = 1; return; }
@@ -669,24 +695,30 @@ static inline int bits_for(uint64_t maxval) {
 }
 
 // Accumulates events over one or more seeding batches, then finishes into a syl_sample.
+// Nothing in begin() / add() synchronises with the host: the event array is sized up front from the
+// expected number of survivors, the seeding kernel appends at a running device counter, and every
+// post-pass kernel reads the event count from device memory with grids sized for the capacity.  The ONE
+// host synchronisation of a sketch is in finish(); if the events did not fit (homopolymer reads at tiny c)
+// finish() reports the true count and the caller redoes the sample with that capacity.
 struct SampleBuilder {
     syl_ctx *ctx;
     int k;
     uint64_t c;
     int no_dedup, sem;
-    uint64_t n_reads = 0, n_bases = 0, n_events = 0, cap = 0;
-    DevBuf<EventRec> b_ev;  // event array (a scratch block of the ctx cache)
-    EventRec *ev = nullptr;
+    uint64_t n_reads = 0, n_bases = 0, cap = 0;
+    DevBuf<EventRec> b_ev;   // event array (a scratch block of the ctx cache)
+    DevBuf<uint32_t> b_pend; // indices of events whose pair keys are filled in by k_events_fix
     // Post-pass buckets: fixed before the first batch from the expected number of events, so that
-    // k_seed can fill the bucket histogram while it flushes the events.
+    // the seeding kernel can fill the bucket histogram while it flushes the events.
     uint64_t expect_bases = 0, expect_reads = 0;
     uint32_t nbk = 0;
     uint64_t Mb = 0;
     DevBuf<uint32_t> cnt;
-    bool hist_valid = true;  // false after a capacity retry (partial counts of the failed attempt)
+    // ctx->d_counters slots: [0] events, [1] pending events, [2] duplicates removed, [3] pending snapshot
+    unsigned long long *d_count() const { return reinterpret_cast<unsigned long long *>(ctx->d_counters); }
 
-    int plan_buckets() {
-        if (nbk) return SYL_OK;
+    int begin(uint64_t cap_override) {
+        cudaStream_t st = ctx->stream;
         const uint64_t win = expect_bases > expect_reads * (uint64_t)(k - 1) ? expect_bases - expect_reads * (uint64_t)(k - 1) : 0;
         const uint64_t n_exp = win / c;
         nbk = 4096;
@@ -694,52 +726,38 @@ struct SampleBuilder {
         const uint64_t thr = fmh_threshold(c);
         unsigned __int128 mb = ((unsigned __int128)nbk << 64) / ((unsigned __int128)thr + 1);
         Mb = mb > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)mb;
-        SYL_TRY(cnt.alloc(nbk, ctx->stream));
-        SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, ctx->stream));
+        SYL_TRY(cnt.alloc(nbk, st));
+        SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, st));
+        cap = expect_bases / c + expect_bases / (4 * c) + 65536;
+        if (cap > expect_bases) cap = expect_bases + 16;
+        if (cap_override) cap = cap_override;
+        if (cap >= 0xFFFFFFFEull) { set_error("more than 2^32-2 survivor events in one sample"); return SYL_ERR_ARG; }
+        SYL_TRY(b_ev.alloc(cap, st));
+        SYL_TRY(b_pend.alloc(cap, st));
+        SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint64_t), st));
         return SYL_OK;
     }
 
-    int reserve(uint64_t need) {
-        if (need <= cap) return SYL_OK;
-        const uint64_t ncap = std::max<uint64_t>(need, cap * 2);
-        cudaStream_t st = ctx->stream;
-        DevBuf<EventRec> ne;
-        SYL_TRY(ne.alloc(ncap, st));
-        if (n_events) SYL_CUDA(cudaMemcpyAsync(ne.p, ev, n_events * sizeof(EventRec), cudaMemcpyDeviceToDevice, st));
-        b_ev.swap(ne);  // the old block goes back to the cache
-        ev = b_ev.p;
-        cap = ncap;
-        return SYL_OK;
-    }
-
-    // one batch of reads, device resident; read indices continue from the previous batch.
-    // k_seed appends the batch's events (hash, read, pair keys) straight to the event array.
-    int add(const uint8_t *d_bases, uint64_t nb, const uint64_t *d_off, uint64_t off_bias, uint64_t nr) {
+    // one batch of reads, device resident (ASCII bytes or 2-bit words); read indices continue from the
+    // previous batch.  The seeding kernel appends the batch's events (hash, read, pair keys) to the event array.
+    int add(const uint8_t *d_bases, const uint32_t *d_packed, uint64_t nb, const uint64_t *d_off, uint64_t off_bias, uint64_t nr) {
         cudaStream_t st = ctx->stream;
         if (nr == 0) return SYL_OK;
-        uint64_t scap = nb / c + nb / (4 * c) + 65536;
-        if (scap > nb) scap = nb + 16;
-        uint64_t n = 0, npend = 0;
-        DevBuf<uint32_t> pend;
-        SYL_TRY(plan_buckets());
-        for (;;) {
-            if (scap >= 0xFFFFFFFFull) { set_error("more than 2^32-2 survivor events in one batch"); return SYL_ERR_ARG; }
-            SYL_TRY(reserve(n_events + scap));
-            SYL_TRY(pend.alloc(scap, st));
-            int rc = seed_device_ex(ctx, d_bases, nb, d_off, off_bias, nr, k, c, sem, /*with_pos=*/0, ev + n_events, scap, &n,
-                                    /*emit_events=*/1, n_reads, no_dedup, pend.p, &npend, cnt.p, Mb, nbk);
-            if (rc == SYL_ERR_CAPACITY) { scap = n + 16; hist_valid = false; continue; }
-            if (rc != SYL_OK) return rc;
-            break;
-        }
-        if (npend) {
-            const unsigned grid = (unsigned)std::min<uint64_t>(nblk(npend, EV_THREADS), 4096);
-            k_events_fix<<<grid, EV_THREADS, 0, st>>>(ev + n_events, pend.p, reinterpret_cast<const unsigned long long *>(ctx->d_counters + 1),
-                                                     d_bases, d_off, off_bias, n_reads);
+        unsigned long long *dc = d_count();
+        SYL_CUDA(cudaMemcpyAsync(dc + 3, dc + 1, 8, cudaMemcpyDeviceToDevice, st));  // pending entries before this batch
+        SeedJob job;
+        job.d_bases = d_bases; job.d_packed = d_packed; job.n_bases = nb; job.d_rec_off = d_off; job.off_bias = off_bias;
+        job.n_rec = nr; job.k = k; job.c = c; job.sem = sem; job.with_pos = 0; job.d_out = b_ev.p; job.cap = cap;
+        job.emit_events = 1; job.rec_base = n_reads; job.no_dedup = no_dedup; job.d_pend = b_pend.p;
+        job.d_bucket_cnt = cnt.p; job.Mb = Mb; job.nbk = nbk; job.d_count = dc; job.d_pend_count = dc + 1;
+        SYL_TRY(seed_enqueue(ctx, job));
+        if (!no_dedup && nb) {  // reads cut by a tile edge: their pair keys come from global memory
+            const uint64_t n_words = (nb + 15) / 16;
+            if (d_packed) k_events_fix<true><<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b_ev.p, b_pend.p, dc + 3, dc + 1, cap, nullptr, d_packed, n_words, d_off, off_bias, n_reads);
+            else k_events_fix<false><<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b_ev.p, b_pend.p, dc + 3, dc + 1, cap, d_bases, nullptr, 0, d_off, off_bias, n_reads);
             ctx->launches++;
             SYL_CUDA(cudaGetLastError());
         }
-        n_events += n;
         n_reads += nr;
         n_bases += nb;
         return SYL_OK;
@@ -821,8 +839,10 @@ struct SampleBuilder {
         return SYL_OK;
     }
 
-    int finish(syl_sample **out) {
+    // need_cap: set when SYL_ERR_CAPACITY is returned (the true number of events)
+    int finish(syl_sample **out, uint64_t *need_cap) {
         cudaStream_t st = ctx->stream;
+        *need_cap = 0;
         syl_sample *s = new (std::nothrow) syl_sample();
         if (!s) return SYL_ERR_OOM;
         s->device = ctx->device;
@@ -831,14 +851,20 @@ struct SampleBuilder {
         s->k = k;
         s->c = c;
         s->mean_read_length = n_reads ? (double)n_bases / (double)n_reads : 0.;
-        const uint64_t N = n_events;
-        if (N == 0) { *out = s; return SYL_OK; }
-        if (N >= 0xFFFFFFFFull) { delete s; set_error("more than 2^32-2 survivor events in one sample"); return SYL_ERR_ARG; }
+        auto fail = [&](int rc) { syl_sample_free(s); return rc; };
+#define SB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? SYL_ERR_OOM : SYL_ERR_CUDA); } } while (0)
+        if (n_reads == 0 || n_bases == 0) { *out = s; return SYL_OK; }
         static const bool force_sort = []() { const char *e = getenv("SYL_SAMPLE_POSTPASS"); return e && std::string(e) == "sort"; }();
         static const uint32_t grp_cap = []() { const char *e = getenv("SYL_GROUP_CAP"); int v = e ? atoi(e) : GRP_CAP; return (uint32_t)std::min(std::max(v, 32), GRP_CAP); }();
-        auto fail = [&](int rc) { syl_sample_free(s); return rc; };
+        unsigned long long *dc = d_count();
+        EventRec *ev = b_ev.p;
         int rc;
         if (force_sort) {
+            SB_CUDA(cudaMemcpyAsync(ctx->h_counters, dc, 8, cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+            const uint64_t N = ctx->h_counters[0];
+            if (N > cap) { *need_cap = N; syl_sample_free(s); return SYL_ERR_CAPACITY; }
+            if (N == 0) { *out = s; return SYL_OK; }
             DevBuf<uint64_t> uq;
             DevBuf<uint32_t> ct;
             uint64_t U = 0, nd = 0;
@@ -847,37 +873,33 @@ struct SampleBuilder {
             k_unpack_events<<<nblk(N, 256), 256, 0, st>>>(ev, N, e_h.p, e_rf.p, e_p0.p, e_p1.p);
             ctx->launches++;
             if ((rc = dedup_sorted(e_h.p, e_rf.p, e_p0.p, e_p1.p, N, uq, ct, &U, &nd)) != SYL_OK) return fail(rc);
-            SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8));
-            SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4));
-            SYL_CUDA(cudaMemcpyAsync(s->hash, uq.p, U * 8, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaMemcpyAsync(s->count, ct.p, U * 4, cudaMemcpyDeviceToDevice, st));
-            SYL_CUDA(cudaStreamSynchronize(st));
+            if ((rc = hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8))) return fail(rc);
+            if ((rc = hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4))) return fail(rc);
+            SB_CUDA(cudaMemcpyAsync(s->hash, uq.p, U * 8, cudaMemcpyDeviceToDevice, st));
+            SB_CUDA(cudaMemcpyAsync(s->count, ct.p, U * 4, cudaMemcpyDeviceToDevice, st));
+            SB_CUDA(cudaStreamSynchronize(st));
             s->n = U;
             s->num_dup_removed = nd;
             *out = s;
             return SYL_OK;
         }
-        // ---- primary path: bucket partition + CTA-local sort/dedup (nbk, Mb, cnt: plan_buckets)
-        const uint32_t ng = (uint32_t)(N / GRP_T + 1);
-        DevBuf<uint32_t> boff, cursor, st_cnt, g_nuniq, g_e0, g_n, uoff, fsz, foff, g_bf, g_be, g_src;
-        DevBuf<uint64_t> st_hash;
+        // ---- primary path: bucket partition + CTA-local grouping / dedup (nbk, Mb, cnt: begin()).
+        // Every grid is sized for the capacity; the kernels read the event count from device memory.
+        const uint32_t ng = (uint32_t)(cap / GRP_T + 1);
+        DevBuf<uint32_t> boff, cursor, st_cnt, g_nuniq, g_e0, g_n, uoff, fsz, foff, g_bf, g_be, g_src, tmp_c;
+        DevBuf<uint64_t> st_hash, tmp_h;
         DevBuf<uint8_t> g_fb;
         DevBuf<EventRec> part;
         if ((rc = boff.alloc((uint64_t)nbk + 1, st)) || (rc = cursor.alloc(nbk, st)) ||
-            (rc = part.alloc(N, st)) || (rc = st_hash.alloc(N, st)) || (rc = st_cnt.alloc(N, st)) ||
+            (rc = part.alloc(cap, st)) || (rc = st_hash.alloc(cap, st)) || (rc = st_cnt.alloc(cap, st)) ||
+            (rc = tmp_h.alloc(cap, st)) || (rc = tmp_c.alloc(cap, st)) ||
             (rc = g_nuniq.alloc(ng, st)) || (rc = g_e0.alloc(ng, st)) || (rc = g_n.alloc(ng, st)) ||
             (rc = g_fb.alloc(ng, st)) || (rc = uoff.alloc((uint64_t)ng + 1, st)) || (rc = fsz.alloc(ng, st)) ||
             (rc = foff.alloc((uint64_t)ng + 1, st)) || (rc = g_bf.alloc(ng, st)) || (rc = g_be.alloc(ng, st)) ||
             (rc = g_src.alloc(ng, st)))
             return fail(rc);
-        unsigned long long *d_ndup = reinterpret_cast<unsigned long long *>(ctx->d_counters + 2);
-        SYL_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)nbk * 4, st));
-        SYL_CUDA(cudaMemsetAsync(d_ndup, 0, 8, st));
-        if (!hist_valid) {  // recount: a retried batch left partial counts behind
-            SYL_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbk * 4, st));
-            k_bucket_hist<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, cnt.p);
-            ctx->launches++;
-        }
+        unsigned long long *d_ndup = dc + 2;
+        SB_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)nbk * 4, st));
         {   // boff = exclusive scan of cnt (nbk >= 4096 entries): local scans, scan of block totals, add back
             const uint32_t nblk1 = nbk / 1024;
             DevBuf<uint32_t> btot, boff2;
@@ -885,55 +907,69 @@ struct SampleBuilder {
             k_scan_local<<<nblk1, 1024, 0, st>>>(cnt.p, nbk, boff.p, btot.p);
             k_scan_u32<<<1, 1024, 0, st>>>(btot.p, nblk1, boff2.p);
             k_scan_add<<<nblk1, 1024, 0, st>>>(boff.p, nbk, boff2.p);
-            ctx->launches += 2;
+            ctx->launches += 3;
         }
-        k_scatter_events<<<nblk(N, 256), 256, 0, st>>>(ev, N, Mb, nbk, boff.p, cursor.p, part.p);
-        SYL_CUDA(cudaFuncSetAttribute(k_group_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+        k_scatter_events<<<ctx->num_sms * 8, 256, 0, st>>>(ev, dc, cap, Mb, nbk, boff.p, cursor.p, part.p);
+        SB_CUDA(cudaFuncSetAttribute(k_group_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
         k_group_ranges<<<nblk(ng, 256), 256, 0, st>>>(boff.p, nbk, ng, g_bf.p, g_be.p);
         {
             KernelTimer kt(ctx, SYL_KERNEL_GROUP_DEDUP);
-            k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, Mb, nbk, no_dedup, st_hash.p, st_cnt.p,
-                                                                       g_nuniq.p, g_e0.p, g_n.p, g_fb.p, d_ndup);
+            k_group_dedup<<<ng, GRP_THREADS, sizeof(GroupSmem), st>>>(part.p, boff.p, g_bf.p, g_be.p, grp_cap, (uint32_t)cap, Mb, nbk, no_dedup,
+                                                                       st_hash.p, st_cnt.p, g_nuniq.p, g_e0.p, g_n.p, g_fb.p, d_ndup);
         }
         k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
         k_fallback_sizes<<<nblk(ng, 256), 256, 0, st>>>(g_n.p, g_fb.p, ng, fsz.p);
         k_scan_u32<<<1, 1024, 0, st>>>(fsz.p, ng, foff.p);
-        ctx->launches += 6;
-        SYL_CUDA(cudaGetLastError());
-        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 1, uoff.p + ng, 4, cudaMemcpyDeviceToHost, st));
-        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, foff.p + ng, 4, cudaMemcpyDeviceToHost, st));
-        SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 2, d_ndup, 8, cudaMemcpyDeviceToHost, st));
-        SYL_CUDA(cudaStreamSynchronize(st));
-        const uint64_t U1 = (uint32_t)ctx->h_counters[1], NF = (uint32_t)ctx->h_counters[3];
+        k_compact_uniq<<<ng, 128, 0, st>>>(st_hash.p, st_cnt.p, g_e0.p, g_nuniq.p, uoff.p, g_fb.p, g_src.p, nullptr, nullptr,
+                                            tmp_h.p, tmp_c.p);
+        ctx->launches += 7;
+        SB_CUDA(cudaGetLastError());
+        SB_CUDA(cudaMemcpyAsync(ctx->h_counters, dc, 24, cudaMemcpyDeviceToHost, st));  // events, pending, duplicates
+        SB_CUDA(cudaMemcpyAsync(ctx->h_counters + 4, uoff.p + ng, 4, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(ctx->h_counters + 5, foff.p + ng, 4, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));  // the one synchronisation of a sketch
+        const uint64_t N = ctx->h_counters[0];
+        if (N > cap) { *need_cap = N; syl_sample_free(s); return SYL_ERR_CAPACITY; }
+        const uint64_t U1 = (uint32_t)ctx->h_counters[4], NF = (uint32_t)ctx->h_counters[5];
         uint64_t ndup = ctx->h_counters[2];
         static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
-        if (dbg) fprintf(stderr, "[sample post-pass] events %llu buckets %u groups %u: in-kernel uniques %llu, events handed to the generic path %llu (%.1f %%)\n",
-                         (unsigned long long)N, nbk, ng, (unsigned long long)U1, (unsigned long long)NF, 100.0 * NF / N);
-        // fallback groups through the generic path
-        DevBuf<uint64_t> fh, f_rf, f_p0, f_p1, f_uq;
-        DevBuf<uint32_t> f_ct;
-        uint64_t U2 = 0, nd2 = 0;
-        if (NF) {
+        if (dbg) fprintf(stderr, "[sample post-pass] events %llu (cap %llu) buckets %u groups %u: in-kernel uniques %llu, events handed to the generic path %llu (%.1f %%)\n",
+                         (unsigned long long)N, (unsigned long long)cap, nbk, ng, (unsigned long long)U1, (unsigned long long)NF, N ? 100.0 * NF / N : 0.);
+        uint64_t U = U1;
+        if (NF) {  // fallback groups through the generic path (heavy-hitter k-mers, duplicate-heavy replays)
+            DevBuf<uint64_t> fh, f_rf, f_p0, f_p1, f_uq;
+            DevBuf<uint32_t> f_ct;
+            uint64_t U2 = 0, nd2 = 0;
             if ((rc = fh.alloc(NF, st)) || (rc = f_rf.alloc(NF, st)) || (rc = f_p0.alloc(NF, st)) || (rc = f_p1.alloc(NF, st)))
                 return fail(rc);
             k_gather_fallback<<<ng, 256, 0, st>>>(part.p, g_e0.p, g_n.p, g_fb.p, foff.p, fh.p, f_rf.p, f_p0.p, f_p1.p);
             ctx->launches++;
             if ((rc = dedup_sorted(fh.p, f_rf.p, f_p0.p, f_p1.p, NF, f_uq, f_ct, &U2, &nd2)) != SYL_OK) return fail(rc);
             ndup += nd2;
+            U = U1 + U2;
+            if (U2) {  // slot the generic path's pairs into their groups' positions and redo the output offsets
+                k_fallback_place<<<nblk(ng, 128), 128, 0, st>>>(g_fb.p, g_bf.p, g_be.p, ng, nbk, Mb, f_uq.p, U2, g_nuniq.p, g_src.p);
+                k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
+                k_compact_uniq<<<ng, 128, 0, st>>>(st_hash.p, st_cnt.p, g_e0.p, g_nuniq.p, uoff.p, g_fb.p, g_src.p, f_uq.p, f_ct.p,
+                                                    tmp_h.p, tmp_c.p);
+                ctx->launches += 3;
+                SB_CUDA(cudaGetLastError());
+            }
+            if ((rc = hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8))) return fail(rc);
+            if ((rc = hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4))) return fail(rc);
+            SB_CUDA(cudaMemcpyAsync(s->hash, tmp_h.p, U * 8, cudaMemcpyDeviceToDevice, st));
+            SB_CUDA(cudaMemcpyAsync(s->count, tmp_c.p, U * 4, cudaMemcpyDeviceToDevice, st));
+            SB_CUDA(cudaStreamSynchronize(st));  // f_uq / f_ct go out of scope
+        } else {
+            // exact-size result arrays; the copies are ordered on the ctx stream like every later use of the handle
+            if ((rc = hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8))) return fail(rc);
+            if ((rc = hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4))) return fail(rc);
+            if (U) {
+                SB_CUDA(cudaMemcpyAsync(s->hash, tmp_h.p, U * 8, cudaMemcpyDeviceToDevice, st));
+                SB_CUDA(cudaMemcpyAsync(s->count, tmp_c.p, U * 4, cudaMemcpyDeviceToDevice, st));
+            }
         }
-        const uint64_t U = U1 + U2;
-        SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(U, 1) * 8));
-        SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(U, 1) * 4));
-        if (U2) {  // slot the generic path's pairs into their groups' positions and redo the output offsets
-            k_fallback_place<<<nblk(ng, 128), 128, 0, st>>>(g_fb.p, g_bf.p, g_be.p, ng, nbk, Mb, f_uq.p, U2, g_nuniq.p, g_src.p);
-            k_scan_u32<<<1, 1024, 0, st>>>(g_nuniq.p, ng, uoff.p);
-            ctx->launches += 2;
-        }
-        k_compact_uniq<<<ng, 128, 0, st>>>(st_hash.p, st_cnt.p, g_e0.p, g_nuniq.p, uoff.p, g_fb.p, g_src.p, f_uq.p, f_ct.p,
-                                            s->hash, s->count);
-        ctx->launches++;
-        SYL_CUDA(cudaGetLastError());
-        SYL_CUDA(cudaStreamSynchronize(st));
+#undef SB_CUDA
         s->n = U;
         s->num_dup_removed = ndup;
         *out = s;
@@ -943,35 +979,167 @@ struct SampleBuilder {
 
 }  // namespace syl
 
-using namespace syl;
+namespace syl {
 
-extern "C" {
-
-int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
-                     const uint64_t *rec_off, uint64_t n_reads, int k, uint64_t c, int no_dedup,
-                     int sem, syl_sample **out) {
-    if (!ctx || !out || (!bases && n_bases) || !rec_off) { set_error("NULL argument"); return SYL_ERR_ARG; }
-    if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
-    *out = nullptr;
-    SYL_CUDA(cudaSetDevice(ctx->device));
-    syl::tl_ctx = ctx;
-    SampleBuilder b{ctx, k, c, no_dedup, sem};
-    b.expect_bases = n_bases;
-    b.expect_reads = n_reads;
-    cudaStream_t st = ctx->stream;
-    if (mem == SYL_MEM_DEVICE) {
-        SYL_TRY(b.add(bases, n_bases, rec_off, 0, n_reads));
-        return b.finish(out);
+// ---- host-memory ingest: pack on the host, ship 2-bit words ----------------------------------------
+// ASCII bases in (pinned or pageable) host memory are cut into chunks on record boundaries; the ctx's
+// worker pool packs chunk i+1.. into a ring of pinned staging buffers (exact BYTE_TO_SEQ codes, 16
+// bases per word; record offsets rebased to u32) while chunk i crosses PCIe and earlier chunks are
+// seeded.  4.3 bytes of H2D traffic per 16 bases instead of 16.5.
+constexpr int ING_SLOTS = 4;
+constexpr uint64_t ING_CHUNK = 32ull << 20;   // bases per chunk (multiple of 16); SYL_INGEST_CHUNK overrides (tests)
+static uint64_t ingest_chunk() {
+    if (const char *e = getenv("SYL_INGEST_CHUNK")) {
+        const long long v = atoll(e);
+        if (v >= 16) return (uint64_t)v & ~15ull;
     }
-    if (mem != SYL_MEM_HOST) { set_error("bad mem"); return SYL_ERR_ARG; }
-    // Host buffers: cut the reads into chunks of <= CHUNK bytes on record boundaries and copy
-    // chunk i+1 on the ctx copy stream while chunk i is being seeded (pinned caller memory
-    // overlaps fully).  Bases and the matching slice of rec_off are copied verbatim; kernels
-    // subtract the slice's first offset (off_bias).  Staging buffers live in the ctx.
+    return ING_CHUNK;
+}
+constexpr uint64_t ING_MAXREC = 1ull << 19;   // records per chunk
+constexpr uint64_t ING_SLICE = 256ull << 10;  // bases per work item
+constexpr uint64_t ING_OSLICE = 64ull << 10;  // offsets per work item
+
+struct HostIngest {
+    std::unique_ptr<PackPool> pool;
+    uint32_t *h_words[ING_SLOTS] = {}, *h_off[ING_SLOTS] = {};  // pinned
+    uint32_t *d_words[ING_SLOTS] = {}, *d_off32[ING_SLOTS] = {};
+    uint64_t *d_off64[ING_SLOTS] = {};
+    uint64_t cap_words = 0, cap_recs = 0;
+    cudaEvent_t ev_copied[ING_SLOTS] = {}, ev_used[ING_SLOTS] = {};
+    cudaStream_t copy_stream = nullptr;
+
+    void release_buffers() {
+        for (int i = 0; i < ING_SLOTS; i++) {
+            if (h_words[i]) cudaFreeHost(h_words[i]);
+            if (h_off[i]) cudaFreeHost(h_off[i]);
+            if (d_words[i]) cudaFree(d_words[i]);
+            if (d_off32[i]) cudaFree(d_off32[i]);
+            if (d_off64[i]) cudaFree(d_off64[i]);
+            h_words[i] = h_off[i] = d_words[i] = d_off32[i] = nullptr;
+            d_off64[i] = nullptr;
+        }
+        cap_words = cap_recs = 0;
+    }
+    int ensure(uint64_t words, uint64_t recs) {
+        if (!copy_stream) {
+            SYL_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < ING_SLOTS; i++) {
+                SYL_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+                SYL_CUDA(cudaEventCreateWithFlags(&ev_used[i], cudaEventDisableTiming));
+            }
+        }
+        if (words <= cap_words && recs <= cap_recs) return SYL_OK;
+        SYL_CUDA(cudaDeviceSynchronize());
+        const uint64_t w = std::max(words, cap_words), r = std::max(recs, cap_recs);
+        release_buffers();
+        for (int i = 0; i < ING_SLOTS; i++) {
+            SYL_CUDA(cudaMallocHost((void **)&h_words[i], (w + 16) * 4));
+            SYL_CUDA(cudaMallocHost((void **)&h_off[i], (r + 16) * 4));
+            SYL_CUDA(cudaMalloc((void **)&d_words[i], (w + 16) * 4));
+            SYL_CUDA(cudaMalloc((void **)&d_off32[i], (r + 16) * 4));
+            SYL_CUDA(cudaMalloc((void **)&d_off64[i], (r + 16) * 8));
+        }
+        cap_words = w;
+        cap_recs = r;
+        return SYL_OK;
+    }
+    ~HostIngest() {
+        pool.reset();
+        release_buffers();
+        for (int i = 0; i < ING_SLOTS; i++) {
+            if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+            if (ev_used[i]) cudaEventDestroy(ev_used[i]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+
+void ingest_destroy(syl_ctx *ctx) {
+    delete static_cast<HostIngest *>(ctx->ingest);
+    ctx->ingest = nullptr;
+}
+
+struct Chunk { uint64_t r0, r1, base, nb; };
+
+// records [r0, r1) per chunk: at most ING_CHUNK bases and ING_MAXREC records, at least one record
+static void plan_chunks(const uint64_t *rec_off, uint64_t n_reads, std::vector<Chunk> &chunks) {
+    const uint64_t CH = ingest_chunk();
+    uint64_t r0 = 0;
+    while (r0 < n_reads) {
+        const uint64_t base = rec_off[r0];
+        uint64_t lo = r0 + 1, hi = std::min(n_reads, r0 + ING_MAXREC);
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (rec_off[mid] - base <= CH) lo = mid; else hi = mid - 1;
+        }
+        chunks.push_back({r0, lo, base, rec_off[lo] - base});
+        r0 = lo;
+    }
+}
+
+// host ASCII -> packed chunks -> builder
+static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases, const uint64_t *rec_off, uint64_t n_reads) {
+    if (!ctx->ingest) ctx->ingest = new HostIngest();
+    HostIngest &I = *static_cast<HostIngest *>(ctx->ingest);
+    if (!I.pool) I.pool.reset(new PackPool(default_pack_threads()));
+    std::vector<Chunk> chunks;
+    plan_chunks(rec_off, n_reads, chunks);
+    uint64_t max_words = 0, max_recs = 0;
+    for (const Chunk &c : chunks) {
+        if (c.nb >= 0xFFFFFFF0ull) { set_error("a single record of 4 GB or more"); return SYL_ERR_ARG; }
+        max_words = std::max(max_words, (c.nb + 15) / 16);
+        max_recs = std::max(max_recs, c.r1 - c.r0 + 1);
+    }
+    SYL_TRY(I.ensure(std::max<uint64_t>(max_words, ING_CHUNK / 16), std::max<uint64_t>(max_recs, 65536)));
+    cudaStream_t st = ctx->stream, cs = I.copy_stream;
+    std::vector<PackItem> items;
+    std::vector<std::atomic<uint32_t>> remaining(chunks.size());
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const Chunk &c = chunks[ci];
+        const int slot = (int)(ci % ING_SLOTS);
+        uint32_t n_items = 0;
+        for (uint64_t o = 0; o < c.nb; o += ING_SLICE, n_items++)
+            items.push_back({bases + c.base + o, std::min(ING_SLICE, c.nb - o), I.h_words[slot] + o / 16, nullptr, 0, 0, nullptr, (uint32_t)ci});
+        const uint64_t no = c.r1 - c.r0 + 1;
+        for (uint64_t o = 0; o < no; o += ING_OSLICE, n_items++)
+            items.push_back({nullptr, 0, nullptr, rec_off + c.r0 + o, c.base, std::min(ING_OSLICE, no - o), I.h_off[slot] + o, (uint32_t)ci});
+        remaining[ci].store(n_items, std::memory_order_relaxed);
+    }
+    std::atomic<int64_t> gate(ING_SLOTS - 1);
+    I.pool->start(&items, &remaining, &gate);
+    int rc = SYL_OK;
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const Chunk &c = chunks[ci];
+        const int slot = (int)(ci % ING_SLOTS);
+        const uint64_t nw = (c.nb + 15) / 16, no = c.r1 - c.r0 + 1;
+        I.pool->wait_chunk((uint32_t)ci);
+        cudaStreamWaitEvent(cs, I.ev_used[slot], 0);  // the seeding of the previous chunk in this slot is done
+        if (cudaMemcpyAsync(I.d_words[slot], I.h_words[slot], nw * 4, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+            cudaMemcpyAsync(I.d_off32[slot], I.h_off[slot], no * 4, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
+            rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
+        }
+        cudaEventRecord(I.ev_copied[slot], cs);
+        cudaStreamWaitEvent(st, I.ev_copied[slot], 0);
+        k_off32_to_64<<<nblk(no, 256), 256, 0, st>>>(I.d_off32[slot], no, I.d_off64[slot]);
+        ctx->launches++;
+        rc = b.add(nullptr, I.d_words[slot], c.nb, I.d_off64[slot], 0, c.r1 - c.r0);
+        cudaEventRecord(I.ev_used[slot], st);
+        if (rc != SYL_OK) break;
+        if (ci >= 1) {  // the pinned buffers of chunk ci-1 have crossed the link: the packers may refill them
+            cudaEventSynchronize(I.ev_copied[(ci - 1) % ING_SLOTS]);
+            gate.store((int64_t)(ci - 1 + ING_SLOTS), std::memory_order_release);
+        }
+    }
+    gate.store((int64_t)1 << 60, std::memory_order_release);  // error exit: let the workers drain
+    I.pool->finish();
+    if (rc != SYL_OK) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
+    return rc;
+}
+
+// host ASCII -> ASCII chunks (SYL_HOST_INGEST=ascii): the round-1 path, 1 byte of H2D traffic per base
+static int feed_host_ascii(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases, const uint64_t *rec_off, uint64_t n_reads) {
     const uint64_t CHUNK = 128ull << 20;
-    static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_start = now();
+    cudaStream_t st = ctx->stream;
     if (!ctx->copy_stream) {
         SYL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -987,7 +1155,6 @@ int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bas
     while (r0 < n_reads || pend.valid) {
         Pending next = {0, 0, 0, slot, false};
         if (r0 < n_reads) {
-            // records [r0, r1) with total bytes <= CHUNK (at least one record)
             uint64_t lo = r0 + 1, hi = n_reads;
             const uint64_t base = rec_off[r0];
             while (lo < hi) {
@@ -1027,17 +1194,105 @@ int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bas
         }
         if (pend.valid) {
             cudaStreamWaitEvent(st, ctx->ev_copied[pend.slot], 0);
-            rc = b.add(ctx->stage_b[pend.slot], pend.nb, ctx->stage_o[pend.slot], pend.bias, pend.nr);
+            rc = b.add(ctx->stage_b[pend.slot], nullptr, pend.nb, ctx->stage_o[pend.slot], pend.bias, pend.nr);
             cudaEventRecord(ctx->ev_used[pend.slot], st);
             if (rc != SYL_OK) break;
         }
         pend = next;
     }
-    const double t_loop = now() - t_start, t0 = now();
-    if (rc == SYL_OK) rc = b.finish(out);
-    else { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
-    if (dbg) fprintf(stderr, "[syl_sketch_reads host] chunk loop %.2f ms, finish %.2f ms\n", t_loop, now() - t0);
+    if (rc != SYL_OK) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
     return rc;
+}
+
+// packed: the input is 2-bit words (device or host memory); else ASCII
+static int sketch_reads_impl(syl_ctx *ctx, int mem, const uint8_t *bases, const uint32_t *packed, uint64_t n_bases,
+                             const uint64_t *rec_off, uint64_t n_reads, int k, uint64_t c, int no_dedup, int sem, syl_sample **out) {
+    if (!ctx || !out || (!bases && !packed && n_bases) || !rec_off) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
+    if (mem != SYL_MEM_HOST && mem != SYL_MEM_DEVICE) { set_error("bad mem"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
+    cudaStream_t st = ctx->stream;
+    const char *hi_env = getenv("SYL_HOST_INGEST");  // read per call: the tests switch it at run time
+    const bool host_ascii = hi_env && std::string(hi_env) == "ascii";
+    static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    uint64_t cap_override = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        SampleBuilder b{ctx, k, c, no_dedup, sem};
+        b.expect_bases = n_bases;
+        b.expect_reads = n_reads;
+        SYL_TRY(b.begin(cap_override));
+        const double t0 = now();
+        int rc = SYL_OK;
+        DevBuf<uint32_t> hp;   // host packed input staged whole
+        DevBuf<uint64_t> ho;
+        if (mem == SYL_MEM_DEVICE) {
+            rc = b.add(bases, packed, n_bases, rec_off, 0, n_reads);
+        } else if (packed) {
+            const uint64_t nw = (n_bases + 15) / 16;
+            SYL_TRY(hp.alloc(nw + 16, st));
+            SYL_TRY(ho.alloc(n_reads + 1, st));
+            if (nw) SYL_CUDA(cudaMemcpyAsync(hp.p, packed, nw * 4, cudaMemcpyHostToDevice, st));
+            SYL_CUDA(cudaMemcpyAsync(ho.p, rec_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+            rc = b.add(nullptr, hp.p, n_bases, ho.p, 0, n_reads);
+        } else if (n_reads && n_bases) {
+            rc = host_ascii ? feed_host_ascii(ctx, b, bases, rec_off, n_reads) : feed_host_packed(ctx, b, bases, rec_off, n_reads);
+        }
+        if (rc != SYL_OK) return rc;
+        const double t1 = now();
+        uint64_t need = 0;
+        rc = b.finish(out, &need);
+        if (dbg) fprintf(stderr, "[syl_sketch_reads host] feed %.2f ms, finish %.2f ms (attempt %d)\n", t1 - t0, now() - t1, attempt);
+        if (rc == SYL_ERR_CAPACITY) { cap_override = need + 16; continue; }  // more events than estimated: redo with the exact size
+        return rc;
+    }
+    set_error("event capacity retry failed");
+    return SYL_ERR_CAPACITY;
+}
+
+}  // namespace syl
+
+using namespace syl;
+
+extern "C" {
+
+int syl_sketch_reads(syl_ctx *ctx, int mem, const uint8_t *bases, uint64_t n_bases,
+                     const uint64_t *rec_off, uint64_t n_reads, int k, uint64_t c, int no_dedup,
+                     int sem, syl_sample **out) {
+    return sketch_reads_impl(ctx, mem, bases, nullptr, n_bases, rec_off, n_reads, k, c, no_dedup, sem, out);
+}
+
+int syl_sketch_reads_packed2(syl_ctx *ctx, int mem, const uint32_t *packed, uint64_t n_bases,
+                             const uint64_t *rec_off, uint64_t n_reads, int k, uint64_t c, int no_dedup,
+                             int sem, syl_sample **out) {
+    if (!packed && n_bases) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    return sketch_reads_impl(ctx, mem, nullptr, packed, n_bases, rec_off, n_reads, k, c, no_dedup, sem, out);
+}
+
+int syl_pack_threads(void) { return default_pack_threads(); }
+
+int syl_pack2(const uint8_t *bases, uint64_t n_bases, uint32_t *words, int n_threads) {
+    if ((!bases && n_bases) || (!words && n_bases)) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    if (n_threads <= 0) n_threads = default_pack_threads();
+    const uint64_t slice = 1ull << 20;  // bases per task (multiple of 16)
+    const uint64_t n_tasks = (n_bases + slice - 1) / slice;
+    n_threads = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_threads, n_tasks));
+    std::atomic<uint64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const uint64_t t = next.fetch_add(1);
+            if (t >= n_tasks) break;
+            const uint64_t o = t * slice;
+            pack2_range(bases + o, std::min(slice, n_bases - o), words + o / 16);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_threads; i++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    return SYL_OK;
 }
 
 int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_t *count,

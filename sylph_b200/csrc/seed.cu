@@ -21,21 +21,22 @@
 //     atomic per CTA
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
-#include "seed_kernel.cuh"
+#include "seed_warp.cuh"
 
 namespace syl {
 
-// tile t -> index of the record that contains flat position t*SEED_TILE
+// tile t -> index of the record that contains flat position t*tile
 __global__ void k_tile_first_rec(const uint64_t *__restrict__ rec_off, uint64_t off_bias, uint64_t n_rec,
-                                 uint64_t n_tiles, uint32_t *__restrict__ tile_rec) {
+                                 uint64_t n_tiles, uint64_t tile, uint32_t *__restrict__ tile_rec) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
     if (t == n_tiles) {
         tile_rec[t] = (uint32_t)(n_rec - 1);
         return;
     }
-    uint64_t pos = t * (uint64_t)SEED_TILE + off_bias;
+    uint64_t pos = t * tile + off_bias;
     // upper_bound over rec_off[0..n_rec]: first i with rec_off[i] > pos
     uint64_t lo = 0, hi = n_rec + 1;
     while (lo < hi) {
@@ -64,78 +65,114 @@ static int pick_run_length(uint64_t mean_len, int k, int sem, int with_pos) {
     return best;
 }
 
-// Host launcher: device-resident inputs, survivors to a device buffer. *n_out is the true
-// number of survivors even when it exceeds cap (then SYL_ERR_CAPACITY).
-// d_rec_off[i] - off_bias is the start of record i inside d_bases (off_bias lets a caller pass a
-// slice of a larger offset array unchanged).
-// emit_events: d_out is an EventRec array (read-sketch path: rec_base = index of the batch's first
-// read, no_dedup as in sketch_sequences_needle) instead of a syl_survivor array; d_pend (cap
-// entries, cap < 2^32) receives the indices of the events whose pair keys are still missing.
-int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
-                   uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
-                   uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
-                   uint32_t *d_pend, uint64_t *n_pend, uint32_t *d_bucket_cnt, uint64_t Mb, uint32_t nbk);
-
-int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
-                uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
-                uint64_t cap, uint64_t *n_out) {
-    return seed_device_ex(ctx, d_bases, n_bases, d_rec_off, off_bias, n_rec, k, c, sem, with_pos, d_out, cap, n_out, 0, 0, 0,
-                          nullptr, nullptr, nullptr, 0, 0);
+// SYL_SEED_IMPL=cta selects the round-1 kernel (one 32K tile per CTA, CTA-wide barriers between the
+// phases; ASCII input only); default is the warp-autonomous persistent kernel of seed_warp.cuh.
+static bool use_warp_kernel() {
+    const char *e = getenv("SYL_SEED_IMPL");  // read per call: the tests switch it at run time
+    return !(e && strcmp(e, "cta") == 0);
 }
 
-int seed_device_ex(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
-                   uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, void *d_out,
-                   uint64_t cap, uint64_t *n_out, int emit_events, uint64_t rec_base, int no_dedup,
-                   uint32_t *d_pend, uint64_t *n_pend, uint32_t *d_bucket_cnt, uint64_t Mb, uint32_t nbk) {
-    *n_out = 0;
-    if (n_pend) *n_pend = 0;
-    if (emit_events && (!d_pend || !n_pend || cap >= 0xFFFFFFFFull)) { set_error("event emission needs a pending list and cap < 2^32"); return SYL_ERR_ARG; }
-    if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
-    if (!(k == 21 || k == 31)) {
+// Enqueue the seeding of one batch on the ctx stream.  No host synchronisation and no counter reset:
+// survivors / events are appended to job.d_out at the running device counter *job.d_count (entries
+// past job.cap are counted but dropped; the caller compares the final count with cap), pending
+// event indices at *job.d_pend_count.
+int seed_enqueue(syl_ctx *ctx, const SeedJob &job) {
+    if (job.emit_events && (!job.d_pend || job.cap >= 0xFFFFFFFFull)) { set_error("event emission needs a pending list and cap < 2^32"); return SYL_ERR_ARG; }
+    if (job.c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
+    if (!(job.k == 21 || job.k == 31)) {
         set_error("k must be 21 or 31 (the reference panics otherwise, src/avx2_seeding.rs:46-52)");
         return SYL_ERR_UNSUPPORTED;
     }
-    if (sem != SYL_SEM_SCALAR && sem != SYL_SEM_AVX2) { set_error("bad sem"); return SYL_ERR_ARG; }
-    if (n_rec == 0 || n_bases == 0) return SYL_OK;
-    if (n_rec >= 0xFFFFFFFFull) { set_error("more than 2^32-2 records in one batch"); return SYL_ERR_ARG; }
-    if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) != 0) {
+    if (job.sem != SYL_SEM_SCALAR && job.sem != SYL_SEM_AVX2) { set_error("bad sem"); return SYL_ERR_ARG; }
+    if (job.n_rec == 0 || job.n_bases == 0) return SYL_OK;
+    if (job.n_rec >= 0xFFFFFFFFull) { set_error("more than 2^32-2 records in one batch"); return SYL_ERR_ARG; }
+    const void *in = job.d_packed ? (const void *)job.d_packed : (const void *)job.d_bases;
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) != 0) {
         set_error("device base buffer must be 16-byte aligned (TMA bulk copy)");
         return SYL_ERR_ARG;
     }
+    const bool warp = use_warp_kernel() || job.d_packed != nullptr;
     cudaStream_t st = ctx->stream;
-    const uint64_t n_tiles = (n_bases + SEED_TILE - 1) / SEED_TILE;
+    const uint64_t tile = warp ? (uint64_t)SW_TW : (uint64_t)SEED_TILE;
+    const uint64_t n_tiles = (job.n_bases + tile - 1) / tile;
     DevBuf<uint32_t> tile_rec;
     SYL_TRY(tile_rec.alloc(n_tiles + 1, st));
     {
         const int bs = 256;
         const uint64_t nb = (n_tiles + 1 + bs - 1) / bs;
-        k_tile_first_rec<<<(unsigned)nb, bs, 0, st>>>(d_rec_off, off_bias, n_rec, n_tiles, tile_rec.p);
+        k_tile_first_rec<<<(unsigned)nb, bs, 0, st>>>(job.d_rec_off, job.off_bias, job.n_rec, n_tiles, tile, tile_rec.p);
         ctx->launches++;
     }
-    SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint64_t), st));  // [0] survivors, [1] pending events
-    const uint64_t thr = fmh_threshold(c);
-    const size_t smem = sizeof(SeedSmem);
+    const uint64_t thr = fmh_threshold(job.c);
     const ShiftMul smul = {1u << 8, 1u << 18, 1u << 4, 1u, 0u};
     // Run length: every record is cut into runs of W windows and a thread always pays for a full
     // run, so for fixed-length reads W should divide the per-read window count (150 bp, k=31:
     // 120 windows = 4 x 30).  Chosen from the mean record length; long records get 32.
-    const int W = pick_run_length(n_bases / n_rec, k, sem, with_pos);
-    const seed_kern_t kern = emit_events ? (k == 31 ? seed_kernels_k31_ev(W) : seed_kernels_k21_ev(W))
-                                         : (k == 31 ? seed_kernels_k31_sv(W) : seed_kernels_k21_sv(W));
-    SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KernelTimer kt(ctx, SYL_KERNEL_SEED);
-    kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
-        d_bases, n_bases, d_rec_off, off_bias, tile_rec.p, thr, sem, with_pos, d_out, cap,
-        reinterpret_cast<unsigned long long *>(ctx->d_counters), smul, rec_base, no_dedup, d_pend,
-        BucketHist{emit_events ? d_bucket_cnt : nullptr, Mb, nbk});
-    kt.stop();
-    if (ctx->timing) ctx->seed_bases += n_bases;
+    const int W = pick_run_length(job.n_bases / job.n_rec, job.k, job.sem, job.with_pos);
+    const BucketHist bh{job.emit_events ? job.d_bucket_cnt : nullptr, job.Mb, job.nbk};
+    if (!warp) {
+        if (job.d_pend_count != job.d_count + 1) { set_error("internal: cta kernel expects adjacent counters"); return SYL_ERR_ARG; }
+        const size_t smem = sizeof(SeedSmem);
+        const seed_kern_t kern = job.emit_events ? (job.k == 31 ? seed_kernels_k31_ev(W) : seed_kernels_k21_ev(W))
+                                                 : (job.k == 31 ? seed_kernels_k31_sv(W) : seed_kernels_k21_sv(W));
+        SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer kt(ctx, SYL_KERNEL_SEED);
+        kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
+            job.d_bases, job.n_bases, job.d_rec_off, job.off_bias, tile_rec.p, thr, job.sem, job.with_pos, job.d_out, job.cap,
+            job.d_count, smul, job.rec_base, job.no_dedup, job.d_pend, bh);
+        kt.stop();
+    } else {
+        const bool pk = job.d_packed != nullptr;
+        seedw_kern_t kern;
+        if (pk) kern = job.emit_events ? (job.k == 31 ? seedw_kernels_k31_ev_p(W) : seedw_kernels_k21_ev_p(W))
+                                       : (job.k == 31 ? seedw_kernels_k31_sv_p(W) : seedw_kernels_k21_sv_p(W));
+        else kern = job.emit_events ? (job.k == 31 ? seedw_kernels_k31_ev(W) : seedw_kernels_k21_ev(W))
+                                    : (job.k == 31 ? seedw_kernels_k31_sv(W) : seedw_kernels_k21_sv(W));
+        const size_t smem = pk ? seedw_smem_bytes<true>() : seedw_smem_bytes<false>();
+        SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SYL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_THREADS, smem));
+        if (per_sm < 1) { set_error("seeding kernel does not fit on an SM"); return SYL_ERR_CUDA; }
+        static const int force_ctas = []() { const char *e = getenv("SYL_SEED_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+        if (force_ctas > 0) per_sm = std::min(per_sm, force_ctas);
+        uint64_t grid = (uint64_t)per_sm * ctx->num_sms;
+        grid = std::min<uint64_t>(grid, (n_tiles + SW_WARPS - 1) / SW_WARPS);
+        unsigned long long *d_tile = reinterpret_cast<unsigned long long *>(ctx->d_counters + 16);
+        SYL_CUDA(cudaMemsetAsync(d_tile, 0, 8, st));
+        SeedWArgs A;
+        A.bases = job.d_bases; A.packed = job.d_packed; A.n_bases = job.n_bases; A.rec_off = job.d_rec_off;
+        A.off_bias = job.off_bias; A.tile_rec = tile_rec.p; A.n_tiles = n_tiles; A.thr = thr; A.sem = job.sem;
+        A.with_pos = job.with_pos; A.out = job.d_out; A.cap = job.cap; A.g_count = job.d_count; A.g_pend = job.d_pend_count;
+        A.g_tile = d_tile; A.smul = smul; A.rec_base = job.rec_base; A.no_dedup = job.no_dedup; A.pend = job.d_pend; A.bh = bh;
+        KernelTimer kt(ctx, SYL_KERNEL_SEED);
+        kern<<<(unsigned)grid, SW_THREADS, smem, st>>>(A);
+        kt.stop();
+    }
+    if (ctx->timing) ctx->seed_bases += job.n_bases;
     ctx->launches++;
     SYL_CUDA(cudaGetLastError());
-    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    return SYL_OK;
+}
+
+// Synchronous form: device-resident inputs, survivors to a device buffer. *n_out is the true
+// number of survivors even when it exceeds cap (then SYL_ERR_CAPACITY).
+// d_rec_off[i] - off_bias is the start of record i inside d_bases (off_bias lets a caller pass a
+// slice of a larger offset array unchanged).
+int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
+                uint64_t n_rec, int k, uint64_t c, int sem, int with_pos, syl_survivor *d_out,
+                uint64_t cap, uint64_t *n_out) {
+    *n_out = 0;
+    cudaStream_t st = ctx->stream;
+    SeedJob job;
+    job.d_bases = d_bases; job.n_bases = n_bases; job.d_rec_off = d_rec_off; job.off_bias = off_bias; job.n_rec = n_rec;
+    job.k = k; job.c = c; job.sem = sem; job.with_pos = with_pos; job.d_out = d_out; job.cap = cap;
+    job.d_count = reinterpret_cast<unsigned long long *>(ctx->d_counters);
+    job.d_pend_count = job.d_count + 1;
+    SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint64_t), st));
+    SYL_TRY(seed_enqueue(ctx, job));
+    SYL_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SYL_CUDA(cudaStreamSynchronize(st));
     *n_out = ctx->h_counters[0];
-    if (n_pend) *n_pend = ctx->h_counters[1];
     if (*n_out > cap) {
         set_error("survivor buffer too small");
         return SYL_ERR_CAPACITY;

@@ -113,16 +113,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// 16 two-bit fields (the even ones of 32, MSB-first) of x -> 32 bits
-__device__ __forceinline__ uint32_t even_fields(uint64_t x) {
-    x &= 0xCCCCCCCCCCCCCCCCull;
-    x = (x | (x << 2)) & 0xF0F0F0F0F0F0F0F0ull;
-    x = (x | (x << 4)) & 0xFF00FF00FF00FF00ull;
-    x = (x | (x << 8)) & 0xFFFF0000FFFF0000ull;
-    x = (x | (x << 16)) & 0xFFFFFFFF00000000ull;
-    return (uint32_t)(x >> 32);
-}
-
 // 32 consecutive bases (64 bits, MSB-first) of the forward stream starting at tile-relative base q
 __device__ __forceinline__ uint64_t fw64(const SeedSmem &S, uint32_t q) {
     const uint32_t bitpos = 32u + 2u * q, w = bitpos >> 5, sh = bitpos & 31u;

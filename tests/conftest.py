@@ -18,3 +18,24 @@ def ctx():
     c = sylph_b200.Context(0)
     yield c
     c.close()
+
+
+SEED_MODES = {
+    # default kernels: warp-autonomous persistent seeding kernel; host inputs of syl_sketch_reads are packed to
+    # 2 bits by the worker pool and shipped in tiny chunks (many chunks, every staging slot recycled)
+    "warp+packed-ingest": {"SYL_INGEST_CHUNK": "8192"},
+    # the same kernel fed ASCII from the host (1 byte per base over PCIe)
+    "warp+ascii-ingest": {"SYL_HOST_INGEST": "ascii"},
+    # round-1 kernel (one 32K tile per CTA)
+    "cta+ascii-ingest": {"SYL_SEED_IMPL": "cta", "SYL_HOST_INGEST": "ascii"},
+}
+
+
+@pytest.fixture(params=list(SEED_MODES))
+def seed_mode(request, monkeypatch):
+    """Run a test once per seeding / ingest implementation (the library reads these variables per call)."""
+    for k in ("SYL_SEED_IMPL", "SYL_HOST_INGEST", "SYL_INGEST_CHUNK"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in SEED_MODES[request.param].items():
+        monkeypatch.setenv(k, v)
+    return request.param

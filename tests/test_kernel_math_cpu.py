@@ -189,3 +189,28 @@ def test_histogram_formulation_of_get_stats(lam):
         kept = [c for c in covs if c <= max_cov]
         assert nz == len(kept) and total == sum(kept) & 0xFFFFFFFF
         assert h16[1:] == [kept.count(v) for v in range(1, 17)]
+
+
+def test_host_packer_is_exact_byte_to_seq():
+    """syl_pack2 (AVX2 nibble-table classification + scalar tail) against BYTE_TO_SEQ (src/types.rs:50-59) written
+    out directly: every byte value, every length mod 32, multi-threaded == single-threaded.  Runs without a GPU."""
+    import numpy as np
+    from sylph_b200.api import pack2
+    lut = np.zeros(256, np.uint64)
+    for ch, v in ((b"C", 1), (b"c", 1), (b"G", 2), (b"g", 2), (b"T", 3), (b"t", 3), (b"U", 3), (b"u", 3)):
+        lut[ch[0]] = v
+    lut[1], lut[2], lut[3] = 1, 2, 3
+
+    def ref(b):
+        nw = (len(b) + 15) // 16
+        c = np.zeros(nw * 16, np.uint64)
+        c[:len(b)] = lut[b]
+        return (c.reshape(nw, 16) << (30 - 2 * np.arange(16, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+
+    rng = np.random.default_rng(1)
+    every = np.arange(256, dtype=np.uint8).repeat(3)
+    assert np.array_equal(pack2(every, 1), ref(every))
+    for n in list(range(0, 70)) + [1000, 4097, (1 << 21) + 5]:
+        b = rng.integers(0, 256, n, dtype=np.uint8)
+        assert np.array_equal(pack2(b, 1), ref(b)), n
+        assert np.array_equal(pack2(b, 3), ref(b)), n

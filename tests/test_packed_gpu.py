@@ -1,0 +1,95 @@
+"""GPU parity of the 2-bit packed ingest path: packed == ASCII == oracle.
+syl_pack2 (host packer, exact BYTE_TO_SEQ) -> syl_seed_batch_packed2 / syl_sketch_reads_packed2, host and
+device memory, every byte value, ragged records, tile edges of the warp-tile (4096) and the chunk ring."""
+import numpy as np
+import pytest
+
+from tests.test_seed_gpu import oracle_survivors, random_records
+from tests.util import flatten
+
+pytestmark = pytest.mark.gpu
+
+ALL_BYTES = bytes(range(256))
+
+
+def survivors_packed(ctx, buf, off, k, c, sem, with_pos, device):
+    from sylph_b200.api import pack2
+    words = pack2(buf)
+    if device:
+        import torch
+        w = torch.from_numpy(words.view(np.int32)).cuda()
+        o = torch.from_numpy(off.astype(np.int64)).cuda()
+        return ctx.extract_markers_batch(w, o, k=k, c=c, sem=sem, with_pos=with_pos, packed_bases=len(buf))
+    return ctx.extract_markers_batch(words, off, k=k, c=c, sem=sem, with_pos=with_pos, packed_bases=len(buf))
+
+
+@pytest.mark.parametrize("k", [31, 21])
+@pytest.mark.parametrize("sem", [1, 0])
+@pytest.mark.parametrize("device", [False, True])
+def test_seeding_packed_equals_oracle_all_byte_values(ctx, k, sem, device):
+    rng = np.random.default_rng(3 + k + sem)
+    lengths = [0, 1, k - 1, k, k + 1, k + 3, 2 * k - 1, 2 * k, 66, 150, 151, 400, 401, 4095, 4096, 4097, 4096 + 47, 4096 + 48,
+               3 * 4096 + 5, 0, 17, 40000] + list(rng.integers(0, 500, size=600))
+    buf, off = random_records(rng, lengths, alphabet=ALL_BYTES)
+    sv = survivors_packed(ctx, buf, off, k, 5, sem, True, device)
+    exp = oracle_survivors(buf, off, k, 5, sem, True)
+    got = sorted((int(a), int(b), int(h)) for h, a, b in zip(sv["hash"], sv["rec"], sv["pos"]))
+    assert got == sorted(exp) and len(exp) > 1000
+    sv2 = ctx.extract_markers_batch(buf, off, k=k, c=5, sem=sem, with_pos=True)      # ASCII path, same survivors
+    assert got == sorted((int(a), int(b), int(h)) for h, a, b in zip(sv2["hash"], sv2["rec"], sv2["pos"]))
+
+
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("no_dedup", [False, True])
+def test_read_sketch_packed_equals_ascii_equals_oracle(ctx, device, no_dedup):
+    """Pair keys come from the packed stream (in-tile) or from packed global memory (reads cut by a warp-tile
+    edge: k_events_fix<packed>); duplicates make the dedup state machine depend on them."""
+    from oracle import oracle as O
+    from sylph_b200.api import pack2
+    rng = np.random.default_rng(77)
+    genome = bytes(rng.choice(list(b"ACGT"), size=120000).astype(np.uint8))
+    seqs = []
+    for _ in range(9000):
+        st = int(rng.integers(0, 120000 - 450))
+        ln = int(rng.choice([60, 66, 70, 100, 149, 150, 150, 151, 250, 400, 401]))
+        s = genome[st:st + ln]
+        if rng.random() < 0.05:
+            s = bytes(rng.choice(list(ALL_BYTES), size=ln).astype(np.uint8))   # arbitrary bytes
+        seqs.append(s)
+        if rng.random() < 0.3:
+            seqs.append(s)
+    seqs += [b"", b"A", b"N" * 150, b"acgtn" * 30]
+    buf, off = flatten([seqs[i] for i in rng.permutation(len(seqs))])
+    eh, ec, _, nd = O.sketch_reads(buf, off, c=5, no_dedup=no_dedup)
+    words = pack2(buf)
+    if device:
+        import torch
+        sp = ctx.sketch_sequences(torch.from_numpy(words.view(np.int32)).cuda(), torch.from_numpy(off.astype(np.int64)).cuda(),
+                                  c=5, no_dedup=no_dedup, packed_bases=len(buf))
+        sa = ctx.sketch_sequences(torch.from_numpy(buf).cuda(), torch.from_numpy(off.astype(np.int64)).cuda(), c=5, no_dedup=no_dedup)
+    else:
+        sp = ctx.sketch_sequences(words, off, c=5, no_dedup=no_dedup, packed_bases=len(buf))
+        sa = ctx.sketch_sequences(buf, off, c=5, no_dedup=no_dedup)
+    for s in (sp, sa):
+        h, c = s.download()
+        assert np.array_equal(h, eh) and np.array_equal(c, ec) and s.num_dup_removed == nd
+    if not no_dedup:
+        assert nd > 1000
+
+
+def test_host_ingest_chunk_ring(ctx, monkeypatch):
+    """Host ASCII -> worker-pool packer -> pinned ring -> device: chunks far smaller than the input so that every
+    staging slot is recycled many times, records larger than a chunk, and 1-thread / many-thread pools agree."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    lengths = list(rng.integers(0, 400, size=4000)) + [70000, 150, 150, 33, 0, 0, 9000]
+    buf, off = random_records(rng, [lengths[i] for i in rng.permutation(len(lengths))], alphabet=b"ACGTNacgt")
+    eh, ec, _, nd = O.sketch_reads(buf, off, c=11)
+    for chunk in ("4096", "65536", None):
+        if chunk:
+            monkeypatch.setenv("SYL_INGEST_CHUNK", chunk)
+        else:
+            monkeypatch.delenv("SYL_INGEST_CHUNK", raising=False)
+        s = ctx.sketch_sequences(buf, off, c=11)
+        h, c = s.download()
+        assert np.array_equal(h, eh) and np.array_equal(c, ec) and s.num_dup_removed == nd, chunk

@@ -6,7 +6,7 @@ import pytest
 
 from tests.util import DATA, flatten, read_fastx
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("seed_mode")]
 
 
 def oracle_survivors(buf, off, k, c, sem, with_pos):

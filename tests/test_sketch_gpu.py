@@ -6,7 +6,7 @@ import pytest
 
 from tests.util import DATA, flatten, read_fastx
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("seed_mode")]
 
 
 def check_reads(ctx, buf, off, k=31, c=200, no_dedup=False, sem=1):
