@@ -358,16 +358,25 @@ def bench_sketch(args, ctx, rank, world, local):
     oc = torch.empty(out_cap, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
     e2e_state = {}
 
+    e2e_state["t"] = []
+
     def step_e2e():
+        t_s = time.perf_counter()
         s = ctx.sketch_sequences(hb_np, ho_np, k=K, c=C)
         h, c = s.download(oh, oc)
         e2e_state["n"] = len(h)
         s.free()
+        e2e_state["t"].append(round((time.perf_counter() - t_s) * 1e3, 3))
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 10))
+    e2e_state["t"] = []
+    ctx.enable_timing(True)
+    ctx.seed_kernel_time(reset=True)
     _, wall_ms = timed(step_e2e, e2e_steps, world)
+    e2e_seed_ms = ctx.seed_kernel_time(reset=True)[0] / e2e_steps
+    ctx.enable_timing(False)
     e2e_value = total_bases * e2e_steps / (wall_ms * 1e-3)
     from sylph_b200 import _lib
     ingest = os.environ.get("SYL_HOST_INGEST", "packed2")
@@ -380,7 +389,8 @@ def bench_sketch(args, ctx, rank, world, local):
                 "u32 chunk-relative record offsets" % _lib.lib().syl_pack_threads())
     e2e = {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": int(12 * e2e_state["n"]), "steps": e2e_steps, "ms_per_step": wall_ms / e2e_steps,
-           "timing": "wall clock bracketed by device syncs, max over ranks", "ingest": what,
+           "timing": "wall clock bracketed by device syncs, max over ranks", "per_step_ms": e2e_state["t"],
+           "seed_kernel_ms_per_step": e2e_seed_ms, "ingest": what,
            "call": "syl_sketch_reads(SYL_MEM_HOST, ASCII bases, u64 offsets) + syl_sample_download into pinned result buffers"}
 
     cpu = None

@@ -4,7 +4,6 @@
 #pragma once
 #include <stdint.h>
 
-#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -27,34 +26,33 @@ struct PackItem {
     uint32_t chunk;       // chunk the slice belongs to
 };
 
-// Persistent worker pool.  run() hands out the items of `items` (ordered by chunk) to the workers;
-// item i of chunk c may only start once gate(c) allows it (its staging buffer is free again), and
-// chunk_done[c] counts the finished items of chunk c so that the caller can ship complete chunks
-// while later ones are still being packed.
+// Persistent worker pool.  start() hands the items of a job (ordered by chunk) to the workers; an
+// item of chunk c may only run once open_gate(g) with g >= c has been called (its pinned staging
+// buffer is free again), and wait_chunk(c) returns when every item of chunk c is done, so that the
+// caller can ship complete chunks while later ones are still being packed.  Workers and the caller
+// BLOCK on condition variables while there is nothing to do (no spinning: on hosts with a CPU quota
+// spinning threads burn the quota of the threads that have work).
 class PackPool {
 public:
     explicit PackPool(int n_threads);
     ~PackPool();
     int threads() const { return (int)workers_.size(); }
-    // start a job; returns immediately.  items / remaining stay owned by the caller and must outlive finish().
-    void start(const std::vector<PackItem> *items, std::vector<std::atomic<uint32_t>> *remaining, std::atomic<int64_t> *gate_chunk);
-    // block until chunk c is completely packed
+    // items / chunk_items stay owned by the caller and must outlive finish(); chunk_items[c] = items of chunk c
+    void start(const std::vector<PackItem> *items, const std::vector<uint32_t> *chunk_items, int64_t gate);
+    void open_gate(int64_t gate);
     void wait_chunk(uint32_t c);
-    // block until every item has been processed (must be called before the next start)
-    void finish();
+    void finish();  // every item processed; must be called before the next start()
 
 private:
     void worker();
     std::vector<std::thread> workers_;
     std::mutex mu_;
-    std::condition_variable cv_;
+    std::condition_variable cv_work_, cv_done_;
     bool stop_ = false;
-    uint64_t generation_ = 0;
     const std::vector<PackItem> *items_ = nullptr;
-    std::vector<std::atomic<uint32_t>> *remaining_ = nullptr;
-    std::atomic<int64_t> *gate_ = nullptr;  // items of chunks <= *gate_ may run
-    std::atomic<uint64_t> next_{0};
-    std::atomic<int> active_{0};
+    std::vector<uint32_t> remaining_;  // per chunk
+    size_t next_ = 0, done_ = 0;
+    int64_t gate_ = -1;
 };
 
 int default_pack_threads();

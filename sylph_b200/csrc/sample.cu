@@ -376,12 +376,13 @@ k_group_dedup(const EventRec *__restrict__ part, const uint32_t *__restrict__ bo
         S.dups = 0;
         S.nlong = 0;
     }
-    for (int i = tid; i < GRP_SLOTS; i += GRP_THREADS) { S.ht[i] = 0xFFFFFFFFFFFFFFFFull; S.scnt[i] = 0; }
     __syncthreads();
     const uint32_t e0 = S.e0, bf = S.bf;
     const uint32_t n = S.e1 <= ev_cap ? S.e1 - S.e0 : 0u;  // past the capacity only after an overflow (sample is redone)
     if (tid == 0) { g_e0[g] = e0; g_n[g] = n; g_nuniq[g] = 0; g_fallback[g] = 0; }
-    if (n == 0) return;
+    if (n == 0) return;  // the grid is sized for the event capacity: most surplus groups leave here
+    for (int i = tid; i < GRP_SLOTS; i += GRP_THREADS) { S.ht[i] = 0xFFFFFFFFFFFFFFFFull; S.scnt[i] = 0; }
+    __syncthreads();
     if (n > cap) { if (tid == 0) g_fallback[g] = 1; return; }
     // (1) stage the events, group equal hashes: slot per event, events per slot
     for (uint32_t i = tid; i < n; i += GRP_THREADS) {
@@ -1093,7 +1094,7 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
     SYL_TRY(I.ensure(std::max<uint64_t>(max_words, ING_CHUNK / 16), std::max<uint64_t>(max_recs, 65536)));
     cudaStream_t st = ctx->stream, cs = I.copy_stream;
     std::vector<PackItem> items;
-    std::vector<std::atomic<uint32_t>> remaining(chunks.size());
+    std::vector<uint32_t> chunk_items(chunks.size());
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const Chunk &c = chunks[ci];
         const int slot = (int)(ci % ING_SLOTS);
@@ -1103,10 +1104,9 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
         const uint64_t no = c.r1 - c.r0 + 1;
         for (uint64_t o = 0; o < no; o += ING_OSLICE, n_items++)
             items.push_back({nullptr, 0, nullptr, rec_off + c.r0 + o, c.base, std::min(ING_OSLICE, no - o), I.h_off[slot] + o, (uint32_t)ci});
-        remaining[ci].store(n_items, std::memory_order_relaxed);
+        chunk_items[ci] = n_items;
     }
-    std::atomic<int64_t> gate(ING_SLOTS - 1);
-    I.pool->start(&items, &remaining, &gate);
+    I.pool->start(&items, &chunk_items, ING_SLOTS - 1);
     int rc = SYL_OK;
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const Chunk &c = chunks[ci];
@@ -1127,10 +1127,10 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
         if (rc != SYL_OK) break;
         if (ci >= 1) {  // the pinned buffers of chunk ci-1 have crossed the link: the packers may refill them
             cudaEventSynchronize(I.ev_copied[(ci - 1) % ING_SLOTS]);
-            gate.store((int64_t)(ci - 1 + ING_SLOTS), std::memory_order_release);
+            I.pool->open_gate((int64_t)(ci - 1 + ING_SLOTS));
         }
     }
-    gate.store((int64_t)1 << 60, std::memory_order_release);  // error exit: let the workers drain
+    I.pool->open_gate((int64_t)1 << 60);  // error exit: let the workers drain
     I.pool->finish();
     if (rc != SYL_OK) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
     return rc;

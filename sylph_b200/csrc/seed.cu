@@ -65,11 +65,35 @@ static int pick_run_length(uint64_t mean_len, int k, int sem, int with_pos) {
     return best;
 }
 
-// SYL_SEED_IMPL=cta selects the round-1 kernel (one 32K tile per CTA, CTA-wide barriers between the
-// phases; ASCII input only); default is the warp-autonomous persistent kernel of seed_warp.cuh.
+// Tile length of the warp kernel.  A warp processes a tile's runs 32 at a time, and a partially filled
+// round costs as many issue slots as a full one, so the tile is sized to hold just under 32 r runs
+// (r rounds): runs per base follow from the mean record length; two runs of slack absorb the partial
+// runs of the records cut by the tile's two edges.  SYL_SEED_TW forces a length (tests, tuning).
+static uint32_t pick_warp_tile(uint64_t mean_len, int k, int sem, int with_pos, int W) {
+    const char *fe = getenv("SYL_SEED_TW");  // read per call: the tests switch it at run time
+    const int forced = fe ? atoi(fe) : 0;
+    if (forced >= 64) return (uint32_t)std::min(forced & ~63, SW_TW & ~63);  // multiples of 64 bases: 16-byte aligned 2-bit tiles
+    const uint64_t w = valid_windows(mean_len, (uint32_t)k, sem, with_pos);
+    if (mean_len == 0 || w == 0) return (uint32_t)(SW_TW & ~63);
+    double runs_per_base;
+    if (mean_len > 2048) runs_per_base = 1.0 / W;                       // long records: windows ~ bases
+    else runs_per_base = (double)((w + W - 1) / W) / (double)mean_len;  // short reads: whole runs per read
+    for (int r = 8; r >= 1; r--) {
+        const double tw = (32.0 * r - 2.0) / runs_per_base;
+        if (tw <= (double)SW_TW) return (uint32_t)std::max(64, (int)tw & ~63);
+    }
+    return (uint32_t)(SW_TW & ~63);
+}
+
+// Two formulations of the kernel (same arithmetic, same results):
+//   cta  (default for ASCII input): one 32K tile per CTA, phases separated by CTA-wide barriers (seed_kernel.cuh)
+//   warp (SYL_SEED_IMPL=warp; always for 2-bit packed input): warp-autonomous persistent kernel (seed_warp.cuh)
+// Measured on 1 Gbp of 150 bp reads: cta 1.44 ms, warp 1.50 ms — the hot loop alone (scripts/hotloop_bench.cu)
+// sustains 0.74 T windows/s = 1.08 ms for the same windows with its two pipes (ALU 18.5, FMA-heavy 13
+// instructions per window) each ~73 % busy, so what the phases around it can still give back is small.
 static bool use_warp_kernel() {
     const char *e = getenv("SYL_SEED_IMPL");  // read per call: the tests switch it at run time
-    return !(e && strcmp(e, "cta") == 0);
+    return e && strcmp(e, "warp") == 0;
 }
 
 // Enqueue the seeding of one batch on the ctx stream.  No host synchronisation and no counter reset:
@@ -93,7 +117,12 @@ int seed_enqueue(syl_ctx *ctx, const SeedJob &job) {
     }
     const bool warp = use_warp_kernel() || job.d_packed != nullptr;
     cudaStream_t st = ctx->stream;
-    const uint64_t tile = warp ? (uint64_t)SW_TW : (uint64_t)SEED_TILE;
+    // Run length: every record is cut into runs of W windows and a thread always pays for a full
+    // run, so for fixed-length reads W should divide the per-read window count (150 bp, k=31:
+    // 120 windows = 4 x 30).  Chosen from the mean record length; long records get 32.
+    const uint64_t mean_len = job.n_bases / job.n_rec;
+    const int W = pick_run_length(mean_len, job.k, job.sem, job.with_pos);
+    const uint64_t tile = warp ? (uint64_t)pick_warp_tile(mean_len, job.k, job.sem, job.with_pos, W) : (uint64_t)SEED_TILE;
     const uint64_t n_tiles = (job.n_bases + tile - 1) / tile;
     DevBuf<uint32_t> tile_rec;
     SYL_TRY(tile_rec.alloc(n_tiles + 1, st));
@@ -105,10 +134,6 @@ int seed_enqueue(syl_ctx *ctx, const SeedJob &job) {
     }
     const uint64_t thr = fmh_threshold(job.c);
     const ShiftMul smul = {1u << 8, 1u << 18, 1u << 4, 1u, 0u};
-    // Run length: every record is cut into runs of W windows and a thread always pays for a full
-    // run, so for fixed-length reads W should divide the per-read window count (150 bp, k=31:
-    // 120 windows = 4 x 30).  Chosen from the mean record length; long records get 32.
-    const int W = pick_run_length(job.n_bases / job.n_rec, job.k, job.sem, job.with_pos);
     const BucketHist bh{job.emit_events ? job.d_bucket_cnt : nullptr, job.Mb, job.nbk};
     if (!warp) {
         if (job.d_pend_count != job.d_count + 1) { set_error("internal: cta kernel expects adjacent counters"); return SYL_ERR_ARG; }
@@ -141,7 +166,7 @@ int seed_enqueue(syl_ctx *ctx, const SeedJob &job) {
         SYL_CUDA(cudaMemsetAsync(d_tile, 0, 8, st));
         SeedWArgs A;
         A.bases = job.d_bases; A.packed = job.d_packed; A.n_bases = job.n_bases; A.rec_off = job.d_rec_off;
-        A.off_bias = job.off_bias; A.tile_rec = tile_rec.p; A.n_tiles = n_tiles; A.thr = thr; A.sem = job.sem;
+        A.off_bias = job.off_bias; A.tile_rec = tile_rec.p; A.n_tiles = n_tiles; A.tw = (uint32_t)tile; A.thr = thr; A.sem = job.sem;
         A.with_pos = job.with_pos; A.out = job.d_out; A.cap = job.cap; A.g_count = job.d_count; A.g_pend = job.d_pend_count;
         A.g_tile = d_tile; A.smul = smul; A.rec_base = job.rec_base; A.no_dedup = job.no_dedup; A.pend = job.d_pend; A.bh = bh;
         KernelTimer kt(ctx, SYL_KERNEL_SEED);

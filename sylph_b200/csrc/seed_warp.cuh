@@ -21,15 +21,19 @@
 namespace syl {
 
 #ifndef SEEDW_TW
-#define SEEDW_TW 4096
+#define SEEDW_TW 3584
 #endif
 #ifndef SEEDW_MINB
 #define SEEDW_MINB 3
 #endif
-constexpr int SW_TW = SEEDW_TW;                 // window starts (== bases) per warp-tile
+#ifndef SEEDW_WARPS
+#define SEEDW_WARPS 8
+#endif
+constexpr int SW_TW = SEEDW_TW;                 // capacity: most window starts (== bases) per warp-tile; the launcher picks
+                                                // the actual tile length tw <= SW_TW so that a tile holds just under 32 r runs
 constexpr int SW_HALO = 48;                     // bases staged past the tile (>= k-1, multiple of 16)
-constexpr int SW_THREADS = 256;
-constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_WARPS = SEEDW_WARPS;
+constexpr int SW_THREADS = 32 * SW_WARPS;
 constexpr int SW_ASC = SW_TW + SW_HALO;         // bytes / bases staged per tile (multiple of 16)
 constexpr int SW_NCH = SW_ASC / 16;             // 16-base words per stream
 constexpr int SW_NCHP = (SW_NCH + 3) & ~3;      // packed input: words copied per tile (16-byte multiple)
@@ -61,6 +65,7 @@ struct SeedWArgs {
     uint64_t off_bias;
     const uint32_t *tile_rec;  // first record overlapping each tile (n_tiles + 1 entries)
     uint64_t n_tiles;
+    uint32_t tw;               // window starts per tile (multiple of 64, <= SW_TW)
     uint64_t thr;
     int sem, with_pos;
     void *out;                 // syl_survivor[cap] or EventRec[cap]
@@ -165,7 +170,7 @@ __device__ __forceinline__ void seedw_resolve(SeedWSlab<PACKED> &S, const SeedWA
         if (has_pair) {
             const long long st = S.rel[j];  // read start, tile-relative
             const long long mid = st + (L >> 1);
-            if (st >= 0 && mid + 32 <= (long long)SW_NCH * 16) {
+            if (st >= 0 && mid + 32 <= (long long)A.tw + SW_HALO) {
                 const uint64_t a = seedw_fw64(fw, (uint32_t)st), b = seedw_fw64(fw, (uint32_t)mid);
                 const uint32_t kf = even_fields(a), kg = even_fields(a << 2);  // s[0,2,..,30] / s[1,3,..,31]
                 const uint32_t kr = even_fields(b), kt = even_fields(b << 2);
@@ -199,35 +204,40 @@ k_seed_w(const SeedWArgs A) {
     uint32_t *const fw = S.fwbuf + 3;  // fw[0] = lead pad word, fw[1 + ch] = bases 16ch .. 16ch+15 (MSB-first)
     const uint32_t thr_hi = (uint32_t)(A.thr >> 32);
     const uint32_t mbar = smem_u32(&S.mbar);
+    const uint32_t asc_n = A.tw + SW_HALO;          // bases staged per tile
+    const int nch = (int)(asc_n >> 4);              // 16-base words per stream
+    const uint32_t nchp = ((uint32_t)nch + 3u) & ~3u;  // packed input: words copied per tile (16-byte multiple)
 
     if (!PACKED) {
-        const uint32_t code = byte_to_seq((uint32_t)tid);
-        lut[0][tid] = (uint8_t)(code << 6);
-        lut[1][tid] = (uint8_t)(code << 4);
-        lut[2][tid] = (uint8_t)(code << 2);
-        lut[3][tid] = (uint8_t)code;
+        for (int b = tid; b < 256; b += SW_THREADS) {
+            const uint32_t code = byte_to_seq((uint32_t)b);
+            lut[0][b] = (uint8_t)(code << 6);
+            lut[1][b] = (uint8_t)(code << 4);
+            lut[2][b] = (uint8_t)(code << 2);
+            lut[3][b] = (uint8_t)code;
+        }
     }
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fw[0] = 0u;
     }
-    for (int i = lane; i < SW_NCHP + 8 - SW_NCH; i += 32) {  // words past the staged bases: read by run loads, never used
-        fw[1 + SW_NCH + i] = 0u;
-        S.cw[SW_NCH + i] = 0u;
+    for (int i = nch + lane; i < SW_NCHP + 8; i += 32) {  // words past the staged bases: read by run loads, never used
+        fw[1 + i] = 0u;
+        S.cw[i] = 0u;
     }
     __syncthreads();  // the only CTA-wide barrier: lut and mbarriers are ready
 
     // stage tile t into this warp's slab: one TMA bulk copy for the 16-byte-aligned body (lane 0),
     // plain loads for the tail of the buffer's last tile
     auto issue_load = [&](uint64_t t) {
-        const uint64_t T0 = t * (uint64_t)SW_TW;
+        const uint64_t T0 = t * (uint64_t)A.tw;
         if (!PACKED) {
             const uint64_t remain = A.n_bases - T0;
-            const uint32_t avail = remain < (uint64_t)SW_ASC ? (uint32_t)remain : (uint32_t)SW_ASC;
+            const uint32_t avail = remain < (uint64_t)asc_n ? (uint32_t)remain : asc_n;
             const uint32_t nbulk = avail & ~15u;
-            if (avail < (uint32_t)SW_ASC)
-                for (uint32_t i = nbulk + lane; i < (uint32_t)SW_ASC + 16; i += 32) S.asc[i] = (i < avail) ? A.bases[T0 + i] : (uint8_t)0;
+            if (avail < asc_n)
+                for (uint32_t i = nbulk + lane; i < asc_n + 16; i += 32) S.asc[i] = (i < avail) ? A.bases[T0 + i] : (uint8_t)0;
             __syncwarp();
             if (lane == 0) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(nbulk) : "memory");
@@ -238,10 +248,10 @@ k_seed_w(const SeedWArgs A) {
         } else {
             const uint64_t w0 = T0 >> 4, n_words = (A.n_bases + 15) >> 4;
             const uint64_t remain = n_words - w0;
-            const uint32_t avail = remain < (uint64_t)SW_NCHP ? (uint32_t)remain : (uint32_t)SW_NCHP;
+            const uint32_t avail = remain < (uint64_t)nchp ? (uint32_t)remain : nchp;
             const uint32_t nbulk = avail & ~3u;  // whole 16-byte groups
-            if (avail < (uint32_t)SW_NCHP)
-                for (uint32_t i = nbulk + lane; i < (uint32_t)SW_NCHP; i += 32)
+            if (avail < nchp)
+                for (uint32_t i = nbulk + lane; i < nchp; i += 32)
                     reinterpret_cast<uint32_t *>(S.asc)[i] = (i < avail) ? A.packed[w0 + i] : 0u;
             __syncwarp();
             if (lane == 0) {
@@ -264,7 +274,7 @@ k_seed_w(const SeedWArgs A) {
         // claim the next tile now; the atomic's result is only needed after the pack phase
         unsigned long long tn_l0 = 0;
         if (lane == 0) tn_l0 = atomicAdd(A.g_tile, 1ull);
-        const uint64_t T0 = t * (uint64_t)SW_TW, T1 = T0 + SW_TW;
+        const uint64_t T0 = t * (uint64_t)A.tw, T1 = T0 + A.tw;
         {   // wait for the bulk copy of tile t
             uint32_t done = 0;
             while (!done) {
@@ -275,7 +285,7 @@ k_seed_w(const SeedWArgs A) {
         }
         if (!PACKED) {
             // pack: 16 ASCII bytes -> one forward word (MSB-first) + one complement word (LSB-first); see k_seed
-            for (int ch = lane; ch < SW_NCH; ch += 32) {
+            for (int ch = lane; ch < nch; ch += 32) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(S.asc + 16 * ch);
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                 uint32_t g[4];
@@ -294,7 +304,7 @@ k_seed_w(const SeedWArgs A) {
             }
         } else {
             // forward stream = the staged words; complement stream: reverse the 16 fields of a word, complement
-            for (int ch = lane; ch < SW_NCHP; ch += 32) {
+            for (int ch = lane; ch < (int)nchp; ch += 32) {
                 const uint32_t f = reinterpret_cast<const uint32_t *>(S.asc)[ch];
                 uint32_t x = __brev(f);
                 x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);

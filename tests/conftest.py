@@ -21,13 +21,13 @@ def ctx():
 
 
 SEED_MODES = {
-    # default kernels: warp-autonomous persistent seeding kernel; host inputs of syl_sketch_reads are packed to
-    # 2 bits by the worker pool and shipped in tiny chunks (many chunks, every staging slot recycled)
-    "warp+packed-ingest": {"SYL_INGEST_CHUNK": "8192"},
-    # the same kernel fed ASCII from the host (1 byte per base over PCIe)
-    "warp+ascii-ingest": {"SYL_HOST_INGEST": "ascii"},
-    # round-1 kernel (one 32K tile per CTA)
-    "cta+ascii-ingest": {"SYL_SEED_IMPL": "cta", "SYL_HOST_INGEST": "ascii"},
+    # defaults: CTA-tile kernel for ASCII device input; host inputs of syl_sketch_reads are packed to 2 bits by the
+    # worker pool (warp kernel, packed variant) and shipped in tiny chunks (many chunks, every staging slot recycled)
+    "default+packed-ingest": {"SYL_INGEST_CHUNK": "8192"},
+    # warp-autonomous persistent kernel on ASCII input, fed ASCII from the host (1 byte per base over PCIe)
+    "warp+ascii-ingest": {"SYL_SEED_IMPL": "warp", "SYL_HOST_INGEST": "ascii"},
+    # CTA-tile kernel everywhere it can run
+    "cta+ascii-ingest": {"SYL_HOST_INGEST": "ascii"},
 }
 
 

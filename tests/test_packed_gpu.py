@@ -93,3 +93,24 @@ def test_host_ingest_chunk_ring(ctx, monkeypatch):
         s = ctx.sketch_sequences(buf, off, c=11)
         h, c = s.download()
         assert np.array_equal(h, eh) and np.array_equal(c, ec) and s.num_dup_removed == nd, chunk
+
+
+@pytest.mark.parametrize("tw", [64, 128, 1024, 3072])
+def test_warp_tile_lengths(ctx, monkeypatch, tw):
+    """The launcher sizes the warp-tile from the mean record length; force odd lengths so that tile edges fall
+    everywhere inside records, halos and pair-key windows (ASCII and packed input, survivors and read sketches)."""
+    from oracle import oracle as O
+    from sylph_b200.api import pack2
+    monkeypatch.setenv("SYL_SEED_TW", str(tw))
+    monkeypatch.setenv("SYL_SEED_IMPL", "warp")
+    rng = np.random.default_rng(100 + tw)
+    lengths = list(rng.integers(0, 420, size=1500)) + [5000, 31, 32, 61, 62, 66]
+    buf, off = random_records(rng, [lengths[i] for i in rng.permutation(len(lengths))], alphabet=b"ACGTNacgt\x00\x03")
+    exp = sorted(oracle_survivors(buf, off, 31, 7, 1, True))
+    for packed in (False, True):
+        sv = survivors_packed(ctx, buf, off, 31, 7, 1, True, False) if packed else ctx.extract_markers_batch(buf, off, k=31, c=7, with_pos=True)
+        assert sorted((int(a), int(b), int(h)) for h, a, b in zip(sv["hash"], sv["rec"], sv["pos"])) == exp
+    eh, ec, _, nd = O.sketch_reads(buf, off, c=7)
+    for s in (ctx.sketch_sequences(buf, off, c=7), ctx.sketch_sequences(pack2(buf), off, c=7, packed_bases=len(buf))):
+        h, c = s.download()
+        assert np.array_equal(h, eh) and np.array_equal(c, ec) and s.num_dup_removed == nd
