@@ -256,6 +256,38 @@ int syl_query(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, 
 int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
                 const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows);
 
+/* ------------------------------------------------------------------------------------------
+ * (5) `profile` over a genome-SHARDED database (one process per GPU; src/contain.rs:284-334 is the loop
+ *     that is sharded).  Every rank holds a db built with its genome_base and ALL samples.  The library
+ *     enqueues the compute stages on the ctx stream; the caller issues the three fixed-size collectives
+ *     between them on the same stream (NCCL; no host synchronisation in between):
+ *
+ *       syl_profile_shard_begin      pass 1 on the shard -> d_table1 (header + rows_per_rank rows)
+ *       all_gather(d_gathered1 <- d_table1)                         [world x table_bytes bytes]
+ *       syl_profile_shard_rank       order of every pass-1 survivor; per sample key the best order
+ *                                    among this shard's genomes -> d_winner (int32[winner_elems])
+ *       all_reduce(d_winner, MIN)                                   [int32]
+ *       syl_profile_shard_pass2      pass 2 (lost k-mers vs the global winner), bootstrap -> d_table2
+ *       all_gather(d_gathered2 <- d_table2)
+ *       syl_profile_shard_finish     the call's one host sync: derep, abundances, per-sample order; every
+ *                                    rank returns the same rows (row.genome = global genome index)
+ *
+ *     SYL_ERR_CAPACITY from finish: redo with rows_per_rank >= *need_rows_per_rank (same verdict on every
+ *     rank).  SYL_ERR_UNSUPPORTED: a k-mer count >= 256 was met (every rank sees it); use the gathered-
+ *     survivor path (sylph_b200/dist.py profile_sharded_gather).  world == 1 is allowed (no collectives).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct syl_profile_job syl_profile_job;
+int syl_profile_shard_begin(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+                            const syl_contain_params *p, uint32_t world, uint32_t rank, uint64_t rows_per_rank,
+                            syl_profile_job **out);
+int syl_profile_job_buffers(const syl_profile_job *job, void **d_table1, void **d_gathered1, uint64_t *table_bytes,
+                            void **d_winner, uint64_t *winner_elems, void **d_table2, void **d_gathered2);
+int syl_profile_shard_rank(syl_profile_job *job);
+int syl_profile_shard_pass2(syl_profile_job *job);
+int syl_profile_shard_finish(syl_profile_job *job, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows,
+                             uint64_t *need_rows_per_rank);
+void syl_profile_job_free(syl_profile_job *job);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,12 @@ SIGNATURES = {
     "syl_contain_params_default": (None, [C.POINTER(ContainParams), _i, _i]),
     "syl_query": (_i, [_vp, _vp, _pp, _u32, C.POINTER(ContainParams), _vp, _u64, _pu64]),
     "syl_profile": (_i, [_vp, _vp, _pp, _u32, C.POINTER(ContainParams), _vp, _u64, _pu64]),
+    "syl_profile_shard_begin": (_i, [_vp, _vp, _pp, _u32, C.POINTER(ContainParams), _u32, _u32, _u64, _pp]),
+    "syl_profile_job_buffers": (_i, [_vp, _pp, _pp, _pu64, _pp, _pu64, _pp, _pp]),
+    "syl_profile_shard_rank": (_i, [_vp]),
+    "syl_profile_shard_pass2": (_i, [_vp]),
+    "syl_profile_shard_finish": (_i, [_vp, _vp, _u64, _pu64, _pu64]),
+    "syl_profile_job_free": (None, [_vp]),
 }
 
 

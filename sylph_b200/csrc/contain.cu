@@ -65,6 +65,16 @@ struct StatParams {
     double min_number_kmers, min_count_correct, min_ani;
 };
 
+// Extras of the device-driven profile (contain_fast below): pass 1 records the containment count of every
+// emitted row in a dense table; pass 2 stashes it (and the genome size) in the row for the host-side
+// derep / abundance step, which then needs nothing but the rows.
+struct StatExtra {
+    uint32_t *contain1_out = nullptr;       // [S x G], pass 1
+    const uint32_t *contain1_in = nullptr;  // [S x G], pass 2 -> row.reserved
+    const uint64_t *gn_size = nullptr;      // [G], pass 2 -> row.seq_abund
+    uint64_t pair_stride = 0;               // G
+};
+
 // ---- index build ----------------------------------------------------------------------------
 
 __global__ void k_db_entries(const uint64_t *__restrict__ kmers, const uint64_t *__restrict__ kmer_off,
@@ -211,7 +221,8 @@ __device__ __forceinline__ void stats_emit(uint32_t sample_idx, uint64_t g, uint
                                            uint32_t nz, const uint32_t *hist, const uint32_t *lost, uint32_t genome_base,
                                            const StatParams &P, int pass2, syl_ani_row *__restrict__ rows, uint64_t rows_cap,
                                            uint32_t *__restrict__ boot_rows, uint32_t *__restrict__ hist_out, uint64_t boot_cap,
-                                           unsigned long long *__restrict__ n_rows, unsigned long long *__restrict__ n_boot) {
+                                           unsigned long long *__restrict__ n_rows, unsigned long long *__restrict__ n_boot,
+                                           const StatExtra X = StatExtra()) {
     const double k = (double)P.k;
     const uint64_t nfull = (uint64_t)(gl - n) + nz;
     const double naive_ani = pow((double)n / (double)gl, 1. / k);
@@ -251,8 +262,9 @@ __device__ __forceinline__ void stats_emit(uint32_t sample_idx, uint64_t g, uint
     r.lambda = has_lambda ? lam : 0.;
     r.ci[0] = r.ci[1] = r.ci[2] = r.ci[3] = 0.;
     r.rel_abund = 0.;
-    r.seq_abund = 0.;
-    r.reserved = 0.;
+    r.seq_abund = X.gn_size ? (double)X.gn_size[g] : 0.;
+    r.reserved = X.contain1_in ? (double)X.contain1_in[(uint64_t)sample_idx * X.pair_stride + g] : 0.;
+    if (X.contain1_out) X.contain1_out[(uint64_t)sample_idx * X.pair_stride + g] = n;
     const unsigned long long ri = atomicAdd(n_rows, 1ull);  // compact output; the host orders rows
     if (ri >= rows_cap) return;
     rows[ri] = r;
@@ -489,7 +501,7 @@ k_stats_hist(const uint8_t *__restrict__ touched, const uint32_t *__restrict__ c
              const uint32_t *__restrict__ glen, const uint32_t *__restrict__ lost, uint64_t n_genomes, uint64_t n_pairs,
              uint32_t genome_base, StatParams P, int pass2, syl_ani_row *__restrict__ rows, uint64_t rows_cap,
              uint32_t *__restrict__ boot_rows, uint32_t *__restrict__ hist_out, uint64_t boot_cap,
-             unsigned long long *__restrict__ n_rows, unsigned long long *__restrict__ n_boot) {
+             unsigned long long *__restrict__ n_rows, unsigned long long *__restrict__ n_boot, const StatExtra X = StatExtra()) {
     __shared__ uint32_t s_hist[STAT_WARPS][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint64_t pair = (uint64_t)blockIdx.x * STAT_WARPS + w;
@@ -549,7 +561,7 @@ k_stats_hist(const uint8_t *__restrict__ touched, const uint32_t *__restrict__ c
     __syncwarp();
     if (lane != 0) return;
     stats_emit(sample_idx, g, n, gl, median, sum, nz, hist, lost, genome_base, P, pass2, rows, rows_cap, boot_rows, hist_out,
-               boot_cap, n_rows, n_boot);
+               boot_cap, n_rows, n_boot, X);
 }
 
 // ---- bootstrap (src/contain.rs:849-898) -------------------------------------------------------
@@ -563,18 +575,26 @@ __device__ __forceinline__ uint64_t wyrand_at(uint64_t seed, uint64_t d) {
 constexpr int BOOT_ITERS = 100;
 constexpr int BOOT_THREADS = 256;
 
-// grid (BOOT_ITERS, n_boot): one CTA resamples |full| values for one iteration of one row.
+// 64 x 64 -> 128-bit product, xor of the two halves (WyRand's output function): four 32 x 32 -> 64
+// multiplies with 64-bit accumulate (IMAD.WIDE), no duplicated partial products.
+__device__ __forceinline__ uint64_t mum_xor(uint64_t a, uint64_t b) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    const uint64_t p00 = (uint64_t)a0 * b0;
+    const uint64_t m1 = (uint64_t)a0 * b1 + (p00 >> 32);            // < 2^64: (2^32-1)^2 + 2^32 - 1
+    const uint64_t m2 = (uint64_t)a1 * b0 + (uint32_t)m1;
+    const uint64_t hi = (uint64_t)a1 * b1 + (m1 >> 32) + (m2 >> 32);
+    const uint64_t lo = (m2 << 32) | (uint32_t)p00;
+    return lo ^ hi;
+}
+
+// One CTA resamples |full| values for one iteration `it` of one bootstrapped row.
 // H layout per row: [0] = number of zeros, [v] = #values == v (v = 1..16; all values of a
 // bootstrapped row are <= 15 because its median is <= 2).  ratio_lambda / ani_from_lambda only
 // need the histogram of the NON-ZERO resampled values and the total, so zero draws (the large
 // majority) cost nothing beyond the RNG.
-__global__ void __launch_bounds__(BOOT_THREADS)
-k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
-            double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
-            uint32_t *__restrict__ reject_flag) {
-    __shared__ uint32_t Hb[17];
-    __shared__ uint64_t cum[17];
-    const uint32_t row = blockIdx.y, it = blockIdx.x;
+__device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32_t *__restrict__ hist_in, const StatParams &P,
+                                         double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
+                                         uint32_t *__restrict__ reject_flag, uint32_t *Hb, uint64_t *cum) {
     const uint32_t *H = hist_in + (uint64_t)row * 17;
     if (threadIdx.x < 17) Hb[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
@@ -590,8 +610,7 @@ k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
     uint64_t s = 7ull + ((uint64_t)it * n + threadIdx.x + 1) * 0x2d358dccaa6c78a5ull;
     const uint64_t s_step = (uint64_t)BOOT_THREADS * 0x2d358dccaa6c78a5ull;
     for (uint32_t j = threadIdx.x; j < n32; j += BOOT_THREADS, s += s_step) {
-        const uint64_t tt = s ^ 0x8bb84b93962eacc9ull;
-        const uint64_t x = (s * tt) ^ __umul64hi(s, tt);
+        const uint64_t x = mum_xor(s, s ^ 0x8bb84b93962eacc9ull);
         // fastrand gen_mod_u64 (Lemire): hi = (x*n) >> 64, lo = (x*n) mod 2^64, with n < 2^32
         const uint64_t a = (uint64_t)(uint32_t)x * n32;                 // x_lo * n
         const uint64_t b = (x >> 32) * n32 + (a >> 32);                 // x_hi * n + carry
@@ -613,36 +632,63 @@ k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
             }
         }
     }
-    n1 += __shfl_xor_sync(0xffffffffu, n1, 16); n2 += __shfl_xor_sync(0xffffffffu, n2, 16); n3 += __shfl_xor_sync(0xffffffffu, n3, 16);
-    n1 += __shfl_xor_sync(0xffffffffu, n1, 8);  n2 += __shfl_xor_sync(0xffffffffu, n2, 8);  n3 += __shfl_xor_sync(0xffffffffu, n3, 8);
-    n1 += __shfl_xor_sync(0xffffffffu, n1, 4);  n2 += __shfl_xor_sync(0xffffffffu, n2, 4);  n3 += __shfl_xor_sync(0xffffffffu, n3, 4);
-    n1 += __shfl_xor_sync(0xffffffffu, n1, 2);  n2 += __shfl_xor_sync(0xffffffffu, n2, 2);  n3 += __shfl_xor_sync(0xffffffffu, n3, 2);
-    n1 += __shfl_xor_sync(0xffffffffu, n1, 1);  n2 += __shfl_xor_sync(0xffffffffu, n2, 1);  n3 += __shfl_xor_sync(0xffffffffu, n3, 1);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        n1 += __shfl_xor_sync(0xffffffffu, n1, d); n2 += __shfl_xor_sync(0xffffffffu, n2, d); n3 += __shfl_xor_sync(0xffffffffu, n3, d);
+    }
     if ((threadIdx.x & 31) == 0) {
         if (n1) atomicAdd(&Hb[1], n1);
         if (n2) atomicAdd(&Hb[2], n2);
         if (n3) atomicAdd(&Hb[3], n3);
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    uint32_t nz = 0;
-    for (int v = 1; v <= 16; v++) nz += Hb[v];
-    RatioOut r = ratio_lambda_hist(Hb, nz, P.min_count_correct);
-    double ani = 0.;
-    bool ok = r.ok && ani_from_lambda_dev(r.lambda, (double)P.k, nz, n, &ani);
-    ok = ok && !isnan(ani) && !isnan(r.lambda);
-    const uint64_t o = (uint64_t)row * BOOT_ITERS + it;
-    res_ani[o] = ani;
-    res_lambda[o] = r.lambda;
-    res_ok[o] = ok ? 1 : 0;
+    if (threadIdx.x == 0) {
+        uint32_t nz = 0;
+        for (int v = 1; v <= 16; v++) nz += Hb[v];
+        RatioOut r = ratio_lambda_hist(Hb, nz, P.min_count_correct);
+        double ani = 0.;
+        bool ok = r.ok && ani_from_lambda_dev(r.lambda, (double)P.k, nz, n, &ani);
+        ok = ok && !isnan(ani) && !isnan(r.lambda);
+        const uint64_t o = (uint64_t)row * BOOT_ITERS + it;
+        res_ani[o] = ani;
+        res_lambda[o] = r.lambda;
+        res_ok[o] = ok ? 1 : 0;
+    }
+}
+
+// grid (BOOT_ITERS, n_boot): host-side row count
+__global__ void __launch_bounds__(BOOT_THREADS)
+k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
+            double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
+            uint32_t *__restrict__ reject_flag) {
+    __shared__ uint32_t Hb[17];
+    __shared__ uint64_t cum[17];
+    boot_one(blockIdx.y, blockIdx.x, hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum);
+}
+
+// persistent form: the number of bootstrapped rows is read from device memory (no host round trip
+// between the statistics kernel and the bootstrap); CTAs stride over the (row, iteration) items
+__global__ void __launch_bounds__(BOOT_THREADS)
+k_boot_iter_p(const uint32_t *__restrict__ hist_in, const unsigned long long *__restrict__ d_nboot, uint64_t boot_cap, StatParams P,
+              double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
+              uint32_t *__restrict__ reject_flag) {
+    __shared__ uint32_t Hb[17];
+    __shared__ uint64_t cum[17];
+    const uint64_t nb = *d_nboot < boot_cap ? *d_nboot : boot_cap;
+    for (uint64_t item = blockIdx.x; item < nb * BOOT_ITERS; item += gridDim.x) {
+        boot_one((uint32_t)(item / BOOT_ITERS), (uint32_t)(item % BOOT_ITERS), hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum);
+        __syncthreads();  // Hb / cum are rewritten by the next item
+    }
 }
 
 // Exact sequential replay for a row whose counter-based draws hit Lemire's rejection branch
 // (the redraw shifts the RNG stream). One thread per flagged row; practically never runs.
 __global__ void k_boot_seq(const uint32_t *__restrict__ hist_in, uint32_t n_boot,
                            StatParams P, const uint32_t *__restrict__ reject_flag, double *__restrict__ res_ani,
-                           double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok) {
+                           double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
+                           const unsigned long long *__restrict__ d_nboot = nullptr) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_nboot && (unsigned long long)n_boot > *d_nboot) n_boot = (uint32_t)*d_nboot;  // n_boot = capacity then
     if (row >= n_boot || !reject_flag[row]) return;
     const uint32_t *H = hist_in + (uint64_t)row * 17;
     uint64_t cum[17], acc = 0;
@@ -689,10 +735,11 @@ __global__ void k_boot_seq(const uint32_t *__restrict__ hist_in, uint32_t n_boot
 __global__ void __launch_bounds__(128)
 k_boot_final(const uint32_t *__restrict__ boot_rows, uint32_t n_boot, const double *__restrict__ res_ani,
              const double *__restrict__ res_lambda, const uint8_t *__restrict__ res_ok,
-             syl_ani_row *__restrict__ rows) {
+             syl_ani_row *__restrict__ rows, const unsigned long long *__restrict__ d_nboot = nullptr) {
     __shared__ double a[BOOT_ITERS], l[BOOT_ITERS];
     __shared__ int s_suc;
     const uint32_t row = blockIdx.x;
+    if (d_nboot && (unsigned long long)n_boot > *d_nboot) n_boot = (uint32_t)*d_nboot;  // n_boot = capacity then
     if (row >= n_boot) return;
     const int t = threadIdx.x;
     if (t == 0) {  // compact the successful iterations (order is irrelevant for rank selection)
@@ -786,7 +833,7 @@ static int scratch_init(syl_ctx *ctx, const syl_db *db, const syl_sample *const 
     SYL_TRY(S.boot_rows.alloc(S.boot_cap, st));
     SYL_TRY(S.hist.alloc(S.boot_cap * 17, st));
     SYL_TRY(S.covs.alloc(1 << 16, st));
-    static const bool force_csr = getenv("SYL_CONTAIN_CSR") != nullptr;  // testing: always take the CSR formulation
+    const bool force_csr = getenv("SYL_CONTAIN_CSR") != nullptr;  // testing: always take the CSR formulation (read per call)
     S.use_hist = !force_csr && S.P * COV_BINS * 4 <= (8ull << 30);
     if (S.use_hist) { SYL_TRY(S.chist.alloc(S.P * COV_BINS, st)); SYL_TRY(S.touched.alloc(S.P, st)); }
     if (S.use_hist && need_pass2 && S.max_n) SYL_TRY(S.hits.alloc(S.S * S.max_n, st));
@@ -936,6 +983,425 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
     return SYL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-driven query / profile ("fast path"): both get_stats passes, the winner decision and the
+// bootstrap are enqueued back to back; the host synchronises ONCE, when it reads the final rows.
+//   pass 1      k_join_hist<pass 1> + k_stats_hist -> rows appended to a per-rank ROW TABLE
+//               (header {n_rows, n_boot, overflow} + R rows of 144 bytes, R fixed per call)
+//   [N ranks: the caller all-gathers the row tables — collective 1]
+//   ranking     k_rank_rows: every pass-1 survivor gets its position in the per-sample order
+//               (final_est_ani descending, genome index ascending) — the reference's winner_table
+//               (src/contain.rs:410-430) keeps, for every k-mer, the genome that comes first in that
+//               order; ties go to the lowest genome index (its own tie winner is timing dependent)
+//   winner      k_local_best: per sample key, the smallest order among the genomes (kept or tracked
+//               k-mers) of its equal range in THIS shard
+//   [N ranks: the caller all-reduces (MIN) the winner array — collective 2]
+//   pass 2      k_join2_order (hit counts / lost k-mers against the winner) + k_stats_hist + bootstrap
+//   [N ranks: the caller all-gathers the pass-2 row tables — collective 3]
+//   finish      D2H of the table(s), derep_if_reassign_threshold (:353-375), abundances (:319-326), sort
+// Single GPU: the winner minimum is taken inside k_join2_order and nothing is gathered.  A coverage
+// count >= COV_BINS or more rows than the table holds is reported in the header; the caller then
+// redoes the call on the synchronous path above (CSR formulation) or with a larger table.
+constexpr uint32_t ORD_NONE = 0x7F7F7F7Fu;  // memset-able; valid as int32 for the MIN all-reduce
+
+struct ShardTable { unsigned long long n_rows, n_boot, ovf, pad; };
+static_assert(sizeof(ShardTable) == 32, "table header");
+static inline size_t table_bytes(uint64_t R) { return sizeof(ShardTable) + R * sizeof(syl_ani_row); }
+__host__ __device__ static inline syl_ani_row *table_rows(void *t) { return reinterpret_cast<syl_ani_row *>(reinterpret_cast<uint8_t *>(t) + sizeof(ShardTable)); }
+
+// order of every pass-1 row inside its sample; rows of this rank also land in the dense order table.
+// `tabs`: `world` tables of `tbytes` bytes each (R rows capacity, R a multiple of 256)
+__global__ void __launch_bounds__(256)
+k_rank_rows(const uint8_t *__restrict__ tabs, uint64_t tbytes, uint32_t world, uint32_t R, uint32_t rank, uint64_t G,
+            uint32_t genome_base, uint32_t *__restrict__ order_tbl) {
+    __shared__ uint32_t s_smp[256], s_gen[256];
+    __shared__ double s_ani[256];
+    const uint64_t total = (uint64_t)world * R;
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    bool valid = false;
+    uint32_t ms = 0, mg = 0, mr = 0;
+    double ma = 0.;
+    if (i < total) {
+        mr = (uint32_t)(i / R);
+        const uint32_t idx = (uint32_t)(i % R);
+        const ShardTable *t = reinterpret_cast<const ShardTable *>(tabs + (uint64_t)mr * tbytes);
+        if (idx < t->n_rows) {
+            const syl_ani_row *row = reinterpret_cast<const syl_ani_row *>(reinterpret_cast<const uint8_t *>(t) + sizeof(ShardTable)) + idx;
+            valid = true; ms = row->sample; mg = row->genome; ma = row->final_est_ani;
+        }
+    }
+    uint32_t ord = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        const ShardTable *t = reinterpret_cast<const ShardTable *>(tabs + (uint64_t)r * tbytes);
+        const uint32_t n = t->n_rows < R ? (uint32_t)t->n_rows : R;
+        const syl_ani_row *rows = reinterpret_cast<const syl_ani_row *>(reinterpret_cast<const uint8_t *>(t) + sizeof(ShardTable));
+        for (uint32_t base = 0; base < n; base += 256) {  // uniform trip count
+            const uint32_t j = base + threadIdx.x;
+            if (j < n) { s_smp[threadIdx.x] = rows[j].sample; s_gen[threadIdx.x] = rows[j].genome; s_ani[threadIdx.x] = rows[j].final_est_ani; }
+            else s_smp[threadIdx.x] = 0xFFFFFFFFu;
+            __syncthreads();
+            if (valid) {
+                const uint32_t m = min(256u, n - base);
+                for (uint32_t q = 0; q < m; q++)
+                    ord += (s_smp[q] == ms && (s_ani[q] > ma || (s_ani[q] == ma && s_gen[q] < mg))) ? 1u : 0u;
+            }
+            __syncthreads();
+        }
+    }
+    if (valid && mr == rank) order_tbl[(uint64_t)ms * G + (mg - genome_base)] = ord;
+}
+
+// per sample key: smallest order among the survivor genomes of its equal range in this shard (kept and
+// tracked k-mers both count, src/contain.rs:416-426)
+__global__ void k_local_best(const SampleView *__restrict__ views, uint64_t G, const uint32_t *__restrict__ gid,
+                             const uint2 *__restrict__ hits, uint64_t hits_stride, const uint32_t *__restrict__ order_tbl,
+                             uint32_t *__restrict__ wbest) {
+    const SampleView sv = views[blockIdx.y];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n) return;
+    const uint2 h = hits[(uint64_t)blockIdx.y * hits_stride + i];
+    uint32_t best = ORD_NONE;
+    const uint32_t *ord = order_tbl + (uint64_t)blockIdx.y * G;
+    for (uint32_t j = h.x; j < h.x + h.y; j++) best = min(best, ord[gid[j] >> 1]);
+    wbest[(uint64_t)blockIdx.y * hits_stride + i] = best;
+}
+
+// pass 2 over the equal ranges recorded by pass 1.  FUSED: the winner (smallest order in the range) is
+// taken here (single GPU); else it comes from wbest (all-reduced over the shards).
+template <bool FUSED>
+__global__ void k_join2_order(const SampleView *__restrict__ views, uint64_t G, const uint32_t *__restrict__ gid,
+                              const uint2 *__restrict__ hits, uint64_t hits_stride, const uint32_t *__restrict__ order_tbl,
+                              const uint32_t *__restrict__ wbest, uint8_t *__restrict__ touched, uint32_t *__restrict__ lost,
+                              uint32_t *__restrict__ chist, unsigned long long *__restrict__ ovf) {
+    const SampleView sv = views[blockIdx.y];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n) return;
+    const uint2 h = hits[(uint64_t)blockIdx.y * hits_stride + i];
+    if (h.y == 0) return;
+    const uint64_t row = (uint64_t)blockIdx.y * G;
+    const uint32_t *ord = order_tbl + row;
+    const uint32_t lo = h.x, e = h.x + h.y, c = sv.count[i];
+    uint32_t winner;
+    if (FUSED) {
+        winner = ORD_NONE;
+        for (uint32_t j = lo; j < e; j += 4) {
+            uint32_t gq[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) gq[q] = j + q < e ? gid[j + q] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (j + q < e) winner = min(winner, ord[gq[q] >> 1]);
+        }
+    } else {
+        winner = wbest[(uint64_t)blockIdx.y * hits_stride + i];
+    }
+    if (winner == ORD_NONE) return;  // no survivor holds this k-mer
+    for (uint32_t j = lo; j < e; j += 4) {
+        uint32_t gq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) gq[q] = j + q < e ? gid[j + q] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j + q >= e) continue;
+            const uint32_t gv = gq[q];
+            if (gv & 1u) continue;  // tracked k-mers only take part in the winner decision
+            const uint32_t g = gv >> 1;
+            const uint32_t o = ord[g];
+            if (o == ORD_NONE) continue;                       // not a pass-1 survivor
+            if (o != winner) { atomicAdd(&lost[row + g], 1u); continue; }  // src/contain.rs:641-646
+            if (!touched[row + g]) touched[row + g] = 1;
+            if (c < COV_BINS) atomicAdd(&chist[(row + g) * COV_BINS + c], 1u);
+            else atomicAdd(ovf, 1ull);
+        }
+    }
+}
+
+}  // namespace syl
+
+// One in-flight device-driven query / profile (C ABI: syl_profile_job).
+struct syl_profile_job {
+    syl_ctx *ctx = nullptr;
+    const syl_db *db = nullptr;
+    syl::StatParams P;       // pass-2 / query parameters
+    bool profile = true;
+    double redundant_ani = 99.;
+    uint32_t S = 0, world = 1, rank = 0;
+    uint64_t G = 0, R = 0, max_n = 0, tbytes = 0;
+    int stage = 0;           // 1 pass 1 enqueued, 2 ranked, 3 pass 2 enqueued
+    syl::DevBuf<syl::SampleView> views;
+    syl::DevBuf<uint8_t> touched, tab1, gat1, tab2, gat2, res_ok;
+    syl::DevBuf<uint32_t> chist, lost, order, contain1, wbest, boot_rows, hist, reject;
+    syl::DevBuf<uint2> hits;
+    syl::DevBuf<double> res_ani, res_lambda;
+    syl::DevBuf<uint64_t> gn_size;
+    std::vector<uint8_t> h_tab;
+};
+
+namespace syl {
+
+static void job_release(syl_profile_job *j) {
+    if (!j) return;
+    syl_ctx *prev = tl_ctx;
+    tl_ctx = j->ctx;  // the scratch blocks go back to the owning ctx's cache
+    delete j;
+    tl_ctx = prev;
+}
+
+static uint64_t default_rows_per_rank(uint32_t S, uint64_t G) {
+    uint64_t R = std::min<uint64_t>((uint64_t)S * G, 256 + 96ull * S);
+    return (std::max<uint64_t>(R, 256) + 255) & ~255ull;
+}
+
+// stage 1: allocate, pass 1 (P1 = the pass-1 parameters: profile skips the bootstrap there)
+static int job_begin(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+                     const syl_contain_params *p, bool profile, uint32_t world, uint32_t rank, uint64_t R, syl_profile_job **out) {
+    cudaStream_t st = ctx->stream;
+    syl_profile_job *j = new (std::nothrow) syl_profile_job();
+    if (!j) return SYL_ERR_OOM;
+    auto fail = [&](int rc) { job_release(j); return rc; };
+#define JOB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? SYL_ERR_OOM : SYL_ERR_CUDA); } } while (0)
+#define JOB_TRY(x) do { int _r = (x); if (_r != SYL_OK) return fail(_r); } while (0)
+    j->ctx = ctx; j->db = db; j->profile = profile; j->S = n_samples; j->G = db->n_genomes; j->world = world; j->rank = rank;
+    syl_contain_params pp = *p;
+    pp.pseudotax = profile ? 1 : 0;
+    j->P = make_params(&pp);
+    j->redundant_ani = pp.redundant_ani;
+    j->R = R ? ((R + 255) & ~255ull) : default_rows_per_rank(n_samples, db->n_genomes);
+    j->tbytes = table_bytes(j->R);
+    const uint64_t NP = (uint64_t)j->S * j->G;
+    if (NP >= 0x7FFFFFFFull) { set_error("samples x genomes exceeds 2^31 pairs per call; split the sample batch"); return fail(SYL_ERR_ARG); }
+    if (NP * COV_BINS * 4 > (8ull << 30)) { set_error("pair histograms exceed 8 GB; split the sample batch"); return fail(SYL_ERR_UNSUPPORTED); }
+    std::vector<SampleView> hv(n_samples);
+    for (uint32_t i = 0; i < n_samples; i++) {
+        hv[i] = {samples[i]->hash, samples[i]->count, samples[i]->n};
+        j->max_n = std::max<uint64_t>(j->max_n, samples[i]->n);
+    }
+    const uint64_t HN = std::max<uint64_t>((uint64_t)j->S * j->max_n, 1);
+    JOB_TRY(j->views.alloc(n_samples, st));
+    JOB_TRY(j->touched.alloc(NP, st)); JOB_TRY(j->chist.alloc(NP * COV_BINS, st)); JOB_TRY(j->hits.alloc(HN, st));
+    JOB_TRY(j->tab1.alloc(j->tbytes, st));
+    JOB_TRY(j->boot_rows.alloc(j->R, st)); JOB_TRY(j->hist.alloc(j->R * 17, st));
+    JOB_TRY(j->res_ani.alloc(j->R * BOOT_ITERS, st)); JOB_TRY(j->res_lambda.alloc(j->R * BOOT_ITERS, st));
+    JOB_TRY(j->res_ok.alloc(j->R * BOOT_ITERS, st)); JOB_TRY(j->reject.alloc(j->R, st));
+    if (profile) {
+        JOB_TRY(j->lost.alloc(NP, st)); JOB_TRY(j->order.alloc(NP, st)); JOB_TRY(j->contain1.alloc(NP, st));
+        JOB_TRY(j->tab2.alloc(j->tbytes, st)); JOB_TRY(j->gn_size.alloc(std::max<uint64_t>(j->G, 1), st));
+        if (world > 1) { JOB_TRY(j->gat1.alloc(j->tbytes * world, st)); JOB_TRY(j->wbest.alloc(HN, st)); }
+    }
+    if (world > 1) JOB_TRY(j->gat2.alloc(j->tbytes * world, st));  // final tables of all ranks (profile: pass 2; query: pass 1)
+    // a pageable source is staged by the driver before cudaMemcpyAsync returns: hv may go out of scope
+    JOB_CUDA(cudaMemcpyAsync(j->views.p, hv.data(), n_samples * sizeof(SampleView), cudaMemcpyHostToDevice, st));
+    if (profile && j->G) JOB_CUDA(cudaMemcpyAsync(j->gn_size.p, db->h_gn_size.data(), j->G * 8, cudaMemcpyHostToDevice, st));
+    JOB_CUDA(cudaMemsetAsync(j->touched.p, 0, NP, st));
+    JOB_CUDA(cudaMemsetAsync(j->chist.p, 0, NP * COV_BINS * 4, st));
+    JOB_CUDA(cudaMemsetAsync(j->hits.p, 0, HN * sizeof(uint2), st));
+    JOB_CUDA(cudaMemsetAsync(j->tab1.p, 0, sizeof(ShardTable), st));
+    ShardTable *t1 = reinterpret_cast<ShardTable *>(j->tab1.p);
+    const dim3 jgrid(nblk(std::max<uint64_t>(j->max_n, 1), 128), (unsigned)j->S);
+    if (j->max_n && db->N) {
+        KernelTimer kt(ctx, SYL_KERNEL_JOIN);
+        k_join_hist<false><<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->keys, db->gid, db->N, db->bstart, db->M, db->NB, db->maxkey,
+                                                  nullptr, nullptr, j->touched.p, nullptr, j->chist.p, &t1->ovf, j->hits.p, j->max_n);
+        ctx->launches++;
+    }
+    StatParams P1 = j->P;
+    if (profile) P1.no_ci = 1;  // pass-1 confidence intervals are never reported (pass-2 rows replace them)
+    StatExtra X;
+    X.pair_stride = j->G;
+    if (profile) X.contain1_out = j->contain1.p;
+    {
+        KernelTimer kt(ctx, SYL_KERNEL_STATS);
+        k_stats_hist<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(j->touched.p, j->chist.p, db->glen, nullptr, j->G, NP, db->genome_base, P1, 0,
+                                                                       table_rows(j->tab1.p), j->R, j->boot_rows.p, j->hist.p, j->R,
+                                                                       &t1->n_rows, &t1->n_boot, X);
+        ctx->launches++;
+    }
+    JOB_CUDA(cudaGetLastError());
+    j->stage = 1;
+    *out = j;
+    return SYL_OK;
+}
+
+// bootstrap of the rows listed in table `tab` (device-side count)
+static int job_bootstrap(syl_profile_job *j, void *tab) {
+    syl_ctx *ctx = j->ctx;
+    cudaStream_t st = ctx->stream;
+    if (j->P.no_ci) return SYL_OK;
+    ShardTable *t = reinterpret_cast<ShardTable *>(tab);
+    SYL_CUDA(cudaMemsetAsync(j->reject.p, 0, (size_t)j->R * 4, st));
+    KernelTimer kt(ctx, SYL_KERNEL_BOOT);
+    k_boot_iter_p<<<ctx->num_sms * 8, BOOT_THREADS, 0, st>>>(j->hist.p, &t->n_boot, j->R, j->P, j->res_ani.p, j->res_lambda.p, j->res_ok.p, j->reject.p);
+    k_boot_seq<<<nblk(j->R, 32), 32, 0, st>>>(j->hist.p, (uint32_t)j->R, j->P, j->reject.p, j->res_ani.p, j->res_lambda.p, j->res_ok.p, &t->n_boot);
+    k_boot_final<<<(unsigned)j->R, 128, 0, st>>>(j->boot_rows.p, (uint32_t)j->R, j->res_ani.p, j->res_lambda.p, j->res_ok.p, table_rows(tab), &t->n_boot);
+    kt.stop();
+    ctx->launches += 3;
+    SYL_CUDA(cudaGetLastError());
+    return SYL_OK;
+}
+
+// stage 2 (profile): order of the survivors from the gathered pass-1 tables, local winner candidates
+static int job_rank(syl_profile_job *j) {
+    syl_ctx *ctx = j->ctx;
+    cudaStream_t st = ctx->stream;
+    const syl_db *db = j->db;
+    const uint64_t NP = (uint64_t)j->S * j->G;
+    SYL_CUDA(cudaMemsetAsync(j->order.p, 0x7F, NP * 4, st));
+    const uint8_t *tabs = j->world > 1 ? j->gat1.p : j->tab1.p;
+    k_rank_rows<<<nblk((uint64_t)j->world * j->R, 256), 256, 0, st>>>(tabs, j->tbytes, j->world, (uint32_t)j->R, j->rank, j->G, db->genome_base, j->order.p);
+    ctx->launches++;
+    if (j->world > 1) {
+        const dim3 jgrid(nblk(std::max<uint64_t>(j->max_n, 1), 128), (unsigned)j->S);
+        KernelTimer kt(ctx, SYL_KERNEL_JOIN2);
+        k_local_best<<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->gid, j->hits.p, j->max_n, j->order.p, j->wbest.p);
+        ctx->launches++;
+    }
+    SYL_CUDA(cudaGetLastError());
+    j->stage = 2;
+    return SYL_OK;
+}
+
+// stage 3 (profile): pass 2 against the (all-reduced) winners, statistics, bootstrap
+static int job_pass2(syl_profile_job *j) {
+    syl_ctx *ctx = j->ctx;
+    cudaStream_t st = ctx->stream;
+    const syl_db *db = j->db;
+    const uint64_t NP = (uint64_t)j->S * j->G;
+    ShardTable *t1 = reinterpret_cast<ShardTable *>(j->tab1.p), *t2 = reinterpret_cast<ShardTable *>(j->tab2.p);
+    SYL_CUDA(cudaMemsetAsync(j->touched.p, 0, NP, st));
+    SYL_CUDA(cudaMemsetAsync(j->lost.p, 0, NP * 4, st));
+    SYL_CUDA(cudaMemsetAsync(j->chist.p, 0, NP * COV_BINS * 4, st));
+    SYL_CUDA(cudaMemsetAsync(j->tab2.p, 0, sizeof(ShardTable), st));
+    const dim3 jgrid(nblk(std::max<uint64_t>(j->max_n, 1), 128), (unsigned)j->S);
+    if (j->max_n && db->N) {
+        KernelTimer kt(ctx, SYL_KERNEL_JOIN2);
+        if (j->world > 1)
+            k_join2_order<false><<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->gid, j->hits.p, j->max_n, j->order.p, j->wbest.p, j->touched.p,
+                                                        j->lost.p, j->chist.p, &t2->ovf);
+        else
+            k_join2_order<true><<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->gid, j->hits.p, j->max_n, j->order.p, nullptr, j->touched.p,
+                                                       j->lost.p, j->chist.p, &t2->ovf);
+        ctx->launches++;
+    }
+    StatExtra X;
+    X.pair_stride = j->G;
+    X.contain1_in = j->contain1.p;
+    X.gn_size = j->gn_size.p;
+    {
+        KernelTimer kt(ctx, SYL_KERNEL_STATS);
+        k_stats_hist<<<nblk(NP, STAT_WARPS), STAT_WARPS * 32, 0, st>>>(j->touched.p, j->chist.p, db->glen, j->lost.p, j->G, NP, db->genome_base, j->P, 1,
+                                                                       table_rows(j->tab2.p), j->R, j->boot_rows.p, j->hist.p, j->R,
+                                                                       &t2->n_rows, &t2->n_boot, X);
+        ctx->launches++;
+    }
+    SYL_CUDA(cudaGetLastError());
+    SYL_TRY(job_bootstrap(j, j->tab2.p));
+    // carry pass 1's overflow / row counts along, so that the final table tells the whole story
+    (void)t1;
+    j->stage = 3;
+    return SYL_OK;
+}
+
+// derep_if_reassign_threshold (src/contain.rs:353-375) + abundances (:319-326) + the output order (:329-334)
+// for the pass-2 rows of all shards: row.reserved = pass-1 containment count, row.seq_abund = genome size
+static void profile_finalize(std::vector<syl_ani_row> &r2, uint32_t n_samples, int k, double redundant_ani, std::vector<syl_ani_row> &all) {
+    std::sort(r2.begin(), r2.end(), [](const syl_ani_row &a, const syl_ani_row &b) {
+        return a.sample != b.sample ? a.sample < b.sample : a.genome < b.genome;
+    });
+    const double threshold = std::pow(redundant_ani / 100., (double)k);
+    size_t i2 = 0;
+    for (uint32_t smp = 0; smp < n_samples; smp++) {
+        std::vector<syl_ani_row> kept;
+        for (; i2 < r2.size() && r2[i2].sample == smp; i2++) {
+            const syl_ani_row &n2 = r2[i2];
+            const double num_reassign = (double)((uint64_t)n2.reserved - n2.contain);
+            const double reass_thresh = threshold * (double)n2.glen;
+            if (num_reassign < reass_thresh) kept.push_back(n2);
+        }
+        double total_cov = 0., total_seq_cov = 0.;
+        for (const syl_ani_row &r : kept) {
+            total_cov += r.final_est_cov;
+            total_seq_cov += r.final_est_cov * r.seq_abund;  // seq_abund still holds gn_size
+        }
+        for (syl_ani_row &r : kept) {
+            const double gs = r.seq_abund;
+            r.rel_abund = r.final_est_cov / total_cov * 100.;
+            r.seq_abund = r.final_est_cov * gs / total_seq_cov * 100. * 1.;
+            r.reserved = 0.;
+        }
+        std::stable_sort(kept.begin(), kept.end(),
+                         [](const syl_ani_row &a, const syl_ani_row &b) { return a.rel_abund > b.rel_abund; });
+        all.insert(all.end(), kept.begin(), kept.end());
+    }
+}
+
+// last stage: read the final table(s); SYL_ERR_CAPACITY: *need_R rows per rank are needed;
+// SYL_ERR_UNSUPPORTED: a coverage count >= COV_BINS somewhere (the caller takes the synchronous CSR path)
+static int job_finish(syl_profile_job *j, std::vector<syl_ani_row> &out, uint64_t *need_R) {
+    syl_ctx *ctx = j->ctx;
+    cudaStream_t st = ctx->stream;
+    *need_R = 0;
+    const uint32_t nt = j->world > 1 ? j->world : 1;
+    const uint8_t *src = j->world > 1 ? j->gat2.p : (j->profile ? j->tab2.p : j->tab1.p);
+    const uint8_t *src1 = (j->world > 1 && j->profile) ? j->gat1.p : j->tab1.p;  // pass-1 tables: only their headers matter here
+    const size_t bytes = j->tbytes * nt;
+    j->h_tab.resize(bytes + sizeof(ShardTable) * nt);
+    SYL_CUDA(cudaMemcpyAsync(j->h_tab.data(), src, bytes, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaMemcpy2DAsync(j->h_tab.data() + bytes, sizeof(ShardTable), src1, j->tbytes, sizeof(ShardTable),
+                               (j->world > 1 && j->profile) ? nt : 1, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaStreamSynchronize(st));  // the one synchronisation of the call
+    bool ovf = false;
+    uint64_t need = 0;
+    std::vector<syl_ani_row> rows;
+    for (uint32_t r = 0; r < ((j->world > 1 && j->profile) ? nt : 1); r++) {  // every rank reaches the same verdict
+        const ShardTable *h1 = reinterpret_cast<const ShardTable *>(j->h_tab.data() + bytes) + r;
+        ovf |= h1->ovf != 0;
+        need = std::max<uint64_t>(need, h1->n_rows);
+    }
+    for (uint32_t r = 0; r < nt; r++) {
+        const ShardTable *t = reinterpret_cast<const ShardTable *>(j->h_tab.data() + (size_t)r * j->tbytes);
+        ovf |= t->ovf != 0;
+        need = std::max<uint64_t>(need, std::max(t->n_rows, t->n_boot));
+        const syl_ani_row *tr = reinterpret_cast<const syl_ani_row *>(reinterpret_cast<const uint8_t *>(t) + sizeof(ShardTable));
+        for (uint64_t i = 0; i < std::min<uint64_t>(t->n_rows, j->R); i++) rows.push_back(tr[i]);
+    }
+    if (ovf) { set_error("coverage count >= 256: CSR formulation needed"); return SYL_ERR_UNSUPPORTED; }
+    if (need > j->R) { *need_R = need; set_error("row table too small"); return SYL_ERR_CAPACITY; }
+    if (j->profile) {
+        profile_finalize(rows, j->S, j->P.k, j->redundant_ani, out);
+    } else {
+        std::sort(rows.begin(), rows.end(), [](const syl_ani_row &a, const syl_ani_row &b) {
+            return a.sample != b.sample ? a.sample < b.sample : a.genome < b.genome;
+        });
+        out.swap(rows);
+    }
+    return SYL_OK;
+}
+
+// single-GPU driver of the stages; rc SYL_ERR_UNSUPPORTED = take the synchronous path
+static int contain_fast(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+                        const syl_contain_params *p, bool profile, std::vector<syl_ani_row> &out) {
+    uint64_t R = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        syl_profile_job *j = nullptr;
+        SYL_TRY(job_begin(ctx, db, samples, n_samples, p, profile, 1, 0, R, &j));
+        int rc = SYL_OK;
+        if (profile) {
+            rc = job_rank(j);
+            if (rc == SYL_OK) rc = job_pass2(j);
+        } else {
+            rc = job_bootstrap(j, j->tab1.p);
+        }
+        uint64_t need = 0;
+        if (rc == SYL_OK) rc = job_finish(j, out, &need);
+        job_release(j);
+        if (rc == SYL_ERR_CAPACITY) { R = need + 256; out.clear(); continue; }
+        return rc;
+    }
+    return SYL_ERR_CAPACITY;
+}
+
+// SYL_CONTAIN_CSR / SYL_CONTAIN_SYNC force the synchronous two-pass implementation (tests)
+static bool fast_path_enabled() { return getenv("SYL_CONTAIN_CSR") == nullptr && getenv("SYL_CONTAIN_SYNC") == nullptr; }
+
 static int check_pair_args(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
                            const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows) {
     if (!ctx || !db || !p || !n_rows || (n_samples && !samples) || (cap && !rows)) { set_error("NULL argument"); return SYL_ERR_ARG; }
@@ -1058,16 +1524,88 @@ int syl_query(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, 
     SYL_CUDA(cudaSetDevice(ctx->device));
     syl::tl_ctx = ctx;
     if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
+    std::vector<syl_ani_row> out;
+    if (fast_path_enabled()) {
+        const int frc = contain_fast(ctx, db, samples, n_samples, p, false, out);
+        if (frc == SYL_OK) {
+            *n_rows = out.size();
+            if (out.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
+            std::copy(out.begin(), out.end(), rows);
+            return SYL_OK;
+        }
+        if (frc != SYL_ERR_UNSUPPORTED) return frc;
+        out.clear();
+    }
     ContainScratch S;
     SYL_TRY(scratch_init(ctx, db, samples, n_samples, false, S));
     const StatParams P = make_params(p);
-    std::vector<syl_ani_row> out;
     SYL_TRY(contain_pass(ctx, db, P, false, S, out, false, nullptr));
     *n_rows = out.size();
     if (out.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
     std::copy(out.begin(), out.end(), rows);
     return SYL_OK;
 }
+
+int syl_profile_shard_begin(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
+                            const syl_contain_params *p, uint32_t world, uint32_t rank, uint64_t rows_per_rank,
+                            syl_profile_job **out) {
+    uint64_t dummy = 0;
+    if (!out) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    SYL_TRY(check_pair_args(ctx, db, samples, n_samples, p, nullptr, 0, &dummy));
+    if (world == 0 || rank >= world || n_samples == 0) { set_error("bad world / rank / sample count"); return SYL_ERR_ARG; }
+    if (!db->has_tracked) {  // src/contain.rs:231-234
+        set_error("Attempting profiling, but the database was sketched with the --disable-profiling option");
+        return SYL_ERR_ARG;
+    }
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
+    return job_begin(ctx, db, samples, n_samples, p, true, world, rank, rows_per_rank, out);
+}
+
+int syl_profile_job_buffers(const syl_profile_job *j, void **d_table1, void **d_gathered1, uint64_t *table_bytes,
+                            void **d_winner, uint64_t *winner_elems, void **d_table2, void **d_gathered2) {
+    if (!j) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    if (d_table1) *d_table1 = j->tab1.p;
+    if (d_gathered1) *d_gathered1 = j->gat1.p;
+    if (table_bytes) *table_bytes = j->tbytes;
+    if (d_winner) *d_winner = j->wbest.p;
+    if (winner_elems) *winner_elems = std::max<uint64_t>((uint64_t)j->S * j->max_n, 1);
+    if (d_table2) *d_table2 = j->tab2.p;
+    if (d_gathered2) *d_gathered2 = j->gat2.p;
+    return SYL_OK;
+}
+
+int syl_profile_shard_rank(syl_profile_job *j) {
+    if (!j || j->stage != 1 || !j->profile) { set_error("profile job: wrong stage"); return SYL_ERR_ARG; }
+    SYL_CUDA(cudaSetDevice(j->ctx->device));
+    syl::tl_ctx = j->ctx;
+    return job_rank(j);
+}
+
+int syl_profile_shard_pass2(syl_profile_job *j) {
+    if (!j || j->stage != 2) { set_error("profile job: wrong stage"); return SYL_ERR_ARG; }
+    SYL_CUDA(cudaSetDevice(j->ctx->device));
+    syl::tl_ctx = j->ctx;
+    return job_pass2(j);
+}
+
+int syl_profile_shard_finish(syl_profile_job *j, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows, uint64_t *need_rows_per_rank) {
+    if (!j || j->stage != 3 || !n_rows || (cap && !rows)) { set_error("profile job: wrong stage / NULL argument"); return SYL_ERR_ARG; }
+    SYL_CUDA(cudaSetDevice(j->ctx->device));
+    syl::tl_ctx = j->ctx;
+    std::vector<syl_ani_row> out;
+    uint64_t need = 0;
+    const int rc = job_finish(j, out, &need);
+    if (need_rows_per_rank) *need_rows_per_rank = need;
+    if (rc != SYL_OK) return rc;
+    *n_rows = out.size();
+    if (out.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
+    std::copy(out.begin(), out.end(), rows);
+    return SYL_OK;
+}
+
+void syl_profile_job_free(syl_profile_job *j) { job_release(j); }
 
 int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
                 const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows) {
@@ -1080,6 +1618,17 @@ int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples
     SYL_CUDA(cudaSetDevice(ctx->device));
     syl::tl_ctx = ctx;
     if (db->n_genomes == 0 || n_samples == 0) return SYL_OK;
+    if (fast_path_enabled()) {
+        std::vector<syl_ani_row> fout;
+        const int frc = contain_fast(ctx, db, samples, n_samples, p, true, fout);
+        if (frc == SYL_OK) {
+            *n_rows = fout.size();
+            if (fout.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
+            std::copy(fout.begin(), fout.end(), rows);
+            return SYL_OK;
+        }
+        if (frc != SYL_ERR_UNSUPPORTED) return frc;
+    }
     cudaStream_t st = ctx->stream;
     ContainScratch S;
     SYL_TRY(scratch_init(ctx, db, samples, n_samples, true, S));
