@@ -44,7 +44,7 @@ def sketch_config(args):
 def profile_config(args, world):
     n_samples = args.samples or (1 if world == 1 else 16)
     return {"workload": "profile %d sample sketch(es) vs %d synthetic 4 Mbp genome sketches per GPU (BASELINE.json configs[%d])"
-                        % (n_samples, args.genomes, 2 if world == 1 else 3),
+                        % (n_samples, args.genomes, 2 if n_samples == 1 else 3),
             "genomes_per_gpu": args.genomes, "samples": n_samples, "reads_per_sample": args.reads, "k": K, "c": C}
 
 
@@ -56,7 +56,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sketch", choices=["sketch", "profile"])
     ap.add_argument("--reads", type=int, default=6_666_667, help="reads per GPU (150 bp each)")
-    ap.add_argument("--genomes", type=int, default=10_000, help="genomes per GPU for the containment metric")
+    ap.add_argument("--genomes", type=int, default=None,
+                    help="genomes per GPU for the containment metric (default 10000; 12500 for the 16-sample config-4 shape)")
     ap.add_argument("--samples", type=int, default=None, help="samples for the containment metric (1; 16 when N>1)")
     ap.add_argument("--no-pairs", action="store_true", help="skip the secondary containment measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -430,12 +431,18 @@ PAIR_KERNELS = {"join": "k_join_hist<pass 1>", "join2": "k_join2_hits", "stats":
 
 
 def bench_pairs(args, ctx, rank, world, local, reads):
-    """BASELINE.json configs[2] (N=1) / configs[3] shape (N>1: genome-sharded db, replicated samples)."""
+    """BASELINE.json configs[2] (1 sample x G genomes, 1 GPU) and configs[3] (16 samples x G genomes PER GPU, db sharded
+    by genome, weak scaling: --samples 16 runs the same 16-sample workload on 1 GPU).  Multi-sample runs draw a
+    different community for every sample (seeds 0x5EED0010 + s) from the WHOLE genome range, so pass-1 survivors,
+    winners and lost k-mers come from every shard."""
     import numpy as np
     import torch
     from sylph_b200 import _lib, synth
+    from sylph_b200 import dist as D
+    from sylph_b200.api import contain_params
     n_samples = args.samples or (1 if world == 1 else 16)
     G = args.genomes
+    G_total = G * world
     t0 = time.perf_counter()
     genomes = synth.sketch_db_range(ctx, rank * G, (rank + 1) * G, GENOME_LEN, k=K, c=C)
     db = ctx.build_db(genomes, genome_base=rank * G)
@@ -444,21 +451,24 @@ def bench_pairs(args, ctx, rank, world, local, reads):
     db_keys = int(_lib.lib().syl_genomes_total_kmers(genomes._h))
     samples = []
     bases, off = reads
+    t0 = time.perf_counter()
     for si in range(n_samples):
-        if si == 0 and world == 1:
-            samples.append(ctx.sketch_sequences(bases, off, k=K, c=C))
-        else:  # replicated samples (identical on every rank): different community draws, 1/8 of the depth each
-            b, o = synth.reads(max(10000, args.reads // 8), READ_LEN, seed=synth.SEED_READS + 0x1000 + si, device="cuda")
+        if n_samples == 1:
+            samples.append(ctx.sketch_sequences(bases, off, k=K, c=C))     # the config-2 sample (community = genomes 0..63)
+        else:  # replicated on every rank: full-depth samples, community of 64 genomes spread over all shards
+            seed = synth.SEED_READS + 0x10 + si
+            comm = synth.community_ids(64, G_total, seed=seed)
+            b, o = synth.reads(args.reads, READ_LEN, seed=seed, device="cuda", comm=comm)
             samples.append(ctx.sketch_sequences(b, o, k=K, c=C))
             del b, o
-    from sylph_b200 import dist as D
-    from sylph_b200.api import contain_params
+    torch.cuda.synchronize()
+    t_samples = time.perf_counter() - t0
     P = contain_params(k=K, pseudotax=True)
     st = {}
 
     def step():
-        # `sylph profile`: pass 1, winner table, pass 2, derep, abundances. N>1: db sharded by genome,
-        # pass-1 survivors gathered into a survivor db, rows all-gathered (sylph_b200/dist.py)
+        # `sylph profile`: pass 1, winner table, pass 2, derep, abundances.  N>1: three fixed-size collectives
+        # between the library's stages (sylph_b200/dist.py profile_sharded)
         if world == 1:
             st["rows"] = ctx.profile(db, samples, P)
         else:
@@ -474,15 +484,17 @@ def bench_pairs(args, ctx, rank, world, local, reads):
     launches = ctx.launches - l0
     per_step = {kname: ctx.kernel_time(kname, reset=True)[0] / args.steps for kname in PAIR_KERNELS}
     ctx.enable_timing(False)
-    pairs = float(n_samples) * G * world
+    pairs = float(n_samples) * G_total
     value = pairs * args.steps / (ms * 1e-3)
-    d = genomes.download() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    rows = st["rows"]
     out = {"metric": "(sample x genome) containment pairs/s", "value": value, "unit": "pairs/s", "ms_per_step": ms / args.steps,
            "wall_ms_per_step": wall / args.steps, "steps": args.steps, "gpu_launches": int(launches),
            "config": profile_config(args, world),
-           "workload_stats": {"sample_keys": int(np.sum([len(s) for s in samples])), "rows_per_step": int(len(st["rows"])),
-                              "db_build_s": t_db, "db_keys_per_gpu": db_keys,
-                              "collective": "all_gather of survivor sketches and of result rows (NCCL)" if world > 1 else "none"},
+           "workload_stats": {"sample_keys": int(np.sum([len(s) for s in samples])), "rows_per_step": int(len(rows)),
+                              "db_build_s": t_db, "samples_build_s": t_samples, "db_keys_per_gpu": db_keys,
+                              "shards_with_result_rows": int(len(set((rows["genome"] // G).tolist()))) if len(rows) else 0,
+                              "collectives": ("all_gather(pass-1 row tables) + all_reduce MIN(winner order per sample key) + "
+                                              "all_gather(pass-2 row tables), NCCL, no host sync in between") if world > 1 else "none"},
            "e2e_note": "syl_profile returns rows in host memory: the D2H of the result rows is inside the timed region"}
     # live roofline of the step's dominant kernel: CUDA events recorded inside the library around every launch
     peak, peak_src = measured_peak_hbm()
@@ -497,24 +509,35 @@ def bench_pairs(args, ctx, rank, world, local, reads):
                        "note": "SURVEY §8(d) byte model of a genome-streaming probe loop (8 B x |G| per pair); this implementation "
                                "probes a sorted db index with the sample keys and never streams the db, so this is an equivalent "
                                "bandwidth that is not bounded by HBM (DESIGN.md 4.4)"}
-    if d is not None:
-        from oracle import oracle as O
-        cores = os.cpu_count() or 1
-        h, c = samples[0].download()
-        smp = O.Sample(h, c)
-        p = O.default_params(pseudotax=True)
-        t = time.perf_counter()
-        res = O.contain_sample(p, d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"], smp, nthreads=cores)
-        dt = time.perf_counter() - t
-        out["cpu_baseline"] = {"value": G / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                               "sample": "all %d pairs of the same db/sample, oracle profile (2 x get_stats + winner table) over %d OpenMP threads" % (G, cores),
-                               "rows": len(res)}
-        mine = st["rows"][st["rows"]["sample"] == 0]
-        ok, why = rows_equal_oracle(mine, res)
-        out["parity_checked"] = bool(ok)
-        out["parity_detail"] = ("all %d profile rows of sample 0 equal the oracle's field by field (ints exact, floats 1e-6)" % len(res)) if ok else why
-        if not ok:
-            raise SystemExit("bench: profile rows differ from the oracle: " + str(why))
+    # ---- parity: sample 0's rows against the CPU oracle on the WHOLE db (N>1: shards gathered on every rank)
+    if not args.no_cpu:
+        if world > 1:
+            gsub = genomes.device_tensors()
+            merged, _ = D.gather_survivor_genomes(gsub, np.arange(rank * G, (rank + 1) * G, dtype=np.uint64))
+            d = {k_: v.cpu().numpy().view(np.uint64) for k_, v in merged.items()} if rank == 0 else None
+            del merged
+        else:
+            d = genomes.download()
+        if rank == 0:
+            from oracle import oracle as O
+            cores = os.cpu_count() or 1
+            h, c = samples[0].download()
+            smp = O.Sample(h, c)
+            p = O.default_params(pseudotax=True)
+            t = time.perf_counter()
+            res = O.contain_sample(p, d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"], smp, nthreads=cores)
+            dt = time.perf_counter() - t
+            out["cpu_baseline"] = {"value": G_total / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                   "sample": "all %d pairs of sample 0 against the whole db, oracle profile (2 x get_stats + winner table) "
+                                             "over %d OpenMP threads" % (G_total, cores), "rows": len(res)}
+            mine = rows[rows["sample"] == 0]
+            ok, why = rows_equal_oracle(mine, res)
+            out["parity_checked"] = bool(ok)
+            out["parity_detail"] = ("all %d profile rows of sample 0 (genomes from %d of %d shards) equal the oracle's rows on the "
+                                    "whole %d-genome db field by field (ints exact, floats 1e-6)"
+                                    % (len(res), len(set(int(r.genome) // G for r in res)), world, G_total)) if ok else why
+            if not ok:
+                raise SystemExit("bench: profile rows differ from the oracle: " + str(why))
     for s in samples:
         s.free()
     db.free()
@@ -524,6 +547,9 @@ def bench_pairs(args, ctx, rank, world, local, reads):
 
 def main():
     args = parse()
+    if args.genomes is None:
+        world_env = int(os.environ.get("WORLD_SIZE", 1))
+        args.genomes = 12_500 if ((args.samples or (1 if world_env == 1 else 16)) > 1) else 10_000
     if args.impl == "reference":
         run_reference(args)
         return

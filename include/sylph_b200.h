@@ -19,6 +19,12 @@
  *     caller (one ctx per rayon worker / per rank).  No global mutable state.
  *   - there is NO CPU fallback: if no sm_100-class device / kernel image is available, calls
  *     fail with SYL_ERR_CUDA.
+ *   - hard limits (reported as SYL_ERR_ARG, never silently wrapped): fewer than 2^32-2 records per batch,
+ *     fewer than 2^32-2 survivor events per sample, fewer than 2^32-2 index entries (genome_kmers + tracked)
+ *     and 2^31 genomes per db shard, fewer than 2^31 (sample, genome) pairs and at most 8 GB of per-pair
+ *     histograms (2^23 pairs) per syl_query / syl_profile call — split the sample batch above that.
+ *   - handles (syl_sample / syl_genomes / syl_db / syl_profile_job) borrow device blocks from the ctx that
+ *     created them: free them before their ctx, and use them with that ctx.
  */
 #ifndef SYLPH_B200_H
 #define SYLPH_B200_H
@@ -181,6 +187,8 @@ uint64_t syl_genomes_count(const syl_genomes *g);
 uint64_t syl_genomes_total_kmers(const syl_genomes *g);
 uint64_t syl_genomes_total_tracked(const syl_genomes *g);
 int syl_genomes_has_tracked(const syl_genomes *g);
+int syl_genomes_k(const syl_genomes *g);
+uint64_t syl_genomes_c(const syl_genomes *g);
 /* Copy out: kmer_off/tracked_off have n_genomes+1 entries; any pointer may be NULL to skip. */
 int syl_genomes_download(syl_ctx *ctx, const syl_genomes *g, uint64_t *kmers, uint64_t *kmer_off,
                          uint64_t *tracked, uint64_t *tracked_off, uint64_t *gn_size);

@@ -74,6 +74,8 @@ SIGNATURES = {
     "syl_genomes_total_kmers": (_u64, [_vp]),
     "syl_genomes_total_tracked": (_u64, [_vp]),
     "syl_genomes_has_tracked": (_i, [_vp]),
+    "syl_genomes_k": (_i, [_vp]),
+    "syl_genomes_c": (_u64, [_vp]),
     "syl_genomes_download": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "syl_genomes_device_ptrs": (_i, [_vp, _pp, _pp, _pp, _pp, _pp]),
     "syl_genomes_free": (None, [_vp]),

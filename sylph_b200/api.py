@@ -248,10 +248,81 @@ class Context:
         params = params or contain_params(pseudotax=False)
         return self._pairs(_lib.lib().syl_query, db, samples, params, cap)
 
+    def profile_shard_begin(self, db, samples, params=None, world=1, rank=0, rows_per_rank=0):
+        """Stage 1 of `profile` over a genome-sharded db (pass 1 on this rank's shard) -> ProfileJob."""
+        _CTX_STREAM[0] = self._stream
+        params = params or contain_params(pseudotax=True)
+        arr = (C.c_void_p * max(len(samples), 1))(*[s._h for s in samples])
+        h = C.c_void_p()
+        _lib.check(_lib.lib().syl_profile_shard_begin(self._h, db._h, arr, len(samples), C.byref(params), int(world), int(rank),
+                                                      int(rows_per_rank), C.byref(h)))
+        return ProfileJob(self, h, int(world))
+
     def profile(self, db, samples, params=None, cap=None):
         """`sylph profile`: pass 1, winner table, pass 2, derep, abundances; per sample sorted by rel_abund."""
         params = params or contain_params(pseudotax=True)
         return self._pairs(_lib.lib().syl_profile, db, samples, params, cap)
+
+
+class ProfileJob:
+    """One in-flight `profile` over a genome-sharded db (syl_profile_job): see include/sylph_b200.h section (5).
+    The torch tensors returned by tables() / winner() alias the job's device buffers for the collectives."""
+
+    def __init__(self, ctx, handle, world):
+        self.ctx, self._h, self.world = ctx, handle, world
+
+    def _tensor(self, ptr, n, typestr):
+        import torch
+        if not ptr or n == 0:
+            return None
+        return torch.as_tensor(_CudaArray(ptr, n, self, typestr), device="cuda")
+
+    def buffers(self):
+        """-> dict(table1, gathered1, winner, table2, gathered2) of torch CUDA tensors (uint8 / int32)."""
+        L = _lib.lib()
+        p = [C.c_void_p() for _ in range(5)]
+        tb, wn = C.c_uint64(0), C.c_uint64(0)
+        _lib.check(L.syl_profile_job_buffers(self._h, C.byref(p[0]), C.byref(p[1]), C.byref(tb), C.byref(p[2]), C.byref(wn),
+                                             C.byref(p[3]), C.byref(p[4])))
+        w = self.world
+        return dict(table1=self._tensor(p[0].value, tb.value, "|u1"),
+                    gathered1=self._tensor(p[1].value, tb.value * w, "|u1") if w > 1 else None,
+                    winner=self._tensor(p[2].value, wn.value, "<i4") if w > 1 else None,
+                    table2=self._tensor(p[3].value, tb.value, "|u1"),
+                    gathered2=self._tensor(p[4].value, tb.value * w, "|u1") if w > 1 else None)
+
+    def rank(self):
+        _lib.check(_lib.lib().syl_profile_shard_rank(self._h))
+
+    def pass2(self):
+        _lib.check(_lib.lib().syl_profile_shard_pass2(self._h))
+
+    def finish(self, cap=4096):
+        """-> (rows or None, return code, rows_per_rank needed)"""
+        L = _lib.lib()
+        while True:
+            rows = np.empty(cap, dtype=ANI_ROW_DTYPE)
+            n, need = C.c_uint64(0), C.c_uint64(0)
+            rc = L.syl_profile_shard_finish(self._h, rows.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(need))
+            if rc == _lib.SYL_ERR_CAPACITY and need.value == 0:   # the caller's buffer, not the row table
+                cap = max(n.value, 2 * cap)
+                continue
+            if rc == _lib.SYL_OK:
+                return rows[: n.value].copy(), rc, 0
+            if rc in (_lib.SYL_ERR_CAPACITY, _lib.SYL_ERR_UNSUPPORTED):
+                return None, rc, need.value
+            _lib.check(rc)
+
+    def free(self):
+        if self._h:
+            _lib.lib().syl_profile_job_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def pack2(bases, threads=0):
@@ -293,11 +364,11 @@ class Db:
 
 
 class _CudaArray:
-    """Minimal __cuda_array_interface__ carrier (int64 view of a device u64 array)."""
+    """Minimal __cuda_array_interface__ carrier (default: int64 view of a device u64 array)."""
 
-    def __init__(self, ptr, n, owner):
+    def __init__(self, ptr, n, owner, typestr="<i8"):
         self.owner = owner
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class Sample:
@@ -357,6 +428,14 @@ class Genomes:
     @property
     def has_tracked(self):
         return bool(_lib.lib().syl_genomes_has_tracked(self._h))
+
+    @property
+    def k(self):
+        return int(_lib.lib().syl_genomes_k(self._h))
+
+    @property
+    def c(self):
+        return int(_lib.lib().syl_genomes_c(self._h))
 
     def download(self):
         """-> dict(kmers, kmer_off, tracked, tracked_off, gn_size)"""

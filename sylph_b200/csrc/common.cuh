@@ -180,6 +180,7 @@ struct DevBuf {
     T *p = nullptr;
     size_t n = 0, cap_bytes = 0;
     cudaStream_t s = nullptr;
+    syl_ctx *owner = nullptr;  // ctx whose block cache the buffer came from (and goes back to)
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -190,6 +191,7 @@ struct DevBuf {
         n = count;
         size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
         syl_ctx *c = tl_ctx;
+        owner = c;
         if (c) {  // best fit from the ctx cache
             size_t best = (size_t)-1, bi = 0;
             for (size_t i = 0; i < c->free_blocks.size(); i++) {
@@ -215,12 +217,11 @@ struct DevBuf {
         return SYL_OK;
     }
     void swap(DevBuf &o) {
-        std::swap(p, o.p); std::swap(n, o.n); std::swap(cap_bytes, o.cap_bytes); std::swap(s, o.s);
+        std::swap(p, o.p); std::swap(n, o.n); std::swap(cap_bytes, o.cap_bytes); std::swap(s, o.s); std::swap(owner, o.owner);
     }
     void release() {
         if (p) {
-            syl_ctx *c = tl_ctx;
-            if (c) c->free_blocks.emplace_back((void *)p, cap_bytes);
+            if (owner) owner->free_blocks.emplace_back((void *)p, cap_bytes);  // not tl_ctx: two contexts on one thread never trade blocks
             else cudaFree(p);
         }
         p = nullptr;

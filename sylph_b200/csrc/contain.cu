@@ -1139,11 +1139,7 @@ struct syl_profile_job {
 namespace syl {
 
 static void job_release(syl_profile_job *j) {
-    if (!j) return;
-    syl_ctx *prev = tl_ctx;
-    tl_ctx = j->ctx;  // the scratch blocks go back to the owning ctx's cache
-    delete j;
-    tl_ctx = prev;
+    delete j;  // the scratch blocks go back to the owning ctx's cache (DevBuf::owner)
 }
 
 static uint64_t default_rows_per_rank(uint32_t S, uint64_t G) {

@@ -368,17 +368,21 @@ int syl_genomes_upload(syl_ctx *ctx, int mem, const uint64_t *kmers, const uint6
     g->has_tracked = (tracked && tracked_off) ? 1 : 0;
     int rc = genomes_alloc(g, st, n_genomes, nk, nt);
     if (rc != SYL_OK) { syl_genomes_free(g); return rc; }
-    if (nk) SYL_CUDA(cudaMemcpyAsync(g->kmers, kmers, nk * 8, kind, st));
-    SYL_CUDA(cudaMemcpyAsync(g->kmer_off, kmer_off, (n_genomes + 1) * 8, kind, st));
-    if (g->has_tracked) {
-        if (nt) SYL_CUDA(cudaMemcpyAsync(g->tracked, tracked, nt * 8, kind, st));
-        SYL_CUDA(cudaMemcpyAsync(g->tracked_off, tracked_off, (n_genomes + 1) * 8, kind, st));
-    } else {
-        SYL_CUDA(cudaMemsetAsync(g->tracked_off, 0, (n_genomes + 1) * 8, st));
-    }
-    if (gn_size && n_genomes) SYL_CUDA(cudaMemcpyAsync(g->gn_size, gn_size, n_genomes * 8, kind, st));
-    else if (n_genomes) SYL_CUDA(cudaMemsetAsync(g->gn_size, 0, n_genomes * 8, st));
-    SYL_CUDA(cudaStreamSynchronize(st));
+    auto fill = [&]() -> int {  // any failure below frees the handle and its blocks
+        if (nk) SYL_CUDA(cudaMemcpyAsync(g->kmers, kmers, nk * 8, kind, st));
+        SYL_CUDA(cudaMemcpyAsync(g->kmer_off, kmer_off, (n_genomes + 1) * 8, kind, st));
+        if (g->has_tracked) {
+            if (nt) SYL_CUDA(cudaMemcpyAsync(g->tracked, tracked, nt * 8, kind, st));
+            SYL_CUDA(cudaMemcpyAsync(g->tracked_off, tracked_off, (n_genomes + 1) * 8, kind, st));
+        } else {
+            SYL_CUDA(cudaMemsetAsync(g->tracked_off, 0, (n_genomes + 1) * 8, st));
+        }
+        if (gn_size && n_genomes) SYL_CUDA(cudaMemcpyAsync(g->gn_size, gn_size, n_genomes * 8, kind, st));
+        else if (n_genomes) SYL_CUDA(cudaMemsetAsync(g->gn_size, 0, n_genomes * 8, st));
+        SYL_CUDA(cudaStreamSynchronize(st));
+        return SYL_OK;
+    };
+    if ((rc = fill()) != SYL_OK) { syl_genomes_free(g); return rc; }
     *out = g;
     return SYL_OK;
 }
@@ -405,6 +409,7 @@ int syl_genomes_concat(syl_ctx *ctx, const syl_genomes *const *parts, uint32_t n
     int rc = genomes_alloc(g, st, G, nk, nt);
     if (rc != SYL_OK) { syl_genomes_free(g); return rc; }
     uint64_t g0 = 0, k0 = 0, t0 = 0;
+    auto fill = [&]() -> int {  // any failure below frees the handle and its blocks
     for (uint32_t i = 0; i < n_parts; i++) {
         const syl_genomes *p = parts[i];
         if (p->total_kmers) SYL_CUDA(cudaMemcpyAsync(g->kmers + k0, p->kmers, p->total_kmers * 8, cudaMemcpyDeviceToDevice, st));
@@ -421,6 +426,9 @@ int syl_genomes_concat(syl_ctx *ctx, const syl_genomes *const *parts, uint32_t n
     }
     SYL_CUDA(cudaGetLastError());
     SYL_CUDA(cudaStreamSynchronize(st));
+    return SYL_OK;
+    };
+    if ((rc = fill()) != SYL_OK) { syl_genomes_free(g); return rc; }
     *out = g;
     return SYL_OK;
 }
@@ -452,17 +460,21 @@ int syl_genomes_select(syl_ctx *ctx, const syl_genomes *g, const uint32_t *idx, 
     if (rc != SYL_OK) { syl_genomes_free(o); return rc; }
     DevBuf<uint64_t> d_src;
     if ((rc = d_src.alloc(4 * (uint64_t)std::max<uint32_t>(n, 1), st)) != SYL_OK) { syl_genomes_free(o); return rc; }
-    SYL_CUDA(cudaMemcpyAsync(o->kmer_off, nko.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    SYL_CUDA(cudaMemcpyAsync(o->tracked_off, nto.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (n) {
-        SYL_CUDA(cudaMemcpyAsync(o->gn_size, ngs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        SYL_CUDA(cudaMemcpyAsync(d_src.p, src.data(), (size_t)n * 32, cudaMemcpyHostToDevice, st));
-        k_copy_ranges<<<n, 256, 0, st>>>(d_src.p, g->kmers, g->tracked, o->kmers,
-                                         o->tracked, o->kmer_off, o->tracked_off);
-        ctx->launches++;
-        SYL_CUDA(cudaGetLastError());
-    }
-    SYL_CUDA(cudaStreamSynchronize(st));
+    auto fill = [&]() -> int {  // any failure below frees the handle and its blocks
+        SYL_CUDA(cudaMemcpyAsync(o->kmer_off, nko.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        SYL_CUDA(cudaMemcpyAsync(o->tracked_off, nto.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (n) {
+            SYL_CUDA(cudaMemcpyAsync(o->gn_size, ngs.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            SYL_CUDA(cudaMemcpyAsync(d_src.p, src.data(), (size_t)n * 32, cudaMemcpyHostToDevice, st));
+            k_copy_ranges<<<n, 256, 0, st>>>(d_src.p, g->kmers, g->tracked, o->kmers,
+                                             o->tracked, o->kmer_off, o->tracked_off);
+            ctx->launches++;
+            SYL_CUDA(cudaGetLastError());
+        }
+        SYL_CUDA(cudaStreamSynchronize(st));
+        return SYL_OK;
+    };
+    if ((rc = fill()) != SYL_OK) { syl_genomes_free(o); return rc; }
     *out = o;
     return SYL_OK;
 }
@@ -471,6 +483,8 @@ uint64_t syl_genomes_count(const syl_genomes *g) { return g ? g->n : 0; }
 uint64_t syl_genomes_total_kmers(const syl_genomes *g) { return g ? g->total_kmers : 0; }
 uint64_t syl_genomes_total_tracked(const syl_genomes *g) { return g ? g->total_tracked : 0; }
 int syl_genomes_has_tracked(const syl_genomes *g) { return g ? g->has_tracked : 0; }
+int syl_genomes_k(const syl_genomes *g) { return g ? g->k : 0; }
+uint64_t syl_genomes_c(const syl_genomes *g) { return g ? g->c : 0; }
 
 int syl_genomes_download(syl_ctx *ctx, const syl_genomes *g, uint64_t *kmers, uint64_t *kmer_off,
                          uint64_t *tracked, uint64_t *tracked_off, uint64_t *gn_size) {

@@ -1305,23 +1305,28 @@ int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_
     syl_sample *s = new (std::nothrow) syl_sample();
     if (!s) return SYL_ERR_OOM;
     s->device = ctx->device; s->owner = ctx; s->stream = st; s->k = k; s->c = c; s->n = n;
-    SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(n, 1) * 8));
-    SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(n, 1) * 4));
-    if (n) {
-        DevBuf<uint64_t> kin;
-        DevBuf<uint32_t> vin;
-        SYL_TRY(kin.alloc(n, st)); SYL_TRY(vin.alloc(n, st));
-        cudaMemcpyKind kind = mem == SYL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        SYL_CUDA(cudaMemcpyAsync(kin.p, hash, n * 8, kind, st));
-        SYL_CUDA(cudaMemcpyAsync(vin.p, count, n * 4, kind, st));
-        size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, kin.p, s->hash, vin.p, s->count, n, 0, 64, st);
-        DevBuf<uint8_t> tmp;
-        SYL_TRY(tmp.alloc(tb, st));
-        SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kin.p, s->hash, vin.p, s->count, n, 0, 64, st));
-        ctx->launches += 8;
-        SYL_CUDA(cudaStreamSynchronize(st));
-    }
+    auto fill = [&]() -> int {  // any failure below frees the handle and its blocks
+        SYL_TRY(hblock_alloc(ctx, (void **)&s->hash, std::max<uint64_t>(n, 1) * 8));
+        SYL_TRY(hblock_alloc(ctx, (void **)&s->count, std::max<uint64_t>(n, 1) * 4));
+        if (n) {
+            DevBuf<uint64_t> kin;
+            DevBuf<uint32_t> vin;
+            SYL_TRY(kin.alloc(n, st)); SYL_TRY(vin.alloc(n, st));
+            cudaMemcpyKind kind = mem == SYL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+            SYL_CUDA(cudaMemcpyAsync(kin.p, hash, n * 8, kind, st));
+            SYL_CUDA(cudaMemcpyAsync(vin.p, count, n * 4, kind, st));
+            size_t tb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, kin.p, s->hash, vin.p, s->count, n, 0, 64, st);
+            DevBuf<uint8_t> tmp;
+            SYL_TRY(tmp.alloc(tb, st));
+            SYL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kin.p, s->hash, vin.p, s->count, n, 0, 64, st));
+            ctx->launches += 8;
+            SYL_CUDA(cudaStreamSynchronize(st));
+        }
+        return SYL_OK;
+    };
+    const int frc = fill();
+    if (frc != SYL_OK) { syl_sample_free(s); return frc; }
     *out = s;
     return SYL_OK;
 }

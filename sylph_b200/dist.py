@@ -4,9 +4,14 @@ CPU tests).  The path shards naturally:
   sketching : independent samples / genome batches per rank, no collective
   query     : db sharded by genome (syl_db_build(genome_base=...)), samples replicated, every rank
               emits its rows; ONE all-gather of the row tables at the end (the only collective)
-  profile   : pass 1 per shard; the pass-1 survivors (10^1-10^3 genomes) are gathered into a small
-              survivor db on every rank; the exact two-pass profile of sample s then runs on rank
-              s % world and the rows are all-gathered
+  profile   : profile_sharded — three fixed-size collectives between the library's compute stages, all
+              enqueued on one stream with no host synchronisation in between (include/sylph_b200.h (5)):
+                pass 1 per shard -> all_gather of the per-rank row tables
+                order of the survivors + per-key local winner -> all_reduce(MIN) of the winner array
+                pass 2 per shard + bootstrap -> all_gather of the pass-2 row tables -> host finish
+              profile_sharded_gather is the round-1 formulation (pass-1 survivors' sketches gathered into a
+              small survivor db on every rank); it remains as the fallback for samples with k-mer counts
+              >= 256 (CSR formulation) and as an independent cross-check in the tests.
 
 torch is plumbing here (process group, collectives); all compute goes through the C ABI.
 """
@@ -116,9 +121,57 @@ def gather_survivor_genomes(sub, global_ids):
     return _merge_csr(parts), np.concatenate(ids)
 
 
-def profile_sharded(ctx, genomes, db, samples, genome_base, params=None):
-    """`sylph profile` over a genome-sharded db (see module docstring). Returns all rows on every rank,
-    per sample sorted by rel_abund descending; row.genome is the GLOBAL genome id."""
+def profile_sharded(ctx, genomes, db, samples, genome_base, params=None, rows_per_rank=0):
+    """`sylph profile` over a genome-sharded db: three collectives (module docstring).  Returns all rows on
+    every rank, per sample sorted by rel_abund descending; row.genome is the GLOBAL genome id.
+    `genomes` / `genome_base` are only used by the fallback (profile_sharded_gather)."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    params = params or contain_params(pseudotax=True)
+    own_stream = ctx._stream != torch.cuda.current_stream().cuda_stream   # the collectives run on torch's stream
+
+    def fence():
+        if own_stream:
+            ctx.sync()
+            torch.cuda.current_stream().synchronize()
+
+    for _ in range(4):
+        job = ctx.profile_shard_begin(db, samples, params, world, rank, rows_per_rank)
+        try:
+            b = job.buffers()
+            if world > 1:
+                fence()
+                dist.all_gather_into_tensor(b["gathered1"], b["table1"])
+                fence()
+            job.rank()
+            if world > 1:
+                fence()
+                dist.all_reduce(b["winner"], op=dist.ReduceOp.MIN)
+                fence()
+            job.pass2()
+            if world > 1:
+                fence()
+                dist.all_gather_into_tensor(b["gathered2"], b["table2"])
+                fence()
+            rows, rc, need = job.finish()
+        finally:
+            job.free()
+        if rc == _lib.SYL_OK:
+            return rows
+        if rc == _lib.SYL_ERR_CAPACITY:          # same verdict on every rank: redo with a larger row table
+            rows_per_rank = need + 256
+            continue
+        return profile_sharded_gather(ctx, genomes, db, samples, genome_base, params)   # SYL_ERR_UNSUPPORTED
+    raise RuntimeError("profile_sharded: row table kept overflowing")
+
+
+def profile_sharded_gather(ctx, genomes, db, samples, genome_base, params=None):
+    """Round-1 formulation of the sharded profile: pass 1 per shard, the pass-1 survivors' sketches are
+    gathered into a small survivor db on every rank, the exact two-pass profile of sample s runs on rank
+    s % world, rows all-gathered.  ~14 collectives; handles every input (CSR formulation included)."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -141,7 +194,7 @@ def profile_sharded(ctx, genomes, db, samples, genome_base, params=None):
     out = np.zeros(0, dtype=ANI_ROW_DTYPE)
     if len(gids):
         g = ctx.upload_genomes(merged["kmers"], merged["kmer_off"], merged["tracked"], merged["tracked_off"],
-                               merged["gn_size"], k=params.k)
+                               merged["gn_size"], k=params.k, c=genomes.c)
         sdb = ctx.build_db(g)
         mine = [i for i in range(len(samples)) if i % world == rank]
         if mine:

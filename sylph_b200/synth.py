@@ -82,9 +82,16 @@ def community_cdf(n_comm, seed=SEED_READS, sigma=1.5):
     return cdf
 
 
+def community_ids(n_comm, n_genomes, seed=SEED_READS):
+    """n_comm genome ids spread over [0, n_genomes) (a pure function of the seed; duplicates possible): the
+    community of a sample that is profiled against a sharded db, so that survivors come from every shard."""
+    return _lsr(mix(torch.tensor(seed + 0x79), torch.arange(n_comm, dtype=torch.int64)), 1) % int(n_genomes)
+
+
 def reads_chunk(r0, r1, read_len=150, n_comm=64, genome_len=4_000_000, seed=SEED_READS, device="cpu",
-                cdf=None):
-    """ASCII bases of reads [r0, r1) (fixed length) -> uint8 tensor of (r1-r0)*read_len bytes."""
+                cdf=None, comm=None):
+    """ASCII bases of reads [r0, r1) (fixed length) -> uint8 tensor of (r1-r0)*read_len bytes.
+    comm: int64 tensor of the community's genome ids (default: genomes 0 .. n_comm-1)."""
     if cdf is None:
         cdf = community_cdf(n_comm, seed)
     cdf = cdf.to(device)
@@ -96,6 +103,8 @@ def reads_chunk(r0, r1, read_len=150, n_comm=64, genome_len=4_000_000, seed=SEED
     src = torch.where(is_dup, _lsr(mix(torch.tensor(seed + 2, device=device), j), 1) % j.clamp_min(1), j)
     hg = mix(torch.tensor(seed + 3, device=device), src)
     gid = torch.searchsorted(cdf, _u01(hg)).clamp_max(n_comm - 1)
+    if comm is not None:
+        gid = comm.to(device)[gid]
     start = _lsr(mix(torch.tensor(seed + 4, device=device), src), 1) % (genome_len - read_len + 1)
     rev = (mix(torch.tensor(seed + 5, device=device), src) & 1) == 1
     o = torch.arange(read_len, dtype=torch.int64, device=device)
@@ -117,14 +126,14 @@ def reads_chunk(r0, r1, read_len=150, n_comm=64, genome_len=4_000_000, seed=SEED
 
 
 def reads(n_reads, read_len=150, n_comm=64, genome_len=4_000_000, seed=SEED_READS, device="cpu",
-          chunk=1 << 19):
+          chunk=1 << 19, comm=None):
     """-> (uint8 flat buffer padded to a multiple of 16 bytes, int64 offsets[n_reads+1])"""
     cdf = community_cdf(n_comm, seed)
     total = n_reads * read_len
     buf = torch.zeros((total + 15) // 16 * 16 + 64, dtype=torch.uint8, device=device)
     for r0 in range(0, n_reads, chunk):
         r1 = min(n_reads, r0 + chunk)
-        buf[r0 * read_len:r1 * read_len] = reads_chunk(r0, r1, read_len, n_comm, genome_len, seed, device, cdf)
+        buf[r0 * read_len:r1 * read_len] = reads_chunk(r0, r1, read_len, n_comm, genome_len, seed, device, cdf, comm)
     off = torch.arange(n_reads + 1, dtype=torch.int64, device=device) * read_len
     return buf[:total], off
 

@@ -39,3 +39,12 @@ def seed_mode(request, monkeypatch):
     for k, v in SEED_MODES[request.param].items():
         monkeypatch.setenv(k, v)
     return request.param
+
+
+@pytest.fixture(params=["device-driven", "synchronous"])
+def contain_mode(request, monkeypatch):
+    """syl_query / syl_profile: device-driven path (one host sync) and the synchronous two-pass path."""
+    monkeypatch.delenv("SYL_CONTAIN_SYNC", raising=False)
+    if request.param == "synchronous":
+        monkeypatch.setenv("SYL_CONTAIN_SYNC", "1")
+    return request.param

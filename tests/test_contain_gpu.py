@@ -8,7 +8,7 @@ import pytest
 
 from tests.util import DATA, flatten, read_fastx
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("contain_mode")]
 
 FLOAT_TOL = 1e-6
 
@@ -204,3 +204,23 @@ def test_k21_scalar_semantics_end_to_end(ctx):
         exp = O.contain_sample(p, d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"], O.Sample(*hc))
         assert len(exp) > 5
         compare(rows, exp, pt)
+
+
+def test_sharded_profile_stages_on_one_gpu(ctx):
+    """The three-collective sharded profile (include/sylph_b200.h (5)) with world = 1 (no collectives) must
+    equal syl_profile; a row table that is too small is reported and the call is redone with the needed size."""
+    from sylph_b200 import dist as D
+    from sylph_b200.api import contain_params
+    g, s1 = synth_db_and_sample(ctx, 120, 100000, 60000, 100, c=20)
+    samples = [s1]
+    for si in range(5):
+        _, s = synth_db_and_sample(ctx, 1, 100000, 30000, 100, c=20, read_seed=0x5EED0100 + si)
+        samples.append(s)
+    db = ctx.build_db(g)
+    exp = ctx.profile(db, samples, contain_params(pseudotax=True))
+    assert len(exp) > 256                     # more rows than the smallest row table holds
+    for rpr in (0, 256):
+        rows = D.profile_sharded(ctx, g, db, samples, 0, contain_params(pseudotax=True), rows_per_rank=rpr)
+        assert len(rows) == len(exp)
+        for f in rows.dtype.names:
+            assert np.array_equal(rows[f], exp[f]), (rpr, f)
