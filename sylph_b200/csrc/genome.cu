@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace syl {
 int seed_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_rec_off, uint64_t off_bias,
@@ -96,8 +97,9 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t *a, uint64_t 
 // clusters of closely spaced k-mers, each starting with such a head.  One thread per survivor:
 // heads walk their (tiny: ~1.15 elements at c=200) cluster; everything else returns.
 __global__ void k_spacing(const uint64_t *__restrict__ poskey, uint64_t n, uint64_t min_spacing,
-                          uint8_t *__restrict__ flag) {
+                          uint8_t *__restrict__ flag, const uint32_t *__restrict__ d_n = nullptr) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_n && *d_n < n) n = *d_n;
     if (i >= n || flag[i] == 0) return;
     const uint64_t key = poskey[i], contig = key >> 32, pos = key & 0xFFFFFFFFull;
     // previous non-duplicate survivor of the same contig
@@ -196,9 +198,11 @@ static int genomes_alloc(syl_genomes *g, cudaStream_t st, uint64_t n_genomes, ui
     return SYL_OK;
 }
 
-int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_contig_off,
-                          uint64_t n_contigs, const uint64_t *d_genome_off, uint64_t n_genomes, int k, uint64_t c,
-                          uint64_t min_spacing, int pseudotax, int sem, syl_genomes *out) {
+// Generic post-pass: two library radix sorts (position, then hash).  Handles every input; used when the
+// slotted path below does not apply (tiny c, SYL_SEED_IMPL=warp, SYL_GENOME_POSTPASS=sort) or reports an overflow.
+static int sketch_genomes_device_sort(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_contig_off,
+                                      uint64_t n_contigs, const uint64_t *d_genome_off, uint64_t n_genomes, int k, uint64_t c,
+                                      uint64_t min_spacing, int pseudotax, int sem, syl_genomes *out) {
     cudaStream_t st = ctx->stream;
     // 1. survivors with positions
     uint64_t scap = n_bases / c + n_bases / (4 * c) + 65536;
@@ -282,6 +286,268 @@ int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases
     if (!pseudotax) SYL_CUDA(cudaMemsetAsync(out->tracked_off, 0, (n_genomes + 1) * 8, st));
     SYL_CUDA(cudaStreamSynchronize(st));
     return SYL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sort-free post-pass.
+//   * k_seed writes every tile's survivors into the tile's own slot (SlotOut), so the output is in
+//     tile = position order already; k_tile_sort_compact orders the <= 512 survivors INSIDE a tile by
+//     (contig, position) in shared memory and compacts the tiles (scan of the per-tile counts).
+//   * duplicates (a hash seen twice in one genome, src/sketch.rs:594-600): a genome's survivors are now
+//     contiguous; CTA (genome, part) walks them and groups the hashes of ITS share of the hash space
+//     (~6 000 of them) in a shared-memory table — no sort by hash.
+//   * k_spacing as before; kept / tracked survivors are compacted with block counts + one small scan.
+// One host synchronisation (the totals), like the read-sketch path.
+constexpr uint32_t GEN_SLOT = 512;        // survivors per tile slot (= the seeding kernel's staging capacity)
+constexpr uint32_t GEN_PART_N = 6000;     // expected hashes per (genome, part) CTA
+constexpr uint32_t GEN_SLOTS = 16384;     // table slots per CTA (load factor ~0.37)
+constexpr int GEN_DUP_THREADS = 512;
+
+// tile t: slot -> sorted by (contig, pos) -> compact arrays at toff[t]
+__global__ void __launch_bounds__(256)
+k_tile_sort_compact(const syl_survivor *__restrict__ slots, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ toff,
+                    uint64_t *__restrict__ poskey, uint64_t *__restrict__ hash) {
+    __shared__ uint64_t sk[GEN_SLOT], sh[GEN_SLOT];
+    const uint32_t t = blockIdx.x, n = tile_cnt[t];
+    if (n == 0) return;
+    uint32_t P = 32;
+    while (P < n) P <<= 1;
+    const syl_survivor *src = slots + (uint64_t)t * GEN_SLOT;
+    for (uint32_t i = threadIdx.x; i < P; i += 256) {
+        if (i < n) { const syl_survivor v = src[i]; sk[i] = ((uint64_t)v.rec << 32) | v.pos; sh[i] = v.hash; }
+        else { sk[i] = 0xFFFFFFFFFFFFFFFFull; sh[i] = 0; }
+    }
+    __syncthreads();
+    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t q = threadIdx.x; q < (P >> 1); q += 256) {
+                const uint32_t i = ((q & ~(j - 1)) << 1) | (q & (j - 1)), l = i | j;
+                const bool up = (i & kk) == 0;
+                const uint64_t a = sk[i], b = sk[l];
+                if ((a > b) == up) { sk[i] = b; sk[l] = a; const uint64_t x = sh[i]; sh[i] = sh[l]; sh[l] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t base = toff[t];
+    for (uint32_t i = threadIdx.x; i < n; i += 256) { poskey[base + i] = sk[i]; hash[base + i] = sh[i]; }
+}
+
+// gs[g] = index of genome g's first survivor (g = 0 .. n_genomes; gs[n_genomes] = N); N from device memory
+__global__ void k_genome_ranges(const uint64_t *__restrict__ poskey, const uint32_t *__restrict__ d_n, const uint64_t *__restrict__ genome_off,
+                                uint64_t n_genomes, uint32_t *__restrict__ gs) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_genomes) return;
+    const uint64_t N = *d_n;
+    gs[g] = g == n_genomes ? (uint32_t)N : (uint32_t)lower_bound_u64(poskey, N, genome_off[g] << 32);
+}
+
+__global__ void k_genome_parts(const uint32_t *__restrict__ gs, uint64_t n_genomes, uint32_t *__restrict__ parts) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_genomes) parts[g] = (gs[g + 1] - gs[g] + GEN_PART_N - 1) / GEN_PART_N;
+}
+
+__device__ __forceinline__ uint32_t gen_part_of(uint64_t h, uint32_t P) {
+    return (uint32_t)((((h >> 8) & 0xFFFFFFull) * P) >> 24);  // hashes are uniform below the threshold: so are these 24 bits
+}
+
+// block b -> (genome g, part p); flags the survivors of g whose hash falls into part p: 0 = the hash occurs
+// >= 2x in the genome (dropped, src/sketch.rs:594-600,605), 3 = undecided (k_spacing decides kept / tracked)
+__global__ void __launch_bounds__(GEN_DUP_THREADS)
+k_genome_dups(const uint64_t *__restrict__ hash, const uint32_t *__restrict__ gs, const uint32_t *__restrict__ pstart, uint64_t n_genomes,
+              uint8_t *__restrict__ flag, uint32_t *__restrict__ overflow) {
+    extern __shared__ __align__(16) uint8_t gd_smem[];
+    unsigned long long *tab = reinterpret_cast<unsigned long long *>(gd_smem);
+    uint8_t *dup = gd_smem + (size_t)GEN_SLOTS * 8;
+    const uint32_t b = blockIdx.x;
+    if (b >= pstart[n_genomes]) return;
+    uint32_t lo = 0, hi = (uint32_t)n_genomes;  // last g with pstart[g] <= b
+    while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (pstart[mid] <= b) lo = mid; else hi = mid; }
+    const uint32_t g = lo, p = b - pstart[g], P = pstart[g + 1] - pstart[g];
+    const uint32_t s0 = gs[g], s1 = gs[g + 1];
+    for (uint32_t i = threadIdx.x; i < GEN_SLOTS; i += GEN_DUP_THREADS) { tab[i] = 0xFFFFFFFFFFFFFFFFull; dup[i] = 0; }
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += GEN_DUP_THREADS) {
+        const unsigned long long h = hash[i];
+        if (gen_part_of(h, P) != p) continue;
+        uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
+        uint32_t probes = 0;
+        for (;; probes++) {
+            if (probes >= GEN_SLOTS) { atomicExch(overflow, 1u); break; }  // table full (pathological skew): generic path
+            const unsigned long long prev = atomicCAS(&tab[sl], 0xFFFFFFFFFFFFFFFFull, h);
+            if (prev == 0xFFFFFFFFFFFFFFFFull) break;
+            if (prev == h) { dup[sl] = 1; break; }
+            sl = (sl + 1) & (GEN_SLOTS - 1);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = s0 + threadIdx.x; i < s1; i += GEN_DUP_THREADS) {
+        const unsigned long long h = hash[i];
+        if (gen_part_of(h, P) != p) continue;
+        uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
+        uint32_t probes = 0;
+        while (tab[sl] != h && probes < GEN_SLOTS) { sl = (sl + 1) & (GEN_SLOTS - 1); probes++; }
+        flag[i] = (probes < GEN_SLOTS && dup[sl]) ? 0 : 3;
+    }
+}
+
+// per block of 1024 survivors: number of kept (flag 1) and tracked (flag 2) ones
+__global__ void __launch_bounds__(256) k_flag_counts(const uint8_t *__restrict__ flag, const uint32_t *__restrict__ d_n,
+                                                     uint32_t *__restrict__ bk, uint32_t *__restrict__ bt) {
+    __shared__ uint32_t sk[8], st_[8];
+    const uint64_t N = *d_n, base = (uint64_t)blockIdx.x * 1024;
+    uint32_t ck = 0, ct = 0;
+    for (int e = 0; e < 4; e++) {
+        const uint64_t i = base + threadIdx.x + 256 * e;
+        if (i < N) { const uint8_t f = flag[i]; ck += f == 1; ct += f == 2; }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { ck += __shfl_xor_sync(0xffffffffu, ck, d); ct += __shfl_xor_sync(0xffffffffu, ct, d); }
+    if ((threadIdx.x & 31) == 0) { sk[threadIdx.x >> 5] = ck; st_[threadIdx.x >> 5] = ct; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0, b = 0;
+        for (int w = 0; w < 8; w++) { a += sk[w]; b += st_[w]; }
+        bk[blockIdx.x] = a;
+        bt[blockIdx.x] = b;
+    }
+}
+
+// scatter the kept / tracked hashes of one 1024-survivor block (in order) and record, per survivor, how many
+// kept / tracked ones precede it (the per-genome CSR offsets are read from these)
+__global__ void __launch_bounds__(1024) k_scatter_flagged_blocks(const uint64_t *__restrict__ hash, const uint8_t *__restrict__ flag,
+                                                                 const uint32_t *__restrict__ d_n, const uint32_t *__restrict__ bk_off,
+                                                                 const uint32_t *__restrict__ bt_off, uint64_t *__restrict__ kmers,
+                                                                 uint64_t *__restrict__ tracked, uint32_t *__restrict__ scan_k,
+                                                                 uint32_t *__restrict__ scan_t) {
+    __shared__ uint32_t wk[32], wt[32];
+    const uint64_t N = *d_n, i = (uint64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint8_t f = i < N ? flag[i] : 0;
+    const uint32_t mk = __ballot_sync(0xffffffffu, f == 1), mt = __ballot_sync(0xffffffffu, f == 2);
+    if (lane == 0) { wk[wid] = __popc(mk); wt[wid] = __popc(mt); }
+    __syncthreads();
+    uint32_t pk = bk_off[blockIdx.x], pt = bt_off[blockIdx.x];
+    for (int w = 0; w < wid; w++) { pk += wk[w]; pt += wt[w]; }
+    pk += __popc(mk & ((1u << lane) - 1u));
+    pt += __popc(mt & ((1u << lane) - 1u));
+    if (i < N) {
+        scan_k[i] = pk;
+        scan_t[i] = pt;
+        if (f == 1) kmers[pk] = hash[i];
+        else if (f == 2 && tracked) tracked[pt] = hash[i];
+    }
+}
+
+__global__ void k_genome_offsets32(const uint32_t *__restrict__ gs, const uint32_t *__restrict__ d_n, const uint64_t *__restrict__ genome_off,
+                                   uint64_t n_genomes, const uint32_t *__restrict__ scan_k, const uint32_t *__restrict__ scan_t,
+                                   const uint32_t *__restrict__ d_tot_k, const uint32_t *__restrict__ d_tot_t, int pseudotax,
+                                   const uint64_t *__restrict__ contig_off, uint64_t *__restrict__ kmer_off,
+                                   uint64_t *__restrict__ tracked_off, uint64_t *__restrict__ gn_size) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_genomes) return;
+    const uint32_t N = *d_n, first = gs[g];
+    kmer_off[g] = first < N ? scan_k[first] : *d_tot_k;
+    tracked_off[g] = pseudotax ? (first < N ? scan_t[first] : *d_tot_t) : 0;
+    if (g < n_genomes) gn_size[g] = contig_off[genome_off[g + 1]] - contig_off[genome_off[g]];  // src/sketch.rs:581
+}
+
+// rc SYL_ERR_UNSUPPORTED: a slot / table overflowed — the caller takes the generic path
+static int sketch_genomes_device_slots(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_contig_off,
+                                       uint64_t n_contigs, const uint64_t *d_genome_off, uint64_t n_genomes, int k, uint64_t c,
+                                       uint64_t min_spacing, int pseudotax, int sem, syl_genomes *out) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_tiles = seed_cta_tiles(n_bases);
+    if (n_tiles * GEN_SLOT >= 0xFFFFFFFFull) { set_error("genome batch too large; split the batch"); return SYL_ERR_ARG; }
+    const uint64_t cap = std::min<uint64_t>(n_tiles * GEN_SLOT, n_bases / c + n_bases / (4 * c) + 65536);  // compact survivors
+    DevBuf<syl_survivor> slots;
+    DevBuf<uint32_t> tile_cnt, toff, gs, parts, pstart, bk, bt, bk_off, bt_off, scan_k, scan_t, t1, t2, flags32;
+    DevBuf<uint64_t> poskey, hash, tmp_k, tmp_t;
+    DevBuf<uint8_t> flag;
+    SYL_TRY(slots.alloc(n_tiles * GEN_SLOT, st));
+    SYL_TRY(tile_cnt.alloc(n_tiles, st)); SYL_TRY(toff.alloc(n_tiles + 1, st));
+    SYL_TRY(flags32.alloc(2, st));  // [0] slot overflow, [1] table overflow
+    SYL_CUDA(cudaMemsetAsync(flags32.p, 0, 8, st));
+    SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint64_t), st));
+    SeedJob job;
+    job.d_bases = d_bases; job.n_bases = n_bases; job.d_rec_off = d_contig_off; job.off_bias = 0; job.n_rec = n_contigs;
+    job.k = k; job.c = c; job.sem = sem; job.with_pos = 1; job.d_out = slots.p; job.cap = n_tiles * GEN_SLOT;
+    job.d_count = reinterpret_cast<unsigned long long *>(ctx->d_counters);
+    job.d_pend_count = job.d_count + 1;
+    job.slot_cap = GEN_SLOT; job.d_tile_cnt = tile_cnt.p; job.d_slot_overflow = flags32.p;
+    SYL_TRY(seed_enqueue(ctx, job));
+    KernelTimer kt_post(ctx, SYL_KERNEL_GENOME_POST);
+    SYL_TRY(scan_u32(ctx, tile_cnt.p, n_tiles, toff.p, t1, t2));   // toff[n_tiles] = N (device)
+    const uint32_t *d_n = toff.p + n_tiles;
+    SYL_TRY(poskey.alloc(cap, st)); SYL_TRY(hash.alloc(cap, st)); SYL_TRY(flag.alloc(cap, st));
+    k_tile_sort_compact<<<(unsigned)n_tiles, 256, 0, st>>>(slots.p, tile_cnt.p, toff.p, poskey.p, hash.p);
+    SYL_TRY(gs.alloc(n_genomes + 1, st)); SYL_TRY(parts.alloc(n_genomes, st)); SYL_TRY(pstart.alloc(n_genomes + 1, st));
+    k_genome_ranges<<<nblk(n_genomes + 1, 256), 256, 0, st>>>(poskey.p, d_n, d_genome_off, n_genomes, gs.p);
+    k_genome_parts<<<nblk(n_genomes, 256), 256, 0, st>>>(gs.p, n_genomes, parts.p);
+    SYL_TRY(scan_u32(ctx, parts.p, n_genomes, pstart.p, t1, t2));
+    const size_t dsm = (size_t)GEN_SLOTS * 9;
+    SYL_CUDA(cudaFuncSetAttribute(k_genome_dups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    const uint64_t dup_grid = cap / GEN_PART_N + n_genomes + 1;  // >= sum of ceil(n_g / PART_N)
+    k_genome_dups<<<(unsigned)dup_grid, GEN_DUP_THREADS, dsm, st>>>(hash.p, gs.p, pstart.p, n_genomes, flag.p, flags32.p + 1);
+    // N is only known on the device: size the element-wise grids for the capacity (threads past N return)
+    k_spacing<<<nblk(cap, 256), 256, 0, st>>>(poskey.p, cap, min_spacing, flag.p, d_n);
+    const uint64_t nb = (cap + 1023) / 1024;
+    SYL_TRY(bk.alloc(nb, st)); SYL_TRY(bt.alloc(nb, st)); SYL_TRY(bk_off.alloc(nb + 1, st)); SYL_TRY(bt_off.alloc(nb + 1, st));
+    SYL_TRY(scan_k.alloc(cap, st)); SYL_TRY(scan_t.alloc(cap, st)); SYL_TRY(tmp_k.alloc(cap, st)); SYL_TRY(tmp_t.alloc(cap, st));
+    k_flag_counts<<<(unsigned)nb, 256, 0, st>>>(flag.p, d_n, bk.p, bt.p);
+    SYL_TRY(scan_u32(ctx, bk.p, nb, bk_off.p, t1, t2));
+    DevBuf<uint32_t> t3, t4;
+    SYL_TRY(scan_u32(ctx, bt.p, nb, bt_off.p, t3, t4));
+    k_scatter_flagged_blocks<<<(unsigned)nb, 1024, 0, st>>>(hash.p, flag.p, d_n, bk_off.p, bt_off.p, tmp_k.p, pseudotax ? tmp_t.p : nullptr,
+                                                            scan_k.p, scan_t.p);
+    ctx->launches += 8;
+    // per-genome offsets go straight into the handle; the k-mer arrays need the totals first
+    out->has_tracked = pseudotax ? 1 : 0;
+    out->stream = st;
+    out->owner = tl_ctx;
+    out->n = n_genomes;
+    SYL_TRY(hblock_alloc(out->owner, (void **)&out->kmer_off, (n_genomes + 1) * 8));
+    SYL_TRY(hblock_alloc(out->owner, (void **)&out->tracked_off, (n_genomes + 1) * 8));
+    SYL_TRY(hblock_alloc(out->owner, (void **)&out->gn_size, std::max<uint64_t>(n_genomes, 1) * 8));
+    k_genome_offsets32<<<nblk(n_genomes + 1, 128), 128, 0, st>>>(gs.p, d_n, d_genome_off, n_genomes, scan_k.p, scan_t.p, bk_off.p + nb,
+                                                                 bt_off.p + nb, pseudotax, d_contig_off, out->kmer_off, out->tracked_off,
+                                                                 out->gn_size);
+    ctx->launches++;
+    kt_post.stop();
+    SYL_CUDA(cudaGetLastError());
+    uint32_t *h32 = reinterpret_cast<uint32_t *>(ctx->h_counters + 4);
+    SYL_CUDA(cudaMemcpyAsync(h32, flags32.p, 8, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaMemcpyAsync(h32 + 2, bk_off.p + nb, 4, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaMemcpyAsync(h32 + 3, bt_off.p + nb, 4, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaMemcpyAsync(h32 + 4, d_n, 4, cudaMemcpyDeviceToHost, st));
+    SYL_CUDA(cudaStreamSynchronize(st));  // the one synchronisation of the call
+    if (h32[0] || h32[1] || h32[4] > cap) return SYL_ERR_UNSUPPORTED;
+    const uint64_t total_kept = h32[2], total_tracked = pseudotax ? h32[3] : 0;
+    SYL_TRY(hblock_alloc(out->owner, (void **)&out->kmers, std::max<uint64_t>(total_kept, 1) * 8));
+    SYL_TRY(hblock_alloc(out->owner, (void **)&out->tracked, std::max<uint64_t>(total_tracked, 1) * 8));
+    out->total_kmers = total_kept;
+    out->total_tracked = total_tracked;
+    if (total_kept) SYL_CUDA(cudaMemcpyAsync(out->kmers, tmp_k.p, total_kept * 8, cudaMemcpyDeviceToDevice, st));
+    if (total_tracked) SYL_CUDA(cudaMemcpyAsync(out->tracked, tmp_t.p, total_tracked * 8, cudaMemcpyDeviceToDevice, st));
+    return SYL_OK;
+}
+
+int sketch_genomes_device(syl_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint64_t *d_contig_off,
+                          uint64_t n_contigs, const uint64_t *d_genome_off, uint64_t n_genomes, int k, uint64_t c,
+                          uint64_t min_spacing, int pseudotax, int sem, syl_genomes *out) {
+    const char *e = getenv("SYL_GENOME_POSTPASS");  // "sort" forces the generic path (tests); read per call
+    const bool force_sort = e && std::string(e) == "sort";
+    // slots hold 512 survivors per 32K-base tile: c >= 96 keeps the expected number below 350
+    if (!force_sort && c >= 96 && seed_cta_kernel_selected() && n_bases && n_contigs && n_genomes) {
+        const int rc = sketch_genomes_device_slots(ctx, d_bases, n_bases, d_contig_off, n_contigs, d_genome_off, n_genomes, k, c,
+                                                   min_spacing, pseudotax, sem, out);
+        if (rc != SYL_ERR_UNSUPPORTED) return rc;
+        // a slot or table overflowed (low-complexity sequence): release what was allocated and take the generic path
+        hblock_free(out->owner, out->kmer_off); hblock_free(out->owner, out->tracked_off); hblock_free(out->owner, out->gn_size);
+        out->kmer_off = out->tracked_off = out->gn_size = nullptr;
+    }
+    return sketch_genomes_device_sort(ctx, d_bases, n_bases, d_contig_off, n_contigs, d_genome_off, n_genomes, k, c, min_spacing,
+                                      pseudotax, sem, out);
 }
 
 }  // namespace syl

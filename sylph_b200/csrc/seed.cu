@@ -96,6 +96,9 @@ static bool use_warp_kernel() {
     return e && strcmp(e, "warp") == 0;
 }
 
+uint64_t seed_cta_tiles(uint64_t n_bases) { return (n_bases + SEED_TILE - 1) / SEED_TILE; }
+bool seed_cta_kernel_selected() { return !use_warp_kernel(); }
+
 // Enqueue the seeding of one batch on the ctx stream.  No host synchronisation and no counter reset:
 // survivors / events are appended to job.d_out at the running device counter *job.d_count (entries
 // past job.cap are counted but dropped; the caller compares the final count with cap), pending
@@ -116,6 +119,7 @@ int seed_enqueue(syl_ctx *ctx, const SeedJob &job) {
         return SYL_ERR_ARG;
     }
     const bool warp = use_warp_kernel() || job.d_packed != nullptr;
+    if (job.slot_cap && warp) { set_error("internal: slotted output needs the CTA kernel"); return SYL_ERR_ARG; }
     cudaStream_t st = ctx->stream;
     // Run length: every record is cut into runs of W windows and a thread always pays for a full
     // run, so for fixed-length reads W should divide the per-read window count (150 bp, k=31:
@@ -142,9 +146,10 @@ int seed_enqueue(syl_ctx *ctx, const SeedJob &job) {
                                                  : (job.k == 31 ? seed_kernels_k31_sv(W) : seed_kernels_k21_sv(W));
         SYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(ctx, SYL_KERNEL_SEED);
+        const SlotOut slot{job.emit_events ? 0u : job.slot_cap, job.d_tile_cnt, job.d_slot_overflow};
         kern<<<(unsigned)n_tiles, SEED_THREADS, smem, st>>>(
-            job.d_bases, job.n_bases, job.d_rec_off, job.off_bias, tile_rec.p, thr, job.sem, job.with_pos, job.d_out, job.cap,
-            job.d_count, smul, job.rec_base, job.no_dedup, job.d_pend, bh);
+            job.d_bases, job.n_bases, job.d_rec_off, job.off_bias, tile_rec.p, thr, job.sem, job.with_pos, job.d_out,
+            slot.cap ? 0 : job.cap, job.d_count, smul, job.rec_base, job.no_dedup, job.d_pend, bh, slot);
         kt.stop();
     } else {
         const bool pk = job.d_packed != nullptr;

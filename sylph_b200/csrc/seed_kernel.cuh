@@ -70,7 +70,13 @@ struct BucketHist {
     }
 };
 
-struct ShiftMul { uint32_t m24, m14, m28, one, zero; };  // = 1<<8, 1<<18, 1<<4, 1, 0 (opaque to ptxas)
+struct ShiftMul { uint32_t m24, m14, m28, one, zero; };
+
+// Slotted survivor output (genome sketching): tile t writes its survivors to out[t * cap ..) and their
+// number to tile_cnt[t] instead of appending at a global counter, so that the output is already in tile
+// (= position) order and no global sort is needed.  cap == 0: off.  A tile with more survivors than the
+// slot (or the CTA's staging buffer) holds raises *overflow; the caller then takes the generic path.
+struct SlotOut { uint32_t cap; uint32_t *tile_cnt; uint32_t *overflow; };  // = 1<<8, 1<<18, 1<<4, 1, 0 (opaque to ptxas)
 
 // 64-bit multiply by a 32-bit constant as IMAD.WIDE + IMAD (2 FMA-pipe instructions)
 __device__ __forceinline__ void mul64c(uint32_t lo, uint32_t hi, uint32_t c, uint32_t &plo, uint32_t &phi) {
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(SEED_THREADS, SEED_MINB_CFG)
 k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__restrict__ rec_off, uint64_t off_bias,
        const uint32_t *__restrict__ tile_rec, uint64_t thr, int sem, int with_pos,
        void *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ g_count,
-       const ShiftMul smul, uint64_t rec_base, int no_dedup, uint32_t *__restrict__ pend, const BucketHist bh) {
+       const ShiftMul smul, uint64_t rec_base, int no_dedup, uint32_t *__restrict__ pend, const BucketHist bh, const SlotOut slot) {
     static_assert(W >= SEED_W_MIN && W <= SEED_W_MAX, "run length");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SeedSmem &S = *reinterpret_cast<SeedSmem *>(smem_raw);
@@ -441,6 +447,18 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
 
     // ---- flush staged survivors: one global atomic per CTA, coalesced 16-byte stores
     __syncthreads();
+    if (EMIT == 0 && slot.cap) {  // slotted output: this tile's slot, no atomics (launcher passes cap = 0, so nothing was appended)
+        const unsigned int total = M.stage_count;
+        const unsigned int lim = min((unsigned)SEED_STAGE, slot.cap);
+        const unsigned int nst = min(total, lim);
+        if (tid == 0) {
+            slot.tile_cnt[blockIdx.x] = nst;
+            if (total > lim) atomicExch(slot.overflow, 1u);
+        }
+        syl_survivor *dst = reinterpret_cast<syl_survivor *>(out) + (uint64_t)blockIdx.x * slot.cap;
+        for (unsigned int i = tid; i < nst; i += SEED_THREADS) dst[i] = reinterpret_cast<const syl_survivor *>(M.stage)[i];
+        return;
+    }
     const unsigned int staged = min(M.stage_count, (unsigned)SEED_STAGE);
     if (tid == 0 && staged) M.flush_base = atomicAdd(g_count, (unsigned long long)staged);
     __syncthreads();
@@ -462,7 +480,7 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
 
 
 using seed_kern_t = void (*)(const uint8_t *, uint64_t, const uint64_t *, uint64_t, const uint32_t *, uint64_t, int, int,
-                             void *, uint64_t, unsigned long long *, const ShiftMul, uint64_t, int, uint32_t *, const BucketHist);
+                             void *, uint64_t, unsigned long long *, const ShiftMul, uint64_t, int, uint32_t *, const BucketHist, const SlotOut);
 
 // One translation unit per (K, EMIT) instantiates the three run lengths and exports a getter, so
 // the twelve kernels compile in parallel.

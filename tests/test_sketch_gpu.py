@@ -173,3 +173,53 @@ def test_genomes_multicontig_with_repeats(ctx, k, sem):
     buf, coff = flatten(contigs)
     check_genomes(ctx, buf, coff, np.array(goff, dtype=np.uint64), k=k, c=11, min_spacing=30, sem=sem)
     check_genomes(ctx, buf, coff, np.array(goff, dtype=np.uint64), k=k, c=3, min_spacing=5, sem=sem)
+
+
+@pytest.mark.parametrize("postpass", ["slots", "sort"])
+def test_genomes_c200_slotted_postpass(ctx, monkeypatch, postpass):
+    """c >= 96 takes the sort-free post-pass (per-tile slots, shared-memory duplicate tables, genome.cu); same
+    inputs through the generic radix-sort path.  Long contigs (many tiles), repeats inside a genome (dropped),
+    segments shared across genomes (kept), genomes with thousands of survivors (several hash partitions), empty
+    genomes, --individual-records, no tracked k-mers."""
+    if postpass == "sort":
+        monkeypatch.setenv("SYL_GENOME_POSTPASS", "sort")
+    rng = np.random.default_rng(2024)
+    shared = rand_seqs(rng, [30000])[0]
+    contigs, goff = [], [0]
+    for g in range(24):
+        nc = int(rng.integers(0, 5)) if g != 7 else 0
+        rep = rand_seqs(rng, [6000])[0]
+        for ci in range(nc):
+            ln = int(rng.choice([0, 61, 62, 5000, 70000, 200000, 1500000 if g == 3 else 40000]))
+            s = rand_seqs(rng, [ln])[0]
+            if ln >= 40000 and rng.random() < 0.7:
+                s = s[:10000] + rep + s[16000:20000] + rep + s[26000:]   # repeat inside the genome, twice in one contig
+            if ln >= 70000 and rng.random() < 0.6:
+                s = s[:30000] + shared + s[60000:]                       # shared across genomes
+            contigs.append(s)
+        goff.append(len(contigs))
+    buf, coff = flatten(contigs)
+    goff = np.array(goff, dtype=np.uint64)
+    d = check_genomes(ctx, buf, coff, goff, c=200)
+    assert int(np.diff(d["kmer_off"]).max()) > 6000       # more than one hash partition for the biggest genome
+    check_genomes(ctx, buf, coff, goff, c=100, min_spacing=10)
+    check_genomes(ctx, buf, coff, goff, c=200, pseudotax=False)
+    check_genomes(ctx, buf, coff, goff, c=200, individual=True)
+    check_genomes(ctx, buf, coff, goff, k=21, c=128, sem=0)
+
+
+def test_genomes_low_complexity_overflows_the_tile_slots(ctx):
+    """A tandem repeat whose k-mer survives fills a tile with far more than 512 survivors: the slotted path reports
+    the overflow and the call is redone on the generic path (all copies are duplicates and must vanish)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(9)
+    unit = None
+    for _ in range(2000):
+        u = rand_seqs(rng, [40])[0]
+        if len(O.extract_markers(u * 4, k=31, c=200)) > 0:
+            unit = u
+            break
+    assert unit is not None
+    contigs = [unit * 5000, rand_seqs(rng, [150000])[0], unit * 3000 + rand_seqs(rng, [50000])[0]]
+    buf, coff = flatten(contigs)
+    check_genomes(ctx, buf, coff, np.array([0, 2, 3], dtype=np.uint64), c=200)
