@@ -104,6 +104,10 @@ def lib():
     L.syo_sketch_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_size_t,
                                    C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.syo_sketch_read_pairs.restype = C.c_int
+    L.syo_sketch_read_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_size_t,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.syo_sample_new.restype = C.c_void_p
     L.syo_sample_new.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.syo_sample_free.restype = None
@@ -208,6 +212,26 @@ def sketch_reads(bases, rec_off, k=31, c=200, no_dedup=False, sem=SEM_AVX2, nthr
         n, mean, nd = C.c_size_t(0), C.c_double(0), C.c_uint64(0)
         rc = lib().syo_sketch_reads(_ptr(b), _ptr(off), len(off) - 1, k, c, int(no_dedup), sem, nthreads,
                                     _ptr(h), _ptr(ct), C.byref(n), cap, C.byref(mean), C.byref(nd))
+        if rc == 2:
+            raise ValueError("unsupported k")
+        if rc == 0:
+            return h[:n.value].copy(), ct[:n.value].copy(), mean.value, nd.value
+        cap = n.value + 16
+
+
+def sketch_read_pairs(bases1, off1, bases2, off2, k=31, c=200, no_dedup=False, sem=SEM_AVX2):
+    """sketch_pair_sequences with --fpr 0 (src/sketch.rs:771-895) -> (hash sorted, count, mean_read_length, num_dup_removed)"""
+    b1, b2 = _u8(bases1), _u8(bases2)
+    o1 = np.ascontiguousarray(off1, dtype=np.uint64)
+    o2 = np.ascontiguousarray(off2, dtype=np.uint64)
+    n_pairs = min(len(o1), len(o2)) - 1
+    cap = max(1024, (len(b1) + len(b2)) // 16 + 1024)
+    while True:
+        h = np.empty(cap, dtype=np.uint64)
+        ct = np.empty(cap, dtype=np.uint32)
+        n, mean, nd = C.c_size_t(0), C.c_double(0), C.c_uint64(0)
+        rc = lib().syo_sketch_read_pairs(_ptr(b1), _ptr(o1), _ptr(b2), _ptr(o2), n_pairs, k, c, int(no_dedup), sem,
+                                         _ptr(h), _ptr(ct), C.byref(n), cap, C.byref(mean), C.byref(nd))
         if rc == 2:
             raise ValueError("unsupported k")
         if rc == 0:

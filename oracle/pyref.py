@@ -133,6 +133,56 @@ def sketch_reads(reads, k, c, no_dedup=False, sem_avx2=True):
     return counts, mean, ndup
 
 
+def pair_kmer(s1, s2):
+    """src/sketch.rs:658-688: 16 bases at even / odd offsets from the start of each mate; None if a mate < 33 bp"""
+    if len(s1) < 33 or len(s2) < 33:
+        return None
+    f = g = r = t = 0
+    for i in range(16):
+        f = (f << 2) | BYTE_TO_SEQ[s1[2 * i]]
+        r = (r << 2) | BYTE_TO_SEQ[s2[2 * i]]
+        g = (g << 2) | BYTE_TO_SEQ[s1[2 * i + 1]]
+        t = (t << 2) | BYTE_TO_SEQ[s2[2 * i + 1]]
+    return ((f, r), (g, t))
+
+
+def sketch_read_pairs(reads1, reads2, k, c, no_dedup=False, sem_avx2=True):
+    """src/sketch.rs:771-895 with dedup_fpr == 0: the exact (k-mer, pair key) set, no count threshold
+    -> (dict hash->count, mean_read_length, num_dup_removed)"""
+    counts, pairs = {}, set()
+    mean, n, ndup = 0.0, 0.0, 0
+
+    def dedup(km, pair):
+        nonlocal ndup
+        cur = counts.setdefault(km, 0)
+        if not no_dedup and pair is not None:      # threshold None: *c < u32::MAX always holds
+            ret = False
+            for pk in pair:
+                if (km, pk) in pairs:
+                    if cur > 0:
+                        ret = True
+                else:
+                    pairs.add((km, pk))
+            if ret:
+                ndup += 1
+                return
+        counts[km] = cur + 1
+
+    for s1, s2 in zip(reads1, reads2):
+        v1 = [h for _, h in (seeds_avx2(s1, k, c, False) if sem_avx2 else seeds_scalar(s1, k, c))]
+        v2 = [h for _, h in (seeds_avx2(s2, k, c, False) if sem_avx2 else seeds_scalar(s2, k, c))]
+        pair = pair_kmer(s1, s2)
+        n += 1.0
+        mean = mean + (len(s1) - mean) / n
+        for km in v1:
+            dedup(km, pair)
+        for km in v2:
+            if km in v1:
+                continue
+            dedup(km, pair)
+    return counts, mean, ndup
+
+
 def poisson_cdf(lam, x):
     """statrs Poisson::cdf for integer x (Q(x+1, lam)) by direct summation."""
     term = math.exp(-lam)

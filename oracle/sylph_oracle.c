@@ -448,12 +448,12 @@ static int pair_kmer_single(const uint8_t *s, size_t len, uint32_t p0[2], uint32
     return 1;
 }
 
-/* src/sketch.rs:690-731 dup_removal_lsh_full_exact with threshold Some(MAX_DEDUP_COUNT=4). */
-static void dup_removal(u64map *counts, pairset *set, uint64_t km, int has_pair,
-                        const uint32_t p0[2], const uint32_t p1[2], uint64_t *num_dup,
-                        int no_dedup) {
+/* src/sketch.rs:690-731 dup_removal_lsh_full_exact; c_threshold = Some(MAX_DEDUP_COUNT=4) for single-end reads
+ * (src/constants.rs:14, call :929-939), None = u32::MAX for read pairs with --fpr 0 (call :829-838). */
+static void dup_removal_thr(u64map *counts, pairset *set, uint64_t km, int has_pair,
+                            const uint32_t p0[2], const uint32_t p1[2], uint64_t *num_dup,
+                            int no_dedup, uint32_t c_threshold) {
     uint32_t *c = u64map_entry(counts, km);
-    const uint32_t c_threshold = 4; /* src/constants.rs:14 */
     if (!no_dedup && *c < c_threshold && has_pair) {
         int ret = 0;
         pairkey k0 = {km, p0[0], p0[1]}, k1 = {km, p1[0], p1[1]};
@@ -474,6 +474,29 @@ static void dup_removal(u64map *counts, pairset *set, uint64_t km, int has_pair,
         /* pairset_insert may not move `counts`, so c stays valid */
     }
     (*c)++;
+}
+
+static void dup_removal(u64map *counts, pairset *set, uint64_t km, int has_pair,
+                        const uint32_t p0[2], const uint32_t p1[2], uint64_t *num_dup,
+                        int no_dedup) {
+    dup_removal_thr(counts, set, km, has_pair, p0, p1, num_dup, no_dedup, 4u);
+}
+
+/* src/sketch.rs:658-688 pair_kmer: 16 bases at even / odd offsets from the START of each mate. */
+static int pair_kmer(const uint8_t *s1, size_t len1, const uint8_t *s2, size_t len2, uint32_t p0[2], uint32_t p1[2]) {
+    const size_t kk = 16;
+    if (len1 < 2 * kk + 1 || len2 < 2 * kk + 1) return 0;
+    const uint8_t *L = lut();
+    uint32_t f = 0, g = 0, r = 0, t = 0;
+    for (size_t i = 0; i < kk; i++) {
+        f = (f << 2) | L[s1[2 * i]];
+        r = (r << 2) | L[s2[2 * i]];
+        g = (g << 2) | L[s1[1 + 2 * i]];
+        t = (t << 2) | L[s2[1 + 2 * i]];
+    }
+    p0[0] = f; p0[1] = r;
+    p1[0] = g; p1[1] = t;
+    return 1;
 }
 
 typedef struct { uint64_t h; uint32_t c; } hc;
@@ -554,6 +577,62 @@ int syo_sketch_reads(const uint8_t *bases, const uint64_t *rec_off, uint64_t n_r
         free(ch_hash[ch]); free(ch_rel[ch]);
     }
     free(ch_hash); free(ch_rel); free(ch_n);
+    hc *arr = (hc *)malloc((counts.n + 1) * sizeof(hc));
+    size_t n = 0;
+    for (size_t i = 0; i <= counts.capmask; i++)
+        if (counts.keys[i] != EMPTY_KEY) { arr[n].h = counts.keys[i]; arr[n].c = counts.vals[i]; n++; }
+    qsort(arr, n, sizeof(hc), hc_cmp);
+    int overflow = n > cap;
+    for (size_t i = 0; i < n && i < cap; i++) { out_hash[i] = arr[i].h; out_count[i] = arr[i].c; }
+    *n_out = n;
+    if (mean_read_length) *mean_read_length = mean;
+    if (num_dup_removed) *num_dup_removed = ndup;
+    free(arr);
+    u64map_free(&counts);
+    pairset_free(&set);
+    return overflow;
+}
+
+/* src/sketch.rs:771-895 sketch_pair_sequences with dedup_fpr == 0 (the exact set, :829-838 / :855-865; the
+ * default approximate cuckoo filter is out of scope).  n_pairs = records zipped from the two
+ * files.  Mate 1's k-mers first, then mate 2's that do not occur in mate 1 (:849-853). */
+int syo_sketch_read_pairs(const uint8_t *bases1, const uint64_t *off1, const uint8_t *bases2, const uint64_t *off2,
+                          uint64_t n_pairs, int k, uint64_t c, int no_dedup, int sem, uint64_t *out_hash,
+                          uint32_t *out_count, size_t *n_out, size_t cap, double *mean_read_length,
+                          uint64_t *num_dup_removed) {
+    u64map counts;
+    pairset set;
+    u64map_init(&counts, 1024);
+    pairset_init(&set, 1024);
+    uint64_t ndup = 0;
+    double mean = 0., counter = 0.;
+    size_t vcap = 1024;
+    uint64_t *v1 = (uint64_t *)malloc(vcap * sizeof(uint64_t)), *v2 = (uint64_t *)malloc(vcap * sizeof(uint64_t));
+    for (uint64_t p = 0; p < n_pairs; p++) {
+        const uint8_t *s1 = bases1 + off1[p], *s2 = bases2 + off2[p];
+        const size_t l1 = (size_t)(off1[p + 1] - off1[p]), l2 = (size_t)(off2[p + 1] - off2[p]);
+        const size_t need = (l1 > l2 ? l1 : l2) + 8;
+        if (need > vcap) {
+            vcap = need * 2;
+            v1 = (uint64_t *)realloc(v1, vcap * sizeof(uint64_t));
+            v2 = (uint64_t *)realloc(v2, vcap * sizeof(uint64_t));
+        }
+        const size_t n1 = syo_extract_markers(s1, l1, k, c, sem, v1, vcap);
+        const size_t n2 = syo_extract_markers(s2, l2, k, c, sem, v2, vcap);
+        if (n1 == (size_t)-1 || n2 == (size_t)-1) { free(v1); free(v2); u64map_free(&counts); pairset_free(&set); return 2; }
+        uint32_t p0[2] = {0, 0}, p1[2] = {0, 0};
+        const int has_pair = pair_kmer(s1, l1, s2, l2, p0, p1);
+        counter += 1.;
+        mean = mean + (((double)l1) - mean) / counter; /* :824-826 */
+        for (size_t i = 0; i < n1; i++) dup_removal_thr(&counts, &set, v1[i], has_pair, p0, p1, &ndup, no_dedup, 0xFFFFFFFFu);
+        for (size_t i = 0; i < n2; i++) {
+            int in1 = 0;
+            for (size_t j = 0; j < n1; j++) if (v1[j] == v2[i]) { in1 = 1; break; }   /* temp_vec1.contains(km) */
+            if (in1) continue;
+            dup_removal_thr(&counts, &set, v2[i], has_pair, p0, p1, &ndup, no_dedup, 0xFFFFFFFFu);
+        }
+    }
+    free(v1); free(v2);
     hc *arr = (hc *)malloc((counts.n + 1) * sizeof(hc));
     size_t n = 0;
     for (size_t i = 0; i <= counts.capmask; i++)

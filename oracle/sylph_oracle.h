@@ -68,6 +68,12 @@ int syo_sketch_reads(const uint8_t *bases, const uint64_t *rec_off, uint64_t n_r
                      uint32_t *out_count, size_t *n_out, size_t cap, double *mean_read_length,
                      uint64_t *num_dup_removed);
 
+/* src/sketch.rs:771-895 with dedup_fpr == 0 (exact pair set, no MAX_DEDUP_COUNT cap): mate files as two flat buffers */
+int syo_sketch_read_pairs(const uint8_t *bases1, const uint64_t *off1, const uint8_t *bases2, const uint64_t *off2,
+                          uint64_t n_pairs, int k, uint64_t c, int no_dedup, int sem, uint64_t *out_hash,
+                          uint32_t *out_count, size_t *n_out, size_t cap, double *mean_read_length,
+                          uint64_t *num_dup_removed);
+
 /* ---- containment (src/contain.rs) ---- */
 typedef struct {
     int k;

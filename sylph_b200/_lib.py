@@ -57,6 +57,7 @@ SIGNATURES = {
     "syl_seed_batch_packed2": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _vp, _u64, _pu64]),
     "syl_sketch_reads": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _pp]),
     "syl_sketch_reads_packed2": (_i, [_vp, _i, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _pp]),
+    "syl_sketch_read_pairs": (_i, [_vp, _i, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _pp]),
     "syl_pack2": (_i, [_vp, _u64, _vp, _i]),
     "syl_pack_threads": (_i, []),
     "syl_sample_upload": (_i, [_vp, _i, _vp, _vp, _u64, _i, _u64, _pp]),

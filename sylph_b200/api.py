@@ -167,6 +167,22 @@ class Context:
         _lib.check(L.syl_sketch_reads(self._h, mem_b, pb, nb, po, no - 1, k, c, int(no_dedup), sem, C.byref(h)))
         return Sample(self, h)
 
+    def sketch_pair_sequences(self, bases1, rec_off1, bases2, rec_off2, k=31, c=200, no_dedup=False, sem=SEM_AVX2):
+        """Batched body of sketch_pair_sequences with --fpr 0 (src/sketch.rs:771-895): mate i of pair p is record p of
+        buffer i; pairs = min(records) of the two buffers -> Sample."""
+        _CTX_STREAM[0] = self._stream
+        L = _lib.lib()
+        m1, p1, n1, k1 = _arg(bases1, np.uint8)
+        mo1, po1, no1, k2 = _arg(rec_off1, np.uint64)
+        m2, p2, n2, k3 = _arg(bases2, np.uint8)
+        mo2, po2, no2, k4 = _arg(rec_off2, np.uint64)
+        if len({m1, mo1, m2, mo2}) != 1:
+            raise ValueError("all four buffers must live in the same memory space")
+        n_pairs = min(no1, no2) - 1
+        h = C.c_void_p()
+        _lib.check(L.syl_sketch_read_pairs(self._h, m1, p1, n1, po1, p2, n2, po2, n_pairs, k, c, int(no_dedup), sem, C.byref(h)))
+        return Sample(self, h)
+
     def upload_sample(self, hashes, counts, k=31, c=200):
         _CTX_STREAM[0] = self._stream
         L = _lib.lib()

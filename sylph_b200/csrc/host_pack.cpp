@@ -4,6 +4,7 @@
 #include "host_pack.hpp"
 
 #include <immintrin.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -99,9 +100,26 @@ int default_pack_threads() {
         const int lw = atoi(e);
         if (lw > 1) hc = std::max(1u, hc / (unsigned)lw);
     }
+    // a container's CPU quota (cgroup v2 cpu.max / v1 cfs_quota): threads beyond it only get the process throttled
+    {
+        long long quota = -1, period = 100000;
+        if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+            char q[64] = {0};
+            if (fscanf(f, "%63s %lld", q, &period) >= 1 && strcmp(q, "max") != 0) quota = atoll(q);
+            fclose(f);
+        } else if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+            if (fscanf(g, "%lld", &quota) != 1) quota = -1;
+            fclose(g);
+            if (FILE *h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(h, "%lld", &period) != 1) period = 100000; fclose(h); }
+        }
+        if (quota > 0 && period > 0) {  // leave one core's worth for the thread that feeds the GPU
+            const unsigned q = (unsigned)((quota + period - 1) / period);
+            return (int)std::max(1u, std::min(std::min(hc, 32u), q > 1 ? q - 1 : 1u));
+        }
+    }
     // the packer is memory-bound well before all cores of a big host are busy (measured on a 2 x 32-core
     // host: 16 threads 68 GB/s, 32 threads 85 GB/s, 64 threads 90 GB/s of ASCII input)
-    return (int)std::max(1u, std::min(hc / 2u, 32u));
+    return (int)std::max(1u, std::min(hc > 2 ? hc / 2u : hc, 32u));
 }
 
 PackPool::PackPool(int n_threads) {
@@ -122,6 +140,8 @@ void PackPool::start(const std::vector<PackItem> *items, const std::vector<uint3
         std::lock_guard<std::mutex> lk(mu_);
         items_ = items;
         remaining_ = *chunk_items;
+        taken_.assign(chunk_items->size(), 0);
+        skipped_.assign(chunk_items->size(), 0);
         next_ = 0;
         done_ = 0;
         gate_ = gate;
@@ -145,13 +165,16 @@ void PackPool::worker() {
         });
         if (stop_) return;
         const PackItem it = (*items_)[next_++];
-        lk.unlock();
-        if (it.src) {
-            pack2_range(it.src, it.n, it.dst);
-        } else {
-            for (uint64_t j = 0; j < it.off_n; j++) it.off_dst[j] = (uint32_t)(it.off_src[j] - it.off_base);
+        taken_[it.chunk]++;
+        if (!skipped_[it.chunk]) {
+            lk.unlock();
+            if (it.src) {
+                pack2_range(it.src, it.n, it.dst);
+            } else {
+                for (uint64_t j = 0; j < it.off_n; j++) it.off_dst[j] = (uint32_t)(it.off_src[j] - it.off_base);
+            }
+            lk.lock();
         }
-        lk.lock();
         done_++;
         if (--remaining_[it.chunk] == 0 || done_ == items_->size()) cv_done_.notify_all();
     }
@@ -160,6 +183,18 @@ void PackPool::worker() {
 void PackPool::wait_chunk(uint32_t c) {
     std::unique_lock<std::mutex> lk(mu_);
     cv_done_.wait(lk, [&]() { return remaining_[c] == 0; });
+}
+
+bool PackPool::chunk_done(uint32_t c) {
+    std::lock_guard<std::mutex> lk(mu_);
+    return remaining_[c] == 0 && !skipped_[c];
+}
+
+bool PackPool::try_skip_chunk(uint32_t c) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (taken_[c] != 0 || skipped_[c]) return false;
+    skipped_[c] = 1;
+    return true;
 }
 
 void PackPool::finish() {

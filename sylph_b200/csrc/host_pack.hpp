@@ -41,6 +41,9 @@ public:
     void start(const std::vector<PackItem> *items, const std::vector<uint32_t> *chunk_items, int64_t gate);
     void open_gate(int64_t gate);
     void wait_chunk(uint32_t c);
+    bool chunk_done(uint32_t c);
+    // take chunk c away from the workers if none of its items has been started; true: the caller handles it
+    bool try_skip_chunk(uint32_t c);
     void finish();  // every item processed; must be called before the next start()
 
 private:
@@ -51,6 +54,8 @@ private:
     bool stop_ = false;
     const std::vector<PackItem> *items_ = nullptr;
     std::vector<uint32_t> remaining_;  // per chunk
+    std::vector<uint32_t> taken_;      // per chunk: items handed out
+    std::vector<uint8_t> skipped_;     // per chunk: taken over by the caller
     size_t next_ = 0, done_ = 0;
     int64_t gate_ = -1;
 };

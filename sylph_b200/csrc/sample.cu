@@ -118,6 +118,90 @@ k_events_fix(EventRec *__restrict__ ev, const uint32_t *__restrict__ pend, const
     }
 }
 
+// Read pairs (src/sketch.rs:658-688 pair_kmer): the two keys come from the first 32 bases of BOTH mates; every event of
+// the pair carries them.  Events arrive with recflag = pair << 1 | EV_PENDING; the result is
+// recflag = pair << 2 | mate << 1 | NO_PAIR (a mate shorter than 33 bp, or --no-dedup).
+__global__ void __launch_bounds__(EV_THREADS)
+k_events_fix_paired(EventRec *__restrict__ ev, const uint32_t *__restrict__ pend, const unsigned long long *__restrict__ p_begin,
+                    const unsigned long long *__restrict__ p_end, uint64_t ev_cap, const uint8_t *__restrict__ bases1,
+                    const uint64_t *__restrict__ off1, const uint8_t *__restrict__ bases2, const uint64_t *__restrict__ off2,
+                    uint64_t mate, int no_dedup) {
+    __shared__ uint8_t lut[4][256];
+    for (int i = threadIdx.x; i < 256; i += EV_THREADS) {
+        const uint32_t code = byte_to_seq((uint32_t)i);
+        lut[0][i] = (uint8_t)(code << 6);
+        lut[1][i] = (uint8_t)(code << 4);
+        lut[2][i] = (uint8_t)(code << 2);
+        lut[3][i] = (uint8_t)code;
+    }
+    __syncthreads();
+    const uint64_t i0 = *p_begin, i1 = *p_end;
+    for (uint64_t i = i0 + (uint64_t)blockIdx.x * EV_THREADS + threadIdx.x; i < i1; i += (uint64_t)gridDim.x * EV_THREADS) {
+        const uint32_t ei = pend[i];
+        if (ei >= ev_cap) continue;
+        EventRec *e = ev + ei;
+        const uint64_t pair = (e->recflag & ~EV_PENDING) >> 1;
+        const uint64_t a1 = off1[pair], a2 = off2[pair];
+        const uint64_t L1 = off1[pair + 1] - a1, L2 = off2[pair + 1] - a2;
+        const bool has = !no_dedup && L1 >= 33 && L2 >= 33;  // 2 * 16 + 1 (:660)
+        uint64_t p0 = 0, p1 = 0;
+        if (has) {
+            uint32_t x[8];
+            load32_unaligned(bases1 + a1, x);
+            const uint32_t f = pack16(x, 0x6420, lut), g = pack16(x, 0x7531, lut);
+            load32_unaligned(bases2 + a2, x);
+            const uint32_t r = pack16(x, 0x6420, lut), t = pack16(x, 0x7531, lut);
+            p0 = ((uint64_t)f << 32) | r;  // ([kmer_f, kmer_r], [kmer_g, kmer_t]) (:685)
+            p1 = ((uint64_t)g << 32) | t;
+        }
+        e->recflag = (pair << 2) | (mate << 1) | (has ? 0ull : NO_PAIR);
+        e->p0 = p0;
+        e->p1 = p1;
+    }
+}
+
+// One WARP replays dup_removal_lsh_full_exact(.., threshold None) (src/sketch.rs:690-731, call :829-865) for one
+// k-mer of a paired sample: events sorted by (pair, mate); a mate-2 event whose k-mer also occurs in mate 1 of the
+// same pair is skipped (:849-853); the dedup set never stops growing (no MAX_DEDUP_COUNT), membership is tested by
+// the 32 lanes in parallel.  set[] is this segment's private slice of a global scratch array (2 slots per event).
+__global__ void k_dedup_paired(const uint64_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_len, uint64_t n_seg,
+                               const uint32_t *__restrict__ order, const uint64_t *__restrict__ recflag,
+                               const uint64_t *__restrict__ p0, const uint64_t *__restrict__ p1, int no_dedup,
+                               uint64_t *__restrict__ set, uint32_t *__restrict__ count, unsigned long long *__restrict__ n_dup) {
+    const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_seg) return;
+    const uint64_t start = seg_off[s];
+    const uint32_t len = seg_len[s];
+    uint64_t *S = set + 2 * start;
+    uint32_t nset = 0, c = 0, dups = 0;
+    uint64_t last_m1_pair = 0xFFFFFFFFFFFFFFFFull;
+    for (uint32_t e = 0; e < len; e++) {
+        const uint32_t evi = order[start + e];
+        const uint64_t rf = recflag[evi];
+        const uint64_t pair = rf >> 2;
+        if (((rf >> 1) & 1ull) == 0) last_m1_pair = pair;
+        else if (pair == last_m1_pair) continue;  // temp_vec1.contains(km)
+        if (no_dedup || (rf & NO_PAIR)) { c++; continue; }
+        const uint64_t a = p0[evi], b = p1[evi];
+        bool fa = false, fb = false;
+        for (uint32_t q = lane; q < nset; q += 32) { const uint64_t v = S[q]; fa |= v == a; fb |= v == b; }
+        fa = __any_sync(0xffffffffu, fa);
+        fb = __any_sync(0xffffffffu, fb) || (!fa && a == b);  // the second look-up sees the first key's insertion
+        if (lane == 0) {
+            if (!fa) S[nset] = a;
+            if (!fb) S[nset + (fa ? 0 : 1)] = b;
+        }
+        nset += (fa ? 0u : 1u) + (fb ? 0u : 1u);
+        __syncwarp();
+        if ((fa || fb) && c > 0) dups++; else c++;
+    }
+    if (lane == 0) {
+        count[s] = c;
+        if (dups) atomicAdd(n_dup, (unsigned long long)dups);
+    }
+}
+
 __global__ void k_off32_to_64(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
@@ -634,6 +718,7 @@ struct SampleBuilder {
     uint64_t c;
     int no_dedup, sem;
     uint64_t n_reads = 0, n_bases = 0, cap = 0;
+    bool paired = false;     // read pairs (syl_sketch_read_pairs): events wait for k_events_fix_paired, generic post-pass only
     DevBuf<EventRec> b_ev;   // event array (a scratch block of the ctx cache)
     DevBuf<uint32_t> b_pend; // indices of events whose pair keys are filled in by k_events_fix
     // Post-pass buckets: fixed before the first batch from the expected number of events, so that
@@ -668,7 +753,9 @@ struct SampleBuilder {
 
     // one batch of reads, device resident (ASCII bytes or 2-bit words); read indices continue from the
     // previous batch.  The seeding kernel appends the batch's events (hash, read, pair keys) to the event array.
-    int add(const uint8_t *d_bases, const uint32_t *d_packed, uint64_t nb, const uint64_t *d_off, uint64_t off_bias, uint64_t nr) {
+    // rec_base: index of the batch's first read in the sample (batches may arrive in any order)
+    int add(const uint8_t *d_bases, const uint32_t *d_packed, uint64_t nb, const uint64_t *d_off, uint64_t off_bias, uint64_t nr,
+            uint64_t rec_base) {
         cudaStream_t st = ctx->stream;
         if (nr == 0) return SYL_OK;
         unsigned long long *dc = d_count();
@@ -676,13 +763,13 @@ struct SampleBuilder {
         SeedJob job;
         job.d_bases = d_bases; job.d_packed = d_packed; job.n_bases = nb; job.d_rec_off = d_off; job.off_bias = off_bias;
         job.n_rec = nr; job.k = k; job.c = c; job.sem = sem; job.with_pos = 0; job.d_out = b_ev.p; job.cap = cap;
-        job.emit_events = 1; job.rec_base = n_reads; job.no_dedup = no_dedup; job.d_pend = b_pend.p;
+        job.emit_events = 1; job.rec_base = rec_base; job.no_dedup = paired ? 2 : no_dedup; job.d_pend = b_pend.p;
         job.d_bucket_cnt = cnt.p; job.Mb = Mb; job.nbk = nbk; job.d_count = dc; job.d_pend_count = dc + 1;
         SYL_TRY(seed_enqueue(ctx, job));
-        if (!no_dedup && nb) {  // reads cut by a tile edge: their pair keys come from global memory
+        if (!no_dedup && !paired && nb) {  // reads cut by a tile edge: their pair keys come from global memory
             const uint64_t n_words = (nb + 15) / 16;
-            if (d_packed) k_events_fix<true><<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b_ev.p, b_pend.p, dc + 3, dc + 1, cap, nullptr, d_packed, n_words, d_off, off_bias, n_reads);
-            else k_events_fix<false><<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b_ev.p, b_pend.p, dc + 3, dc + 1, cap, d_bases, nullptr, 0, d_off, off_bias, n_reads);
+            if (d_packed) k_events_fix<true><<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b_ev.p, b_pend.p, dc + 3, dc + 1, cap, nullptr, d_packed, n_words, d_off, off_bias, rec_base);
+            else k_events_fix<false><<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b_ev.p, b_pend.p, dc + 3, dc + 1, cap, d_bases, nullptr, 0, d_off, off_bias, rec_base);
             ctx->launches++;
             SYL_CUDA(cudaGetLastError());
         }
@@ -711,8 +798,8 @@ struct SampleBuilder {
         size_t tmp_bytes = 0, t2 = 0;
         uint32_t *ord = idx_a.p;  // final event order
         uint64_t *hs = key_a.p;   // hashes in final order
-        if (!no_dedup) {
-            const int rec_bits = bits_for((n_reads << 1) | 1);
+        if (!no_dedup || paired) {
+            const int rec_bits = paired ? bits_for((n_reads << 2) | 3) : bits_for((n_reads << 1) | 1);
             cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ev_recflag, key_b.p, idx_a.p, idx_b.p, N, 0, rec_bits, st);
             cub::DeviceRadixSort::SortPairs(nullptr, t2, key_a.p, key_b.p, idx_b.p, idx_a.p, N, 0, hash_bits, st);
             tmp_bytes = std::max(tmp_bytes, t2);
@@ -746,7 +833,7 @@ struct SampleBuilder {
         const uint64_t U = ctx->h_counters[1];
         ctx->launches += 1;
         SYL_TRY(count.alloc(std::max<uint64_t>(U, 1), st));
-        if (no_dedup) {
+        if (no_dedup && !paired) {
             k_copy_len<<<nblk(U, 256), 256, 0, st>>>(seg_len.p, count.p, U);
             ctx->launches++;
         } else {
@@ -756,7 +843,8 @@ struct SampleBuilder {
             SYL_TRY(set.alloc(2 * N, st));
             unsigned long long *d_ndup = reinterpret_cast<unsigned long long *>(ctx->d_counters + 2);
             SYL_CUDA(cudaMemsetAsync(d_ndup, 0, 8, st));
-            k_dedup<<<nblk(U, 128), 128, 0, st>>>(seg_off.p, seg_len.p, U, ord, ev_recflag, ev_p0, ev_p1, set.p, count.p, d_ndup);
+            if (paired) k_dedup_paired<<<nblk(U * 32, 128), 128, 0, st>>>(seg_off.p, seg_len.p, U, ord, ev_recflag, ev_p0, ev_p1, no_dedup, set.p, count.p, d_ndup);
+            else k_dedup<<<nblk(U, 128), 128, 0, st>>>(seg_off.p, seg_len.p, U, ord, ev_recflag, ev_p0, ev_p1, set.p, count.p, d_ndup);
             ctx->launches += 2;
             SYL_CUDA(cudaGetLastError());
             SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 2, d_ndup, 8, cudaMemcpyDeviceToHost, st));
@@ -782,7 +870,8 @@ struct SampleBuilder {
         auto fail = [&](int rc) { syl_sample_free(s); return rc; };
 #define SB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? SYL_ERR_OOM : SYL_ERR_CUDA); } } while (0)
         if (n_reads == 0 || n_bases == 0) { *out = s; return SYL_OK; }
-        static const bool force_sort = []() { const char *e = getenv("SYL_SAMPLE_POSTPASS"); return e && std::string(e) == "sort"; }();
+        static const bool env_sort = []() { const char *e = getenv("SYL_SAMPLE_POSTPASS"); return e && std::string(e) == "sort"; }();
+        const bool force_sort = env_sort || paired;
         static const uint32_t grp_cap = []() { const char *e = getenv("SYL_GROUP_CAP"); int v = e ? atoi(e) : GRP_CAP; return (uint32_t)std::min(std::max(v, 32), GRP_CAP); }();
         unsigned long long *dc = d_count();
         EventRec *ev = b_ev.p;
@@ -934,6 +1023,10 @@ struct HostIngest {
     uint64_t *d_off64[ING_SLOTS] = {};
     uint64_t cap_words = 0, cap_recs = 0;
     cudaEvent_t ev_copied[ING_SLOTS] = {}, ev_used[ING_SLOTS] = {};
+    // chunks that cross the link as ASCII while the packers are behind (pinned caller memory only)
+    uint8_t *d_asc[2] = {};
+    uint64_t *d_aoff[2] = {};
+    cudaEvent_t ev_a_copied[2] = {}, ev_a_used[2] = {};
     cudaStream_t copy_stream = nullptr;
 
     void release_buffers() {
@@ -946,6 +1039,12 @@ struct HostIngest {
             h_words[i] = h_off[i] = d_words[i] = d_off32[i] = nullptr;
             d_off64[i] = nullptr;
         }
+        for (int i = 0; i < 2; i++) {
+            if (d_asc[i]) cudaFree(d_asc[i]);
+            if (d_aoff[i]) cudaFree(d_aoff[i]);
+            d_asc[i] = nullptr;
+            d_aoff[i] = nullptr;
+        }
         cap_words = cap_recs = 0;
     }
     int ensure(uint64_t words, uint64_t recs) {
@@ -954,6 +1053,10 @@ struct HostIngest {
             for (int i = 0; i < ING_SLOTS; i++) {
                 SYL_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
                 SYL_CUDA(cudaEventCreateWithFlags(&ev_used[i], cudaEventDisableTiming));
+            }
+            for (int i = 0; i < 2; i++) {
+                SYL_CUDA(cudaEventCreateWithFlags(&ev_a_copied[i], cudaEventDisableTiming));
+                SYL_CUDA(cudaEventCreateWithFlags(&ev_a_used[i], cudaEventDisableTiming));
             }
         }
         if (words <= cap_words && recs <= cap_recs) return SYL_OK;
@@ -967,6 +1070,10 @@ struct HostIngest {
             SYL_CUDA(cudaMalloc((void **)&d_off32[i], (r + 16) * 4));
             SYL_CUDA(cudaMalloc((void **)&d_off64[i], (r + 16) * 8));
         }
+        for (int i = 0; i < 2; i++) {
+            SYL_CUDA(cudaMalloc((void **)&d_asc[i], (w + 16) * 16));
+            SYL_CUDA(cudaMalloc((void **)&d_aoff[i], (r + 16) * 8));
+        }
         cap_words = w;
         cap_recs = r;
         return SYL_OK;
@@ -977,6 +1084,10 @@ struct HostIngest {
         for (int i = 0; i < ING_SLOTS; i++) {
             if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
             if (ev_used[i]) cudaEventDestroy(ev_used[i]);
+        }
+        for (int i = 0; i < 2; i++) {
+            if (ev_a_copied[i]) cudaEventDestroy(ev_a_copied[i]);
+            if (ev_a_used[i]) cudaEventDestroy(ev_a_used[i]);
         }
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
@@ -1034,31 +1145,78 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
         chunk_items[ci] = n_items;
     }
     I.pool->start(&items, &chunk_items, ING_SLOTS - 1);
-    int rc = SYL_OK;
-    for (size_t ci = 0; ci < chunks.size(); ci++) {
-        const Chunk &c = chunks[ci];
-        const int slot = (int)(ci % ING_SLOTS);
-        const uint64_t nw = (c.nb + 15) / 16, no = c.r1 - c.r0 + 1;
-        I.pool->wait_chunk((uint32_t)ci);
-        cudaStreamWaitEvent(cs, I.ev_used[slot], 0);  // the seeding of the previous chunk in this slot is done
-        if (cudaMemcpyAsync(I.d_words[slot], I.h_words[slot], nw * 4, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
-            cudaMemcpyAsync(I.d_off32[slot], I.h_off[slot], no * 4, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
-            rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
-        }
-        cudaEventRecord(I.ev_copied[slot], cs);
-        cudaStreamWaitEvent(st, I.ev_copied[slot], 0);
-        k_off32_to_64<<<nblk(no, 256), 256, 0, st>>>(I.d_off32[slot], no, I.d_off64[slot]);
-        ctx->launches++;
-        rc = b.add(nullptr, I.d_words[slot], c.nb, I.d_off64[slot], 0, c.r1 - c.r0);
-        cudaEventRecord(I.ev_used[slot], st);
-        if (rc != SYL_OK) break;
-        if (ci >= 1) {  // the pinned buffers of chunk ci-1 have crossed the link: the packers may refill them
-            cudaEventSynchronize(I.ev_copied[(ci - 1) % ING_SLOTS]);
-            I.pool->open_gate((int64_t)(ci - 1 + ING_SLOTS));
-        }
+    // Two resources work in parallel: the packers (host memory bandwidth / CPU quota) and the PCIe link.  Packed
+    // chunks are consumed from the front in order; whenever the front chunk is not packed yet and no ASCII copy
+    // is in flight, a chunk nobody has started is taken from the BACK and shipped as ASCII (4x the bytes, but the
+    // link would idle otherwise).  Needs pinned caller memory (a pageable copy would block this thread).
+    bool steal_ok = false;
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, bases) == cudaSuccess) steal_ok = pa.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+        const char *e = getenv("SYL_HOST_INGEST");
+        if (e && std::string(e) == "packed-only") steal_ok = false;
     }
-    I.pool->open_gate((int64_t)1 << 60);  // error exit: let the workers drain
+    const bool force_steal = getenv("SYL_INGEST_FORCE_STEAL") != nullptr;  // tests: alternate packed / ASCII chunks
+    int rc = SYL_OK;
+    int64_t f = 0, bk = (int64_t)chunks.size() - 1, last_packed = -1;
+    int a_slot = 0, a_last = -1;
+    uint64_t n_ascii = 0, n_packed = 0;
+    while (f <= bk && rc == SYL_OK) {
+        const bool steal_first = force_steal && steal_ok && n_ascii <= n_packed;
+        if (!steal_first && I.pool->chunk_done((uint32_t)f)) {  // ---- packed chunk from the front
+            const size_t ci = (size_t)f;
+            const Chunk &c = chunks[ci];
+            const int slot = (int)(ci % ING_SLOTS);
+            const uint64_t nw = (c.nb + 15) / 16, no = c.r1 - c.r0 + 1;
+            cudaStreamWaitEvent(cs, I.ev_used[slot], 0);  // the seeding of the previous chunk in this slot is done
+            if (cudaMemcpyAsync(I.d_words[slot], I.h_words[slot], nw * 4, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+                cudaMemcpyAsync(I.d_off32[slot], I.h_off[slot], no * 4, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
+                rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
+            }
+            cudaEventRecord(I.ev_copied[slot], cs);
+            cudaStreamWaitEvent(st, I.ev_copied[slot], 0);
+            k_off32_to_64<<<nblk(no, 256), 256, 0, st>>>(I.d_off32[slot], no, I.d_off64[slot]);
+            ctx->launches++;
+            rc = b.add(nullptr, I.d_words[slot], c.nb, I.d_off64[slot], 0, c.r1 - c.r0, c.r0);
+            cudaEventRecord(I.ev_used[slot], st);
+            if (last_packed >= 0) {  // the pinned buffers of the previous packed chunk have crossed the link: refill them
+                cudaEventSynchronize(I.ev_copied[last_packed % ING_SLOTS]);
+                I.pool->open_gate(last_packed + ING_SLOTS);
+            }
+            last_packed = f;
+            f++;
+            n_packed++;
+            continue;
+        }
+        const bool ascii_busy = !force_steal && a_last >= 0 && cudaEventQuery(I.ev_a_copied[a_last]) == cudaErrorNotReady;
+        if (steal_ok && !ascii_busy && bk > f && I.pool->try_skip_chunk((uint32_t)bk)) {  // ---- ASCII chunk from the back
+            const Chunk &c = chunks[(size_t)bk];
+            const int slot = a_slot;
+            a_slot ^= 1;
+            const uint64_t nr = c.r1 - c.r0;
+            cudaStreamWaitEvent(cs, I.ev_a_used[slot], 0);
+            if (cudaMemcpyAsync(I.d_asc[slot], bases + c.base, c.nb, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+                cudaMemcpyAsync(I.d_aoff[slot], rec_off + c.r0, (nr + 1) * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
+                rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
+            }
+            cudaEventRecord(I.ev_a_copied[slot], cs);
+            cudaStreamWaitEvent(st, I.ev_a_copied[slot], 0);
+            rc = b.add(I.d_asc[slot], nullptr, c.nb, I.d_aoff[slot], c.base, nr, c.r0);
+            cudaEventRecord(I.ev_a_used[slot], st);
+            a_last = slot;
+            n_ascii++;
+            bk--;
+            continue;
+        }
+        if (steal_first) { n_packed = n_ascii + 1; continue; }  // nothing left to take from the back: go on with packed chunks
+        I.pool->wait_chunk((uint32_t)f);  // the packers are on it (or the only chunks left are theirs)
+    }
+    I.pool->open_gate((int64_t)1 << 60);  // all remaining items (skipped chunks included) drain
     I.pool->finish();
+    static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
+    if (dbg) fprintf(stderr, "[host ingest] %zu chunks: %llu shipped as ASCII, %zu packed by %d threads\n", chunks.size(),
+                     (unsigned long long)n_ascii, chunks.size() - (size_t)n_ascii, I.pool->threads());
     if (rc != SYL_OK) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
     return rc;
 }
@@ -1121,7 +1279,7 @@ static int feed_host_ascii(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases,
         }
         if (pend.valid) {
             cudaStreamWaitEvent(st, ctx->ev_copied[pend.slot], 0);
-            rc = b.add(ctx->stage_b[pend.slot], nullptr, pend.nb, ctx->stage_o[pend.slot], pend.bias, pend.nr);
+            rc = b.add(ctx->stage_b[pend.slot], nullptr, pend.nb, ctx->stage_o[pend.slot], pend.bias, pend.nr, b.n_reads);
             cudaEventRecord(ctx->ev_used[pend.slot], st);
             if (rc != SYL_OK) break;
         }
@@ -1156,14 +1314,14 @@ static int sketch_reads_impl(syl_ctx *ctx, int mem, const uint8_t *bases, const 
         DevBuf<uint32_t> hp;   // host packed input staged whole
         DevBuf<uint64_t> ho;
         if (mem == SYL_MEM_DEVICE) {
-            rc = b.add(bases, packed, n_bases, rec_off, 0, n_reads);
+            rc = b.add(bases, packed, n_bases, rec_off, 0, n_reads, 0);
         } else if (packed) {
             const uint64_t nw = (n_bases + 15) / 16;
             SYL_TRY(hp.alloc(nw + 16, st));
             SYL_TRY(ho.alloc(n_reads + 1, st));
             if (nw) SYL_CUDA(cudaMemcpyAsync(hp.p, packed, nw * 4, cudaMemcpyHostToDevice, st));
             SYL_CUDA(cudaMemcpyAsync(ho.p, rec_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-            rc = b.add(nullptr, hp.p, n_bases, ho.p, 0, n_reads);
+            rc = b.add(nullptr, hp.p, n_bases, ho.p, 0, n_reads, 0);
         } else if (n_reads && n_bases) {
             rc = host_ascii ? feed_host_ascii(ctx, b, bases, rec_off, n_reads) : feed_host_packed(ctx, b, bases, rec_off, n_reads);
         }
@@ -1196,6 +1354,60 @@ int syl_sketch_reads_packed2(syl_ctx *ctx, int mem, const uint32_t *packed, uint
                              int sem, syl_sample **out) {
     if (!packed && n_bases) { set_error("NULL argument"); return SYL_ERR_ARG; }
     return sketch_reads_impl(ctx, mem, nullptr, packed, n_bases, rec_off, n_reads, k, c, no_dedup, sem, out);
+}
+
+int syl_sketch_read_pairs(syl_ctx *ctx, int mem, const uint8_t *bases1, uint64_t n_bases1, const uint64_t *rec_off1,
+                          const uint8_t *bases2, uint64_t n_bases2, const uint64_t *rec_off2, uint64_t n_pairs,
+                          int k, uint64_t c, int no_dedup, int sem, syl_sample **out) {
+    if (!ctx || !out || (!bases1 && n_bases1) || (!bases2 && n_bases2) || !rec_off1 || !rec_off2) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    if (c == 0) { set_error("c must be >= 1"); return SYL_ERR_ARG; }
+    if (mem != SYL_MEM_HOST && mem != SYL_MEM_DEVICE) { set_error("bad mem"); return SYL_ERR_ARG; }
+    *out = nullptr;
+    SYL_CUDA(cudaSetDevice(ctx->device));
+    syl::tl_ctx = ctx;
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint8_t> hb1, hb2;
+    DevBuf<uint64_t> ho1, ho2;
+    const uint8_t *d1 = bases1, *d2 = bases2;
+    const uint64_t *o1 = rec_off1, *o2 = rec_off2;
+    if (mem == SYL_MEM_HOST) {
+        SYL_TRY(hb1.alloc(n_bases1 + 64, st)); SYL_TRY(hb2.alloc(n_bases2 + 64, st));
+        SYL_TRY(ho1.alloc(n_pairs + 1, st)); SYL_TRY(ho2.alloc(n_pairs + 1, st));
+        if (n_bases1) SYL_CUDA(cudaMemcpyAsync(hb1.p, bases1, n_bases1, cudaMemcpyHostToDevice, st));
+        if (n_bases2) SYL_CUDA(cudaMemcpyAsync(hb2.p, bases2, n_bases2, cudaMemcpyHostToDevice, st));
+        SYL_CUDA(cudaMemcpyAsync(ho1.p, rec_off1, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+        SYL_CUDA(cudaMemcpyAsync(ho2.p, rec_off2, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+        d1 = hb1.p; d2 = hb2.p; o1 = ho1.p; o2 = ho2.p;
+    }
+    uint64_t cap_override = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        SampleBuilder b{ctx, k, c, no_dedup, sem};
+        b.paired = true;
+        b.expect_bases = n_bases1 + n_bases2;
+        b.expect_reads = 2 * n_pairs;
+        SYL_TRY(b.begin(cap_override));
+        unsigned long long *dc = b.d_count();
+        // mate 1, then mate 2: both use the PAIR index as read index; the pending list tells the mates apart
+        SYL_TRY(b.add(d1, nullptr, n_bases1, o1, 0, n_pairs, 0));
+        SYL_CUDA(cudaMemcpyAsync(dc + 17, dc + 1, 8, cudaMemcpyDeviceToDevice, st));  // pending entries of mate 1
+        SYL_TRY(b.add(d2, nullptr, n_bases2, o2, 0, n_pairs, 0));
+        SYL_CUDA(cudaMemsetAsync(dc + 18, 0, 8, st));
+        if (n_pairs) {
+            k_events_fix_paired<<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b.b_ev.p, b.b_pend.p, dc + 18, dc + 17, b.cap, d1, o1, d2, o2, 0, no_dedup);
+            k_events_fix_paired<<<ctx->num_sms * 2, EV_THREADS, 0, st>>>(b.b_ev.p, b.b_pend.p, dc + 17, dc + 1, b.cap, d1, o1, d2, o2, 1, no_dedup);
+            ctx->launches += 2;
+            SYL_CUDA(cudaGetLastError());
+        }
+        b.n_reads = n_pairs;       // mean_read_length = mean length of mate 1 (src/sketch.rs:824-826)
+        b.n_bases = n_bases1;
+        uint64_t need = 0;
+        const int rc = b.finish(out, &need);
+        if (rc == SYL_ERR_CAPACITY) { cap_override = need + 16; continue; }
+        if (rc == SYL_OK) SYL_CUDA(cudaStreamSynchronize(st));  // the staged inputs go out of scope
+        return rc;
+    }
+    set_error("event capacity retry failed");
+    return SYL_ERR_CAPACITY;
 }
 
 int syl_pack_threads(void) { return default_pack_threads(); }

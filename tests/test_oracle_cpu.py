@@ -102,6 +102,46 @@ def test_read_sketch_dedup_vs_pyref():
     assert O.sketch_reads(buf, off, k=31, c=7)[3] > 50
 
 
+def make_pairs(rng, n, genome, with_short=True):
+    """read pairs from one genome: exact duplicate pairs, pairs that share only mate 1's start, mates that overlap
+    (k-mers present in both mates), short mates (< 33 bp: no pair key)"""
+    r1, r2 = [], []
+    G = len(genome)
+    for _ in range(n):
+        st = int(rng.integers(0, G - 400))
+        l1, l2 = int(rng.choice([70, 100, 150])), int(rng.choice([70, 100, 150]))
+        gap = int(rng.choice([-60, 0, 40]))
+        a, b = genome[st:st + l1], genome[st + l1 + gap:st + l1 + gap + l2]
+        if with_short and rng.random() < 0.05:
+            b = b[:20]
+        r1.append(a)
+        r2.append(b)
+        if rng.random() < 0.35:
+            r1.append(a)
+            r2.append(b)
+        if rng.random() < 0.15:
+            r1.append(a)
+            r2.append(genome[st + 17:st + 17 + l2])
+    return r1, r2
+
+
+def test_paired_read_sketch_exact_set_vs_pyref():
+    """sketch_pair_sequences with --fpr 0 (src/sketch.rs:771-895): C oracle == pure-Python restatement."""
+    rng = np.random.default_rng(21)
+    genome = rand_seq(rng, 5000, b"ACGT")
+    r1, r2 = make_pairs(rng, 300, genome)
+    r1 += [b"A" * 150, b"A" * 150, b""]
+    r2 += [b"A" * 150, b"A" * 150, b"ACGT" * 20]
+    b1, o1 = flatten(r1)
+    b2, o2 = flatten(r2)
+    for no_dedup in (False, True):
+        h, c, mean, nd = O.sketch_read_pairs(b1, o1, b2, o2, k=31, c=7, no_dedup=no_dedup)
+        ec, emean, end = R.sketch_read_pairs(r1, r2, 31, 7, no_dedup=no_dedup)
+        assert dict(zip(h.tolist(), c.tolist())) == ec
+        assert nd == end and abs(mean - emean) < 1e-12
+    assert O.sketch_read_pairs(b1, o1, b2, o2, k=31, c=7)[3] > 100
+
+
 def test_poisson_cutoffs_and_device_table():
     exp = [11, 15, 18, 21, 24, 26, 28, 31, 33, 35, 37, 39, 41, 43, 45, 46, 48, 50, 52, 53, 55, 57, 58, 60, 62, 63, 65, 67, 68]
     got = [O.poisson_cutoff(m) for m in range(1, 30)]

@@ -114,3 +114,31 @@ def test_warp_tile_lengths(ctx, monkeypatch, tw):
     for s in (ctx.sketch_sequences(buf, off, c=7), ctx.sketch_sequences(pack2(buf), off, c=7, packed_bases=len(buf))):
         h, c = s.download()
         assert np.array_equal(h, eh) and np.array_equal(c, ec) and s.num_dup_removed == nd
+
+
+def test_host_ingest_mixed_packed_and_ascii_chunks(ctx, monkeypatch):
+    """Pinned caller memory: chunks the packers have not started may cross the link as ASCII (taken from the back
+    of the sample, out of order — the read indices travel with the chunk).  Forced here to alternate."""
+    import torch
+    from oracle import oracle as O
+    rng = np.random.default_rng(6)
+    lengths = list(rng.integers(0, 400, size=6000)) + [150] * 3000 + [70000, 33, 0]
+    buf, off = random_records(rng, [lengths[i] for i in rng.permutation(len(lengths))], alphabet=b"ACGTNacgt")
+    seqs_dup = np.concatenate([buf, buf[: len(buf) // 3]])   # duplicated reads across distant chunks: order-dependent dedup
+    off_dup = np.concatenate([off, off[-1] + off[1:np.searchsorted(off, len(buf) // 3)]]).astype(np.uint64)
+    seqs_dup = seqs_dup[: int(off_dup[-1])]
+    eh, ec, _, nd = O.sketch_reads(seqs_dup, off_dup, c=11)
+    hb = torch.empty(len(seqs_dup), dtype=torch.uint8, pin_memory=True)
+    hb.numpy()[:] = seqs_dup
+    ho = torch.empty(len(off_dup), dtype=torch.int64, pin_memory=True)
+    ho.numpy()[:] = off_dup.astype(np.int64)
+    monkeypatch.setenv("SYL_INGEST_CHUNK", "16384")
+    for force in (True, False):
+        if force:
+            monkeypatch.setenv("SYL_INGEST_FORCE_STEAL", "1")
+        else:
+            monkeypatch.delenv("SYL_INGEST_FORCE_STEAL", raising=False)
+        s = ctx.sketch_sequences(hb.numpy(), ho.numpy().view(np.uint64), c=11)
+        h, c = s.download()
+        assert np.array_equal(h, eh) and np.array_equal(c, ec) and s.num_dup_removed == nd, force
+    assert nd > 100
