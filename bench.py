@@ -54,7 +54,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sketch", choices=["sketch", "profile"])
+    ap.add_argument("--workload", default="sketch", choices=["sketch", "profile", "genomes"])
+    ap.add_argument("--batch-genomes", type=int, default=125, help="genomes (4 Mbp each) per syl_sketch_genomes call of --workload genomes")
     ap.add_argument("--reads", type=int, default=6_666_667, help="reads per GPU (150 bp each)")
     ap.add_argument("--genomes", type=int, default=None,
                     help="genomes per GPU for the containment metric (default 10000; 12500 for the 16-sample config-4 shape)")
@@ -407,6 +408,88 @@ def bench_sketch(args, ctx, rank, world, local):
     return line, (bases, off)
 
 
+def genomes_config(args):
+    return {"workload": "sketch %d synthetic 4 Mbp genomes per step (one syl_sketch_genomes call; the unit of BASELINE.json "
+                        "configs[4]: 113k x 4 Mbp, GTDB-R220-scale db build)" % args.batch_genomes,
+            "genomes_per_step": args.batch_genomes, "genome_len": GENOME_LEN, "k": K, "c": C, "min_spacing": 30,
+            "l2": "inputs (%.2f GB per step) are larger than L2; no flush needed" % (args.batch_genomes * GENOME_LEN / 1e9)}
+
+
+def bench_genomes(args, ctx, rank, world, local):
+    """Genome (database) sketching, device-resident synthetic genomes generated on the device (config 5: 452 GB of bases
+    cannot cross PCIe in useful time).  step = one batch of genomes -> CSR genome_kmers + tracked, resident."""
+    import numpy as np
+    import torch
+    from sylph_b200 import synth
+    nG = args.batch_genomes
+    bases, off = synth.db_chunk(rank * nG, (rank + 1) * nG, GENOME_LEN, device="cuda")
+    goff = torch.arange(nG + 1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    st = {}
+
+    def step():
+        g = ctx.sketch_genomes(bases, off, goff, k=K, c=C)
+        st["g"] = g
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+        st["g"].free()
+    ctx.enable_timing(True)
+    ctx.seed_kernel_time(reset=True)
+    ctx.kernel_time("genome_post", reset=True)
+    l0 = ctx.launches
+
+    def tstep():
+        step()
+        st["g"].free()
+
+    ms, _ = timed(tstep, args.steps, world)
+    launches = ctx.launches - l0
+    kms = ctx.seed_kernel_time(reset=True)[0] / args.steps
+    pms = ctx.kernel_time("genome_post", reset=True)[0] / args.steps
+    ctx.enable_timing(False)
+    n_bases = float(bases.numel())
+    value = sum_over_ranks(n_bases, world) * args.steps / (ms * 1e-3)
+    step()
+    g = st["g"]
+    d = g.download()
+    peak, peak_src = measured_peak_hbm()
+    n_surv_est = int(d["kmer_off"][-1] + d["tracked_off"][-1])
+    alg = n_bases + 16.0 * n_surv_est   # SURVEY §8(d), positions variant: 1 B/base + 16 B per survivor
+    out = {"metric": "bases/s sketched (genomes)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": genomes_config(args), "gpu_launches": int(launches),
+           "workload_stats": {"genome_kmers": int(d["kmer_off"][-1]), "tracked": int(d["tracked_off"][-1])},
+           "kernels_ms_per_step": {"k_seed": kms, "post_pass": pms},
+           "roofline": {"kernel": "k_seed<31, survivors, W=32>", "bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kms,
+                        "kernel_share_of_step": kms / (ms / args.steps), "algorithmic_bytes_per_launch": alg,
+                        "note": "integer-issue bound like the read-sketch kernel (same hot loop)"}}
+    if rank == 0 and not args.no_cpu:   # parity + CPU arm on a few genomes of the batch
+        from oracle import oracle as O
+        from concurrent.futures import ThreadPoolExecutor
+        cores = os.cpu_count() or 1
+        hb = bases.cpu().numpy()
+        idx = list(range(0, nG, max(1, nG // 16)))
+
+        def one(i):
+            return O.sketch_genome(hb[i * GENOME_LEN:(i + 1) * GENOME_LEN], np.array([0, GENOME_LEN], np.uint64), k=K, c=C)
+
+        t = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=min(len(idx), cores)) as ex:
+            exp = list(ex.map(one, idx))
+        dt = time.perf_counter() - t
+        ok = all(np.array_equal(km, d["kmers"][int(d["kmer_off"][i]):int(d["kmer_off"][i + 1])]) and
+                 np.array_equal(tr, d["tracked"][int(d["tracked_off"][i]):int(d["tracked_off"][i + 1])]) for i, (km, tr, _) in zip(idx, exp))
+        out["parity_checked"] = bool(ok)
+        out["cpu_baseline"] = {"value": len(idx) * GENOME_LEN / dt, "unit": "bases/s", "cores": min(len(idx), cores), "kind": "port",
+                               "sample": "%d of the batch's genomes, one oracle thread per genome (reference decomposition: 1 thread per file)" % len(idx)}
+        if not ok:
+            raise SystemExit("bench: genome sketches differ from the oracle")
+    g.free()
+    return out
+
+
 def rows_equal_oracle(rows, exp, tol=1e-6):
     """Field-by-field comparison of syl_profile rows with the oracle's rows (same order): integers exact,
     floats within `tol` relative — the same bar as tests/test_contain_gpu.py::compare. -> (ok, first difference)"""
@@ -563,6 +646,10 @@ def main():
         line, reads = bench_sketch(args, ctx, rank, world, local)
         if not args.no_pairs:
             line["pairs"] = bench_pairs(args, ctx, rank, world, local, reads)
+            del reads
+            line["genomes"] = bench_genomes(args, ctx, rank, world, local)
+    elif args.workload == "genomes":
+        line = bench_genomes(args, ctx, rank, world, local)
     else:
         from sylph_b200 import synth
         reads = synth.reads(args.reads, READ_LEN, seed=synth.SEED_READS + 0x10 * rank, device="cuda")

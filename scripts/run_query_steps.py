@@ -10,7 +10,7 @@ G = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 ctx = sylph_b200.Context(0, stream=torch.cuda.current_stream().cuda_stream)
-genomes = bench.build_db(ctx, 0, G)
+genomes = synth.sketch_db_range(ctx, 0, G)
 db = ctx.build_db(genomes)
 b, o = synth.reads(n_reads, device="cuda")
 smp = ctx.sketch_sequences(b, o)
