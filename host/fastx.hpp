@@ -91,10 +91,11 @@ inline bool read_fastx(const std::string &path, FlatRecords &out, bool want_ids,
             if (want_ids) out.ids.push_back(line.substr(1));
             first = false;
             std::string seq, plus, qual;
-            if (!lr.next(seq)) return false;
+            // a record without its sequence, '+' or quality line is an invalid file (needletail reports an
+            // error for the record; sylph then drops the file, src/sketch.rs:909-915)
+            if (!lr.next(seq) || !lr.next(plus) || plus.empty() || plus[0] != '+' || !lr.next(qual)) return false;
             out.bases.insert(out.bases.end(), seq.begin(), seq.end());
             out.offsets.push_back(out.bases.size());
-            if (!lr.next(plus) || !lr.next(qual)) return true;  // truncated tail: keep what parsed
             do { if (!lr.next(line)) return true; } while (line.empty());
         }
     }

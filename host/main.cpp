@@ -1,5 +1,7 @@
 // sylph-b200 — host driver over libsylph_b200.so mirroring sylph's `sketch`, `query`, `profile`
-// (src/main.rs:25-30) for the in-scope paths: single-end reads and genomes, k in {21,31}.
+// (src/main.rs:25-30) for the in-scope paths: single-end reads, read pairs with the exact dedup set
+// (-1/-2 --fpr 0) and genomes, k in {21,31}.  Files are inflated and parsed by up to -t threads at a time
+// (the reference parallelises per file with rayon, src/sketch.rs:313,371,428) while the GPU works.
 // File classification, defaults and TSV output follow the reference (src/cmdline.rs,
 // src/sketch.rs:95-127,276-479, src/contain.rs:18-94,115-351,461-480).  All compute goes through
 // the C ABI; there is no CPU path.
@@ -8,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <filesystem>
+#include <future>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -45,7 +49,9 @@ static std::string basename_of(const std::string &p) {
 
 struct Args {
     std::string cmd;
-    std::vector<std::string> files, reads, genomes;
+    std::vector<std::string> files, reads, genomes, first_pairs, second_pairs;
+    int threads = 3;       // src/cmdline.rs:61,100
+    double fpr = 0.0001;   // src/constants.rs:16 (paired-end dedup; only 0 = the exact set is supported)
     uint64_t k = 31, c = 200, min_spacing = 30;
     bool individual = false, no_dedup = false, no_pseudotax = false, no_ci = false, no_adj = false, mean_cov = false;
     std::string db_out = "database", sample_dir = "./", out_file, list_file;
@@ -62,7 +68,11 @@ static Args parse(int argc, char **argv) {
         std::string s = argv[i];
         if (s == "-k") a.k = std::stoull(need(i));
         else if (s == "-c") a.c = std::stoull(need(i));
-        else if (s == "-t" || s == "-s" || s == "--sample-threads") need(i);  // threading is the GPU's business
+        else if (s == "-t") a.threads = std::max(1, std::stoi(need(i)));          // files parsed concurrently
+        else if (s == "-s" || s == "--sample-threads") need(i);
+        else if (s == "--fpr") a.fpr = std::stod(need(i));
+        else if (s == "-1" || s == "--first-pairs") { while (i + 1 < argc && argv[i + 1][0] != '-') a.first_pairs.push_back(argv[++i]); }
+        else if (s == "-2" || s == "--second-pairs") { while (i + 1 < argc && argv[i + 1][0] != '-') a.second_pairs.push_back(argv[++i]); }
         else if (s == "--min-spacing") a.min_spacing = std::stoull(need(i));
         else if (s == "-i" || s == "--individual-records") a.individual = true;
         else if (s == "--no-dedup") a.no_dedup = true;
@@ -80,8 +90,8 @@ static Args parse(int argc, char **argv) {
         else if (s == "--no-adjust") a.no_adj = true;
         else if (s == "--mean-coverage") a.mean_cov = true;
         else if (s == "--device") a.device = std::stoi(need(i));
-        else if (s == "-u" || s == "--estimate-unknown" || s == "-1" || s == "-2" || s == "--first-pairs" || s == "--second-pairs")
-            die(s + " is outside the scope of sylph-b200 (paired-end / -u), see DESIGN.md");
+        else if (s == "-u" || s == "--estimate-unknown")
+            die(s + " is outside the scope of sylph-b200 (its read-identity estimate depends on hash-map iteration order), see DESIGN.md");
         else if (!s.empty() && s[0] == '-') die("unknown option " + s);
         else a.files.push_back(s);
     }
@@ -92,50 +102,102 @@ static Args parse(int argc, char **argv) {
         while (lr.next(line)) if (!line.empty()) a.files.push_back(line);
     }
     if (!(a.k == 21 || a.k == 31)) die("Only k = 21, 31 are currently supported");  // src/cmdline.rs:57
+    if (a.fpr < 0. || a.fpr >= 1.) die("Invalid value for --fpr. Exiting.");             // src/sketch.rs:158-161
+    if (a.first_pairs.size() != a.second_pairs.size()) die("Different number of paired sequences. Exiting.");  // :163-166
+    if (!a.first_pairs.empty() && a.fpr != 0.)
+        die("paired-end reads need --fpr 0 (the exact dedup set); the default approximate cuckoo filter is not bit-reproducible and out of scope");
     return a;
 }
 
 // ---- sketching -----------------------------------------------------------------------------------
 
-static bool sketch_reads_file(syl_ctx *ctx, const Args &a, const std::string &file, SequencesSketch &out) {
-    FlatRecords recs;
-    if (!read_fastx(file, recs, false)) { warn(file + " is not a valid fasta/fastq file; skipping."); return false; }
-    syl_sample *s = nullptr;
-    check(syl_sketch_reads(ctx, SYL_MEM_HOST, recs.bases.data(), recs.bases.size(), recs.offsets.data(), recs.n(), (int)a.k,
-                           a.c, a.no_dedup ? 1 : 0, SYL_SEM_AVX2, &s), "syl_sketch_reads");
+// Inflate + parse `files` with up to `threads` of them in flight, handing them to `use` in order: the next files are
+// being read while the GPU sketches the current one.
+struct Parsed { bool ok = false; FlatRecords recs; std::string first_id; };
+template <typename F>
+static void parse_ahead(const std::vector<std::string> &files, int threads, bool want_ids, F use) {
+    std::vector<std::future<std::unique_ptr<Parsed>>> inflight;
+    size_t next = 0;
+    auto launch = [&]() {
+        const std::string f = files[next++];
+        inflight.push_back(std::async(std::launch::async, [f, want_ids]() {
+            std::unique_ptr<Parsed> p(new Parsed());
+            p->ok = read_fastx(f, p->recs, want_ids, &p->first_id);
+            return p;
+        }));
+    };
+    for (size_t i = 0; i < files.size(); i++) {
+        while (next < files.size() && inflight.size() - i < (size_t)threads) launch();
+        std::unique_ptr<Parsed> p = inflight[i].get();
+        use(files[i], *p);
+    }
+}
+
+static void store_sample(syl_ctx *ctx, syl_sample *s, const Args &a, const std::string &file, bool paired, SequencesSketch &out) {
     out.hashes.resize(syl_sample_size(s));
     out.counts.resize(out.hashes.size());
     check(syl_sample_download(ctx, s, out.hashes.data(), out.counts.data()), "syl_sample_download");
-    out.c = a.c; out.k = a.k; out.file_name = file; out.paired = false;
+    out.c = a.c; out.k = a.k; out.file_name = file; out.paired = paired;
     out.mean_read_length = syl_sample_mean_read_length(s);
     syl_sample_free(s);
+}
+
+// src/sketch.rs:771-895 with --fpr 0
+static bool sketch_pair_files(syl_ctx *ctx, const Args &a, const std::string &f1, const std::string &f2, SequencesSketch &out) {
+    auto fut = std::async(std::launch::async, [&]() { std::unique_ptr<Parsed> p(new Parsed()); p->ok = read_fastx(f2, p->recs, false); return p; });
+    FlatRecords r1;
+    const bool ok1 = read_fastx(f1, r1, false);
+    std::unique_ptr<Parsed> p2 = fut.get();
+    if (!ok1 || !p2->ok) die("Paired end reading failed for '" + f1 + "' and '" + f2 + "'. Make sure the files are present or the sequences are valid.");
+    const uint64_t n_pairs = std::min(r1.n(), p2->recs.n());
+    syl_sample *s = nullptr;
+    check(syl_sketch_read_pairs(ctx, SYL_MEM_HOST, r1.bases.data(), r1.offsets[n_pairs], r1.offsets.data(), p2->recs.bases.data(),
+                                p2->recs.offsets[n_pairs], p2->recs.offsets.data(), n_pairs, (int)a.k, a.c, a.no_dedup ? 1 : 0,
+                                SYL_SEM_AVX2, &s), "syl_sketch_read_pairs");
+    store_sample(ctx, s, a, f1, true, out);
+    return true;
+}
+
+static bool sketch_reads_parsed(syl_ctx *ctx, const Args &a, const std::string &file, const Parsed &p, SequencesSketch &out) {
+    if (!p.ok) { warn(file + " is not a valid fasta/fastq file; skipping."); return false; }
+    syl_sample *s = nullptr;
+    check(syl_sketch_reads(ctx, SYL_MEM_HOST, p.recs.bases.data(), p.recs.bases.size(), p.recs.offsets.data(), p.recs.n(), (int)a.k,
+                           a.c, a.no_dedup ? 1 : 0, SYL_SEM_AVX2, &s), "syl_sketch_reads");
+    store_sample(ctx, s, a, file, false, out);
     return true;
 }
 
 // sketches genome files in batches of <= ~1 Gbp through ONE syl_sketch_genomes call per batch
 static void sketch_genome_files(syl_ctx *ctx, const Args &a, const std::vector<std::string> &files, bool pseudotax,
                                 std::vector<GenomeSketch> &out) {
+    // parse ahead (-t files in flight); batches of <= ~1 Gbp go through one syl_sketch_genomes call
+    std::vector<std::unique_ptr<Parsed>> parsed(files.size());
+    {
+        size_t idx = 0;
+        parse_ahead(files, a.threads, a.individual, [&](const std::string &, Parsed &p) { parsed[idx++].reset(new Parsed(std::move(p))); });
+    }
     size_t fi = 0;
     while (fi < files.size()) {
         FlatRecords recs;
         std::vector<uint64_t> genome_off{0};
         std::vector<std::string> names, first_ids;
         while (fi < files.size() && recs.bases.size() < (1ull << 30)) {
-            const std::string &f = files[fi++];
-            std::string first_id;
-            const size_t before = recs.n();
-            FlatRecords tmp;
-            if (!read_fastx(f, a.individual ? recs : tmp, a.individual, &first_id)) { warn(f + " is not a valid fasta/fastq file; skipping."); continue; }
+            const std::string &f = files[fi];
+            Parsed &p = *parsed[fi++];
+            // a file that fails half way contributes nothing (records are merged only after a complete parse)
+            if (!p.ok) { warn(f + " is not a valid fasta/fastq file; skipping."); continue; }
+            const FlatRecords &tmp = p.recs;
+            const uint64_t base = recs.bases.size();
+            recs.bases.insert(recs.bases.end(), tmp.bases.begin(), tmp.bases.end());
+            for (size_t i = 1; i < tmp.offsets.size(); i++) recs.offsets.push_back(base + tmp.offsets[i]);
             if (!a.individual) {
-                const uint64_t base = recs.bases.size();
-                recs.bases.insert(recs.bases.end(), tmp.bases.begin(), tmp.bases.end());
-                for (size_t i = 1; i < tmp.offsets.size(); i++) recs.offsets.push_back(base + tmp.offsets[i]);
                 genome_off.push_back(recs.n());
                 names.push_back(f);
-                first_ids.push_back(first_id);
+                first_ids.push_back(p.first_id);
             } else {
-                for (size_t i = before; i < recs.n(); i++) { names.push_back(f); first_ids.push_back(recs.ids[i]); }
+                for (size_t i = 0; i < tmp.n(); i++) { names.push_back(f); first_ids.push_back(tmp.ids[i]); }
             }
+            parsed[fi - 1].reset();
         }
         const uint64_t G = a.individual ? recs.n() : genome_off.size() - 1;
         if (G == 0) continue;
@@ -167,15 +229,23 @@ static int cmd_sketch(syl_ctx *ctx, const Args &a) {
         else if (is_fastq(f)) reads.push_back(f);
         else warn(f + " does not have a fasta/fastq/gzip type extension.");
     }
-    for (const std::string &f : reads) {
+    const std::string dir = a.sample_dir.empty() || a.sample_dir.back() == '/' ? a.sample_dir : a.sample_dir + "/";
+    for (size_t i = 0; i < a.first_pairs.size(); i++) {  // src/sketch.rs:313-365
         SequencesSketch s;
-        if (!sketch_reads_file(ctx, a, f, s)) continue;
-        const std::string dir = a.sample_dir.empty() || a.sample_dir.back() == '/' ? a.sample_dir : a.sample_dir + "/";
+        if (!sketch_pair_files(ctx, a, a.first_pairs[i], a.second_pairs[i], s)) continue;
+        if (!dir.empty()) std::filesystem::create_directories(dir);
+        const std::string path = dir + basename_of(a.first_pairs[i]) + ".paired.sylsp";
+        write_sylsp(path, s);
+        info("Sketching " + path + " complete.");
+    }
+    parse_ahead(reads, a.threads, false, [&](const std::string &f, Parsed &p) {
+        SequencesSketch s;
+        if (!sketch_reads_parsed(ctx, a, f, p, s)) return;
         if (!dir.empty()) std::filesystem::create_directories(dir);
         const std::string path = dir + basename_of(f) + ".sylsp";
         write_sylsp(path, s);
         info("Sketching " + path + " complete.");
-    }
+    });
     if (!genomes.empty()) {
         std::vector<GenomeSketch> gs;
         sketch_genome_files(ctx, a, genomes, !a.no_pseudotax, gs);
@@ -253,16 +323,18 @@ static int cmd_contain(syl_ctx *ctx, const Args &a, bool pseudotax) {
     std::vector<std::string> names;
     Args ra = a;
     ra.k = gs[0].k;
-    for (const std::string &f : read_files) {
-        if (a.c > gs[0].c) { warn(f + " error: value of -c for contain is greater than the smallest value of -c for a genome sketch. Continuing without sketching."); continue; }
-        FlatRecords recs;
-        if (!read_fastx(f, recs, false)) { warn(f + " is not a valid fasta/fastq file; skipping."); continue; }
+    if (!read_files.empty() && a.c > gs[0].c) {
+        for (const std::string &f : read_files) warn(f + " error: value of -c for contain is greater than the smallest value of -c for a genome sketch. Continuing without sketching.");
+        read_files.clear();
+    }
+    parse_ahead(read_files, a.threads, false, [&](const std::string &f, Parsed &p) {
+        if (!p.ok) { warn(f + " is not a valid fasta/fastq file; skipping."); return; }
         syl_sample *s = nullptr;
-        check(syl_sketch_reads(ctx, SYL_MEM_HOST, recs.bases.data(), recs.bases.size(), recs.offsets.data(), recs.n(), (int)ra.k, a.c, 0,
+        check(syl_sketch_reads(ctx, SYL_MEM_HOST, p.recs.bases.data(), p.recs.bases.size(), p.recs.offsets.data(), p.recs.n(), (int)ra.k, a.c, 0,
                                SYL_SEM_AVX2, &s), "syl_sketch_reads");
         samples.push_back(s);
         names.push_back(f);
-    }
+    });
     for (const std::string &f : sample_files) {
         SequencesSketch sk;
         try { sk = read_sylsp(f); } catch (const std::exception &e) { die(e.what()); }
@@ -284,25 +356,31 @@ static int cmd_contain(syl_ctx *ctx, const Args &a, bool pseudotax) {
         p.no_ci = a.no_ci; p.no_adj = a.no_adj; p.mean_coverage = a.mean_cov;
         p.min_number_kmers = a.min_number_kmers; p.min_count_correct = a.min_count_correct;
         p.minimum_ani = a.min_ani; p.redundant_ani = a.redundant_ani;
-        std::vector<syl_ani_row> rows(std::max<size_t>(1024, std::min<size_t>(gs.size() * samples.size(), 1u << 22)));
-        uint64_t n = 0;
-        for (;;) {
-            int rc = (pseudotax ? syl_profile : syl_query)(ctx, db, samples.data(), (uint32_t)samples.size(), &p, rows.data(), rows.size(), &n);
-            if (rc == SYL_ERR_CAPACITY) { rows.resize(n); continue; }
-            check(rc, pseudotax ? "syl_profile" : "syl_query");
-            break;
-        }
-        rows.resize(n);
-        size_t i = 0;
-        for (uint32_t s = 0; s < samples.size(); s++) {
-            size_t j = i;
-            while (j < rows.size() && rows[j].sample == s) j++;
-            if (!pseudotax)  // src/contain.rs:332-334: stable sort by ANI descending
-                std::stable_sort(rows.begin() + i, rows.begin() + j,
-                                 [](const syl_ani_row &x, const syl_ani_row &y) { return x.final_est_ani > y.final_est_ani; });
-            for (size_t r = i; r < j; r++) print_row(o, rows[r], pseudotax, names[s], gs[rows[r].genome]);
-            info("Finished sample " + names[s] + ".");
-            i = j;
+        // sample batches sized so that samples x genomes stays below the library's per-call limits (2^31 pairs,
+        // 8 GB of per-pair histograms = 2^23 pairs); the reference walks the samples in chunks too (src/contain.rs:239-263)
+        const size_t per_call = std::max<size_t>(1, std::min<size_t>(samples.size(), (size_t)((1ull << 22) / std::max<size_t>(gs.size(), 1))));
+        for (size_t s0 = 0; s0 < samples.size(); s0 += per_call) {
+            const size_t ns = std::min(per_call, samples.size() - s0);
+            std::vector<syl_ani_row> rows(std::max<size_t>(1024, std::min<size_t>(gs.size() * ns, 1u << 22)));
+            uint64_t n = 0;
+            for (;;) {
+                int rc = (pseudotax ? syl_profile : syl_query)(ctx, db, samples.data() + s0, (uint32_t)ns, &p, rows.data(), rows.size(), &n);
+                if (rc == SYL_ERR_CAPACITY) { rows.resize(n); continue; }
+                check(rc, pseudotax ? "syl_profile" : "syl_query");
+                break;
+            }
+            rows.resize(n);
+            size_t i = 0;
+            for (uint32_t s = 0; s < ns; s++) {
+                size_t j = i;
+                while (j < rows.size() && rows[j].sample == s) j++;
+                if (!pseudotax)  // src/contain.rs:332-334: stable sort by ANI descending
+                    std::stable_sort(rows.begin() + i, rows.begin() + j,
+                                     [](const syl_ani_row &x, const syl_ani_row &y) { return x.final_est_ani > y.final_est_ani; });
+                for (size_t r = i; r < j; r++) print_row(o, rows[r], pseudotax, names[s0 + s], gs[rows[r].genome]);
+                info("Finished sample " + names[s0 + s] + ".");
+                i = j;
+            }
         }
     }
     if (o != stdout) fclose(o);

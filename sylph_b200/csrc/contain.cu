@@ -619,17 +619,19 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
             const uint64_t lo = (b << 32) | (uint32_t)a;
             if (lo < n && lo < (0ull - n) % n) atomicExch(reject_flag + row, 1u);  // the reference would redraw
         }
-        if (hi >= z32) {  // full_covs[hi] = v with cum[v-1] <= hi < cum[v]
-            if (hi < c1) n1++;            // the common small values stay in registers
-            else if (hi < c2) n2++;
-            else if (hi < c3) n3++;
-            else {
-                uint32_t v = 4;
+        // full_covs[hi] = v with cum[v-1] <= hi < cum[v].  Branch-free for the common values (0: most draws;
+        // 1, 2, 3: counted in registers) — lanes of a warp draw different values, a branch per value would
+        // serialise them (measured: 60 instructions per draw with the branches, 23 of 32 lanes active).
+        const uint32_t g0 = hi >= z32 ? 1u : 0u, g1 = hi >= c1 ? 1u : 0u, g2 = hi >= c2 ? 1u : 0u, g3 = hi >= c3 ? 1u : 0u;
+        n1 += g0 - g1;
+        n2 += g1 - g2;
+        n3 += g2 - g3;
+        if (g3) {  // a value >= 4: rare for a bootstrapped row (median <= 2)
+            uint32_t v = 4;
 #pragma unroll
-                for (int step = 8; step >= 1; step >>= 1)
-                    if (v + step <= 16 && (uint64_t)hi >= cum[v + step - 1]) v += step;
-                atomicAdd(&Hb[v], 1u);
-            }
+            for (int step = 8; step >= 1; step >>= 1)
+                if (v + step <= 16 && (uint64_t)hi >= cum[v + step - 1]) v += step;
+            atomicAdd(&Hb[v], 1u);
         }
     }
 #pragma unroll
@@ -1225,7 +1227,9 @@ static int job_bootstrap(syl_profile_job *j, void *tab) {
     ShardTable *t = reinterpret_cast<ShardTable *>(tab);
     SYL_CUDA(cudaMemsetAsync(j->reject.p, 0, (size_t)j->R * 4, st));
     KernelTimer kt(ctx, SYL_KERNEL_BOOT);
-    k_boot_iter_p<<<ctx->num_sms * 8, BOOT_THREADS, 0, st>>>(j->hist.p, &t->n_boot, j->R, j->P, j->res_ani.p, j->res_lambda.p, j->res_ok.p, j->reject.p);
+    static int boot_ctas = 0;  // resident CTAs per SM (a partially filled second wave would double the tail)
+    if (!boot_ctas && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&boot_ctas, k_boot_iter_p, BOOT_THREADS, 0) != cudaSuccess) boot_ctas = 4;
+    k_boot_iter_p<<<ctx->num_sms * std::max(boot_ctas, 1), BOOT_THREADS, 0, st>>>(j->hist.p, &t->n_boot, j->R, j->P, j->res_ani.p, j->res_lambda.p, j->res_ok.p, j->reject.p);
     k_boot_seq<<<nblk(j->R, 32), 32, 0, st>>>(j->hist.p, (uint32_t)j->R, j->P, j->reject.p, j->res_ani.p, j->res_lambda.p, j->res_ok.p, &t->n_boot);
     k_boot_final<<<(unsigned)j->R, 128, 0, st>>>(j->boot_rows.p, (uint32_t)j->R, j->res_ani.p, j->res_lambda.p, j->res_ok.p, table_rows(tab), &t->n_boot);
     kt.stop();

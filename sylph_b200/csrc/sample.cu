@@ -1162,8 +1162,9 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
     int64_t f = 0, bk = (int64_t)chunks.size() - 1, last_packed = -1;
     int a_slot = 0, a_last = -1;
     uint64_t n_ascii = 0, n_packed = 0;
+    bool steal_turn = true;  // force_steal only: alternate ASCII and packed chunks
     while (f <= bk && rc == SYL_OK) {
-        const bool steal_first = force_steal && steal_ok && n_ascii <= n_packed;
+        const bool steal_first = force_steal && steal_ok && steal_turn;
         if (!steal_first && I.pool->chunk_done((uint32_t)f)) {  // ---- packed chunk from the front
             const size_t ci = (size_t)f;
             const Chunk &c = chunks[ci];
@@ -1187,10 +1188,11 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
             last_packed = f;
             f++;
             n_packed++;
+            steal_turn = true;
             continue;
         }
         const bool ascii_busy = !force_steal && a_last >= 0 && cudaEventQuery(I.ev_a_copied[a_last]) == cudaErrorNotReady;
-        if (steal_ok && !ascii_busy && bk > f && I.pool->try_skip_chunk((uint32_t)bk)) {  // ---- ASCII chunk from the back
+        if (steal_ok && !ascii_busy && (!force_steal || steal_turn) && bk > f && I.pool->try_skip_chunk((uint32_t)bk)) {  // ---- ASCII chunk from the back
             const Chunk &c = chunks[(size_t)bk];
             const int slot = a_slot;
             a_slot ^= 1;
@@ -1207,9 +1209,10 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
             a_last = slot;
             n_ascii++;
             bk--;
+            steal_turn = false;
             continue;
         }
-        if (steal_first) { n_packed = n_ascii + 1; continue; }  // nothing left to take from the back: go on with packed chunks
+        if (steal_first) { steal_turn = false; continue; }  // nothing to take from the back right now: go on with packed chunks
         I.pool->wait_chunk((uint32_t)f);  // the packers are on it (or the only chunks left are theirs)
     }
     I.pool->open_gate((int64_t)1 << 60);  // all remaining items (skipped chunks included) drain

@@ -95,3 +95,16 @@ def test_fastx_parser_matches_needletail_semantics(tmp_path):
             assert int(h, 16) == _fnv(recs), f
         assert first == recs[0][0].decode(), f
     assert read_fastx(str(fa))[0] == (b"c1 first contig", b"ACGTNNacgtTTTT") and read_fastx(str(fa))[1] == (b"c2", b"")
+
+
+def test_pack_pool_scheduling_never_deadlocks(tmp_path):
+    """The worker pool behind the host-memory read path (gate on the pinned staging ring, chunks taken over by the
+    caller from the back, forced alternation): a scheduler stress test without a GPU — a host-side deadlock would
+    otherwise only show up as a hung GPU test."""
+    import subprocess
+    src = os.path.join(REPO, "tests", "cpp", "pack_pool_stress.cpp")
+    exe = str(tmp_path / "pack_pool_stress")
+    csrc = os.path.join(REPO, "sylph_b200", "csrc")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", csrc, "-o", exe, src, os.path.join(csrc, "host_pack.cpp")])
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout
