@@ -77,15 +77,43 @@ __attribute__((target("avx2"))) void pack2_avx2(const uint8_t *bases, uint64_t n
     if (n % 32) pack2_scalar(bases + 32 * full, n % 32, words + 2 * full);
 }
 
+// 64 bases -> 4 words with AVX-512 VBMI: the low 7 bits of a byte index a 128-entry BYTE_TO_SEQ table held in two
+// registers (VPERMI2B); bytes >= 0x80 are masked to 0.
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack2_avx512(const uint8_t *bases, uint64_t n, uint32_t *words) {
+    alignas(64) uint8_t tlo[64], thi[64];
+    for (int i = 0; i < 64; i++) { tlo[i] = g_lut.t[i]; thi[i] = g_lut.t[64 + i]; }
+    const __m512i tab_lo = _mm512_load_si512(tlo), tab_hi = _mm512_load_si512(thi);
+    const __m512i w41 = _mm512_set1_epi16(0x0104);       // bytes (4, 1): c0*4 + c1
+    const __m512i w161 = _mm512_set1_epi32(0x00010010);  // words (16, 1): p0*16 + p1
+    const __m128i rev = _mm_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12);
+    const uint64_t full = n / 64;
+    for (uint64_t i = 0; i < full; i++) {
+        const __m512i v = _mm512_loadu_si512(bases + 64 * i);
+        const __mmask64 hi = _mm512_movepi8_mask(v);                                // bytes >= 0x80 -> code 0
+        const __m512i code = _mm512_maskz_permutex2var_epi8(~hi, tab_lo, v, tab_hi);  // BYTE_TO_SEQ[b & 0x7F]
+        const __m512i p2 = _mm512_maddubs_epi16(code, w41);
+        const __m512i p4 = _mm512_madd_epi16(p2, w161);                             // 16 dwords: 4 bases each, in the low byte
+        const __m128i b = _mm512_cvtepi32_epi8(p4);                                 // B0 .. B15
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(words + 4 * i), _mm_shuffle_epi8(b, rev));  // word = B0<<24 | B1<<16 | B2<<8 | B3
+    }
+    if (n % 64) pack2_scalar(bases + 64 * full, n % 64, words + 4 * full);
+}
+
 bool have_avx2() {
     static const bool v = __builtin_cpu_supports("avx2") && getenv("SYL_PACK_SCALAR") == nullptr;
+    return v;
+}
+bool have_avx512() {
+    static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
+                          getenv("SYL_PACK_SCALAR") == nullptr && getenv("SYL_PACK_AVX2") == nullptr;
     return v;
 }
 
 }  // namespace
 
 void pack2_range(const uint8_t *bases, uint64_t n_bases, uint32_t *words) {
-    if (have_avx2()) pack2_avx2(bases, n_bases, words);
+    if (have_avx512()) pack2_avx512(bases, n_bases, words);
+    else if (have_avx2()) pack2_avx2(bases, n_bases, words);
     else pack2_scalar(bases, n_bases, words);
 }
 

@@ -191,9 +191,30 @@ def test_histogram_formulation_of_get_stats(lam):
         assert h16[1:] == [kept.count(v) for v in range(1, 17)]
 
 
+@pytest.mark.parametrize("isa", ["best", "avx2", "scalar"])
+def test_host_packer_every_instruction_set(isa):
+    """the three code paths of the host packer (AVX-512 VBMI table look-up, AVX2 nibble tables, scalar table) are
+    selected once per process: run the exactness test below in a child process for each"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.pop("SYL_PACK_AVX2", None)
+    env.pop("SYL_PACK_SCALAR", None)
+    if isa == "avx2":
+        env["SYL_PACK_AVX2"] = "1"
+    if isa == "scalar":
+        env["SYL_PACK_SCALAR"] = "1"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); from tests.test_kernel_math_cpu import "
+                        "test_host_packer_is_exact_byte_to_seq as t; t(); print('ok')" % root],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:]
+
+
 def test_host_packer_is_exact_byte_to_seq():
-    """syl_pack2 (AVX2 nibble-table classification + scalar tail) against BYTE_TO_SEQ (src/types.rs:50-59) written
-    out directly: every byte value, every length mod 32, multi-threaded == single-threaded.  Runs without a GPU."""
+    """syl_pack2 (SIMD classification + scalar tail) against BYTE_TO_SEQ (src/types.rs:50-59) written
+    out directly: every byte value, every length mod 64, multi-threaded == single-threaded.  Runs without a GPU."""
     import numpy as np
     from sylph_b200.api import pack2
     lut = np.zeros(256, np.uint64)
@@ -210,7 +231,7 @@ def test_host_packer_is_exact_byte_to_seq():
     rng = np.random.default_rng(1)
     every = np.arange(256, dtype=np.uint8).repeat(3)
     assert np.array_equal(pack2(every, 1), ref(every))
-    for n in list(range(0, 70)) + [1000, 4097, (1 << 21) + 5]:
+    for n in list(range(0, 140)) + [1000, 4097, (1 << 21) + 5]:
         b = rng.integers(0, 256, n, dtype=np.uint8)
         assert np.array_equal(pack2(b, 1), ref(b)), n
         assert np.array_equal(pack2(b, 3), ref(b)), n

@@ -155,6 +155,21 @@ def test_poisson_cutoffs_and_device_table():
     assert dev == [0] + exp
 
 
+def test_poisson_cutoff_table_against_an_independent_regularized_gamma():
+    """statrs' Poisson::cdf(x) is the regularized upper incomplete gamma Q(x+1, lambda) (src/contain.rs:664-675 walks it
+    up to CUTOFF_PVALUE = 0.9999999999).  The table the kernels use was derived from a direct series; scipy's
+    gammaincc (Cephes igamc: a different algorithm) must put every entry on the same side of the threshold, with a
+    margin well above double rounding (tightest: m = 7 at 1.7e-13)."""
+    from scipy.special import gammaincc
+    exp = [11, 15, 18, 21, 24, 26, 28, 31, 33, 35, 37, 39, 41, 43, 45, 46, 48, 50, 52, 53, 55, 57, 58, 60, 62, 63, 65, 67, 68]
+    thr = 0.9999999999
+    for m, cut in zip(range(1, 30), exp):
+        below, above = float(gammaincc(cut + 1, m)), float(gammaincc(cut + 2, m))   # cdf(cut), cdf(cut + 1)
+        assert below < thr - 1e-13 and above >= thr + 1e-13, (m, cut, below - thr, above - thr)
+        for x in range(m, cut):                                                     # monotone: nothing earlier crosses
+            assert float(gammaincc(x + 1, m)) < thr
+
+
 def test_fastrand_stream_c_vs_pyref():
     rng = R.WyRand(7)
     seq = [rng.usize(17400) for _ in range(50)]
