@@ -145,7 +145,7 @@ int syl_sketch_reads_packed2(syl_ctx *ctx, int mem, const uint32_t *packed, uint
 /* Read pairs — replaces sketch_pair_sequences (src/sketch.rs:771-895) for `--fpr 0`, i.e. the EXACT
  * (k-mer, pair key) set with no count threshold (:829-838, :855-865): pair_kmer (:658-688) keys from the first 32
  * bases of both mates, mate 1's k-mers first, mate 2's k-mers that also occur in mate 1 skipped (:849-853).
- * Mate i of pair p = record p of buffer i; n_pairs = records zipped from the two files.  The reference's default
+ * Mate i of pair p = record p of buffer i; n_pairs = records zipped from the two files; n_bases_i = rec_off_i[n_pairs].  The reference's default
  * (approximate scalable cuckoo filter, fpr 1e-4) is not bit-reproducible and stays out of scope. */
 int syl_sketch_read_pairs(syl_ctx *ctx, int mem, const uint8_t *bases1, uint64_t n_bases1, const uint64_t *rec_off1,
                           const uint8_t *bases2, uint64_t n_bases2, const uint64_t *rec_off2, uint64_t n_pairs,

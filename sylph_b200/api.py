@@ -179,6 +179,7 @@ class Context:
         if len({m1, mo1, m2, mo2}) != 1:
             raise ValueError("all four buffers must live in the same memory space")
         n_pairs = min(no1, no2) - 1
+        n1, n2 = int(k2[n_pairs]), int(k4[n_pairs])   # bases of the zipped records only (a longer file's tail is ignored)
         h = C.c_void_p()
         _lib.check(L.syl_sketch_read_pairs(self._h, m1, p1, n1, po1, p2, n2, po2, n_pairs, k, c, int(no_dedup), sem, C.byref(h)))
         return Sample(self, h)

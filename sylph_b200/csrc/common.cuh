@@ -175,6 +175,7 @@ struct SeedJob {
     uint32_t *d_tile_cnt = nullptr, *d_slot_overflow = nullptr;
 };
 uint64_t seed_cta_tiles(uint64_t n_bases);  // number of tiles of the CTA kernel
+uint64_t seed_cta_tile_bases();             // window starts per tile of the CTA kernel
 bool seed_cta_kernel_selected();            // false when SYL_SEED_IMPL=warp forces the warp kernel
 int seed_enqueue(syl_ctx *ctx, const SeedJob &job);
 void ingest_destroy(syl_ctx *ctx);

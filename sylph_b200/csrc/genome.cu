@@ -303,34 +303,61 @@ constexpr uint32_t GEN_PART_N = 6000;     // expected hashes per (genome, part) 
 constexpr uint32_t GEN_SLOTS = 16384;     // table slots per CTA (load factor ~0.37)
 constexpr int GEN_DUP_THREADS = 512;
 
-// tile t: slot -> sorted by (contig, pos) -> compact arrays at toff[t]
+// tile t: slot -> ordered by (contig, pos) -> compact arrays at toff[t].  A survivor's window start is unique inside
+// its tile, so the order is the rank of its bit in a 32 768-bit map of the tile: set the bits, scan the word
+// popcounts, look the rank up — three barriers instead of the 36 compare-exchange rounds of a bitonic network
+// (which took 0.2 ms per 0.5 Gbp).
 __global__ void __launch_bounds__(256)
 k_tile_sort_compact(const syl_survivor *__restrict__ slots, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ toff,
-                    uint64_t *__restrict__ poskey, uint64_t *__restrict__ hash) {
-    __shared__ uint64_t sk[GEN_SLOT], sh[GEN_SLOT];
+                    const uint64_t *__restrict__ contig_off, uint32_t tile_bases, int k, uint64_t *__restrict__ poskey,
+                    uint64_t *__restrict__ hash) {
+    __shared__ uint32_t bits[1024];   // SEED_TILE = 32768 window starts
+    __shared__ uint32_t pre[1024];    // survivors before word w
+    __shared__ uint32_t wsum[8];
     const uint32_t t = blockIdx.x, n = tile_cnt[t];
     if (n == 0) return;
-    uint32_t P = 32;
-    while (P < n) P <<= 1;
-    const syl_survivor *src = slots + (uint64_t)t * GEN_SLOT;
-    for (uint32_t i = threadIdx.x; i < P; i += 256) {
-        if (i < n) { const syl_survivor v = src[i]; sk[i] = ((uint64_t)v.rec << 32) | v.pos; sh[i] = v.hash; }
-        else { sk[i] = 0xFFFFFFFFFFFFFFFFull; sh[i] = 0; }
-    }
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < 1024; i += 256) bits[i] = 0u;
     __syncthreads();
-    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
-        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-            for (uint32_t q = threadIdx.x; q < (P >> 1); q += 256) {
-                const uint32_t i = ((q & ~(j - 1)) << 1) | (q & (j - 1)), l = i | j;
-                const bool up = (i & kk) == 0;
-                const uint64_t a = sk[i], b = sk[l];
-                if ((a > b) == up) { sk[i] = b; sk[l] = a; const uint64_t x = sh[i]; sh[i] = sh[l]; sh[l] = x; }
-            }
-            __syncthreads();
+    const syl_survivor *src = slots + (uint64_t)t * GEN_SLOT;
+    const uint64_t T0 = (uint64_t)t * tile_bases;
+    syl_survivor mine[2];
+    uint32_t pw[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const uint32_t i = tid + 256 * e;
+        if (i < n) {
+            mine[e] = src[i];
+            pw[e] = (uint32_t)(contig_off[mine[e].rec] + mine[e].pos - (uint64_t)(k - 1) - T0);  // window start, tile-relative
+            atomicOr(&bits[pw[e] >> 5], 1u << (pw[e] & 31u));
         }
     }
-    const uint32_t base = toff[t];
-    for (uint32_t i = threadIdx.x; i < n; i += 256) { poskey[base + i] = sk[i]; hash[base + i] = sh[i]; }
+    __syncthreads();
+    {   // exclusive scan of the 1024 word popcounts: 4 words per thread
+        uint32_t c[4], tot = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) { c[e] = __popc(bits[4 * tid + e]); tot += c[e]; }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        uint32_t base = inc - tot;
+        for (int w = 0; w < wid; w++) base += wsum[w];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { pre[4 * tid + e] = base; base += c[e]; }
+    }
+    __syncthreads();
+    const uint32_t out0 = toff[t];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const uint32_t i = tid + 256 * e;
+        if (i < n) {
+            const uint32_t w = pw[e] >> 5, r = pre[w] + __popc(bits[w] & ((1u << (pw[e] & 31u)) - 1u));
+            poskey[out0 + r] = ((uint64_t)mine[e].rec << 32) | mine[e].pos;
+            hash[out0 + r] = mine[e].hash;
+        }
+    }
 }
 
 // gs[g] = index of genome g's first survivor (g = 0 .. n_genomes; gs[n_genomes] = N); N from device memory
@@ -367,27 +394,40 @@ k_genome_dups(const uint64_t *__restrict__ hash, const uint32_t *__restrict__ gs
     const uint32_t s0 = gs[g], s1 = gs[g + 1];
     for (uint32_t i = threadIdx.x; i < GEN_SLOTS; i += GEN_DUP_THREADS) { tab[i] = 0xFFFFFFFFFFFFFFFFull; dup[i] = 0; }
     __syncthreads();
-    for (uint32_t i = s0 + threadIdx.x; i < s1; i += GEN_DUP_THREADS) {
-        const unsigned long long h = hash[i];
-        if (gen_part_of(h, P) != p) continue;
-        uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
-        uint32_t probes = 0;
-        for (;; probes++) {
-            if (probes >= GEN_SLOTS) { atomicExch(overflow, 1u); break; }  // table full (pathological skew): generic path
-            const unsigned long long prev = atomicCAS(&tab[sl], 0xFFFFFFFFFFFFFFFFull, h);
-            if (prev == 0xFFFFFFFFFFFFFFFFull) break;
-            if (prev == h) { dup[sl] = 1; break; }
-            sl = (sl + 1) & (GEN_SLOTS - 1);
+    // four independent loads per trip: the loop is bound by the latency of the hash loads (L2), not by the table
+    for (uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 4 * GEN_DUP_THREADS) {
+        unsigned long long hq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * GEN_DUP_THREADS; hq[q] = i < s1 ? hash[i] : 0xFFFFFFFFFFFFFFFFull; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned long long h = hq[q];
+            if (h == 0xFFFFFFFFFFFFFFFFull || gen_part_of(h, P) != p) continue;
+            uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
+            uint32_t probes = 0;
+            for (;; probes++) {
+                if (probes >= GEN_SLOTS) { atomicExch(overflow, 1u); break; }  // table full (pathological skew): generic path
+                const unsigned long long prev = atomicCAS(&tab[sl], 0xFFFFFFFFFFFFFFFFull, h);
+                if (prev == 0xFFFFFFFFFFFFFFFFull) break;
+                if (prev == h) { dup[sl] = 1; break; }
+                sl = (sl + 1) & (GEN_SLOTS - 1);
+            }
         }
     }
     __syncthreads();
-    for (uint32_t i = s0 + threadIdx.x; i < s1; i += GEN_DUP_THREADS) {
-        const unsigned long long h = hash[i];
-        if (gen_part_of(h, P) != p) continue;
-        uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
-        uint32_t probes = 0;
-        while (tab[sl] != h && probes < GEN_SLOTS) { sl = (sl + 1) & (GEN_SLOTS - 1); probes++; }
-        flag[i] = (probes < GEN_SLOTS && dup[sl]) ? 0 : 3;
+    for (uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 4 * GEN_DUP_THREADS) {
+        unsigned long long hq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * GEN_DUP_THREADS; hq[q] = i < s1 ? hash[i] : 0xFFFFFFFFFFFFFFFFull; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned long long h = hq[q];
+            if (h == 0xFFFFFFFFFFFFFFFFull || gen_part_of(h, P) != p) continue;
+            uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
+            uint32_t probes = 0;
+            while (tab[sl] != h && probes < GEN_SLOTS) { sl = (sl + 1) & (GEN_SLOTS - 1); probes++; }
+            flag[i0 + q * GEN_DUP_THREADS] = (probes < GEN_SLOTS && dup[sl]) ? 0 : 3;
+        }
     }
 }
 
@@ -480,7 +520,8 @@ static int sketch_genomes_device_slots(syl_ctx *ctx, const uint8_t *d_bases, uin
     SYL_TRY(scan_u32(ctx, tile_cnt.p, n_tiles, toff.p, t1, t2));   // toff[n_tiles] = N (device)
     const uint32_t *d_n = toff.p + n_tiles;
     SYL_TRY(poskey.alloc(cap, st)); SYL_TRY(hash.alloc(cap, st)); SYL_TRY(flag.alloc(cap, st));
-    k_tile_sort_compact<<<(unsigned)n_tiles, 256, 0, st>>>(slots.p, tile_cnt.p, toff.p, poskey.p, hash.p);
+    k_tile_sort_compact<<<(unsigned)n_tiles, 256, 0, st>>>(slots.p, tile_cnt.p, toff.p, d_contig_off, (uint32_t)seed_cta_tile_bases(), k,
+                                                           poskey.p, hash.p);
     SYL_TRY(gs.alloc(n_genomes + 1, st)); SYL_TRY(parts.alloc(n_genomes, st)); SYL_TRY(pstart.alloc(n_genomes + 1, st));
     k_genome_ranges<<<nblk(n_genomes + 1, 256), 256, 0, st>>>(poskey.p, d_n, d_genome_off, n_genomes, gs.p);
     k_genome_parts<<<nblk(n_genomes, 256), 256, 0, st>>>(gs.p, n_genomes, parts.p);

@@ -97,6 +97,7 @@ static bool use_warp_kernel() {
 }
 
 uint64_t seed_cta_tiles(uint64_t n_bases) { return (n_bases + SEED_TILE - 1) / SEED_TILE; }
+uint64_t seed_cta_tile_bases() { return SEED_TILE; }
 bool seed_cta_kernel_selected() { return !use_warp_kernel(); }
 
 // Enqueue the seeding of one batch on the ctx stream.  No host synchronisation and no counter reset:
