@@ -50,6 +50,8 @@ static std::string basename_of(const std::string &p) {
 struct Args {
     std::string cmd;
     std::vector<std::string> files, reads, genomes, first_pairs, second_pairs;
+    bool estimate_unknown = false;
+    double read_seq_id = -1.;  // -I / --read-seq-id (percent)
     int threads = 3;       // src/cmdline.rs:61,100
     double fpr = 0.0001;   // src/constants.rs:16 (paired-end dedup; only 0 = the exact set is supported)
     uint64_t k = 31, c = 200, min_spacing = 30;
@@ -90,8 +92,8 @@ static Args parse(int argc, char **argv) {
         else if (s == "--no-adjust") a.no_adj = true;
         else if (s == "--mean-coverage") a.mean_cov = true;
         else if (s == "--device") a.device = std::stoi(need(i));
-        else if (s == "-u" || s == "--estimate-unknown")
-            die(s + " is outside the scope of sylph-b200 (its read-identity estimate depends on hash-map iteration order), see DESIGN.md");
+        else if (s == "-u" || s == "--estimate-unknown") a.estimate_unknown = true;
+        else if (s == "-I" || s == "--read-seq-id") a.read_seq_id = std::stod(need(i));
         else if (!s.empty() && s[0] == '-') die("unknown option " + s);
         else a.files.push_back(s);
     }
@@ -104,6 +106,8 @@ static Args parse(int argc, char **argv) {
     if (!(a.k == 21 || a.k == 31)) die("Only k = 21, 31 are currently supported");  // src/cmdline.rs:57
     if (a.fpr < 0. || a.fpr >= 1.) die("Invalid value for --fpr. Exiting.");             // src/sketch.rs:158-161
     if (a.first_pairs.size() != a.second_pairs.size()) die("Different number of paired sequences. Exiting.");  // :163-166
+    if (a.estimate_unknown && !(a.read_seq_id > 0.))
+        die("-u needs -I/--read-seq-id here: sylph's automatic read-identity estimate depends on hash-map iteration order (DESIGN.md)");
     if (!a.first_pairs.empty() && a.fpr != 0.)
         die("paired-end reads need --fpr 0 (the exact dedup set); the default approximate cuckoo filter is not bit-reproducible and out of scope");
     return a;
@@ -341,6 +345,7 @@ static int cmd_contain(syl_ctx *ctx, const Args &a, bool pseudotax) {
         if (sk.c > gs[0].c) { warn(f + " value of -c is greater than the smallest value of -c for a genome sketch. Exiting."); continue; }
         syl_sample *s = nullptr;
         check(syl_sample_upload(ctx, SYL_MEM_HOST, sk.hashes.data(), sk.counts.data(), sk.hashes.size(), (int)sk.k, sk.c, &s), "syl_sample_upload");
+        syl_sample_set_mean_read_length(s, sk.mean_read_length);
         samples.push_back(s);
         names.push_back(sk.has_sample_name ? sk.sample_name : sk.file_name);
     }
@@ -356,6 +361,7 @@ static int cmd_contain(syl_ctx *ctx, const Args &a, bool pseudotax) {
         p.no_ci = a.no_ci; p.no_adj = a.no_adj; p.mean_coverage = a.mean_cov;
         p.min_number_kmers = a.min_number_kmers; p.min_count_correct = a.min_count_correct;
         p.minimum_ani = a.min_ani; p.redundant_ani = a.redundant_ani;
+        p.estimate_unknown = a.estimate_unknown ? 1 : 0; p.read_seq_id = a.read_seq_id;
         // sample batches sized so that samples x genomes stays below the library's per-call limits (2^31 pairs,
         // 8 GB of per-pair histograms = 2^23 pairs); the reference walks the samples in chunks too (src/contain.rs:239-263)
         const size_t per_call = std::max<size_t>(1, std::min<size_t>(samples.size(), (size_t)((1ull << 22) / std::max<size_t>(gs.size(), 1))));

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SYL_ABI_VERSION 1
+#define SYL_ABI_VERSION 2
 
 enum {
     SYL_OK = 0,
@@ -163,6 +163,8 @@ uint64_t syl_sample_size(const syl_sample *s);
  * equal up to rounding, only feeds `-u` and `inspect`). */
 double syl_sample_mean_read_length(const syl_sample *s);
 uint64_t syl_sample_num_dup_removed(const syl_sample *s);
+/* mean_read_length of an uploaded sketch (a .sylsp carries it; `-u` reads it, src/contain.rs:295) */
+void syl_sample_set_mean_read_length(syl_sample *s, double mean_read_length);
 int syl_sample_download(syl_ctx *ctx, const syl_sample *s, uint64_t *hash, uint32_t *count);
 /* Raw device pointers (valid until syl_sample_free), for zero-copy interop. */
 int syl_sample_device_ptrs(const syl_sample *s, const uint64_t **hash, const uint32_t **count);
@@ -227,11 +229,13 @@ typedef struct {
     int32_t no_ci;            /* --no-ci */
     int32_t no_adj;           /* --no-adjust */
     int32_t mean_coverage;    /* --mean-coverage */
-    int32_t reserved;
+    int32_t estimate_unknown; /* -u: needs read_seq_id > 0 (the automatic identity estimate get_kmer_identity,
+                                 src/contain.rs:901-951, walks a hash map in iteration order: SYL_ERR_UNSUPPORTED) */
     double min_number_kmers;  /* -M, default 50  (src/cmdline.rs:96) */
     double min_count_correct; /* default 3       (src/cmdline.rs:94) */
     double minimum_ani;       /* -m in percent; < 0 = unset => 90 (query) / 95 (profile) */
     double redundant_ani;     /* -R, default 99  (src/cmdline.rs:119) */
+    double read_seq_id;       /* --read-seq-id in percent (src/contain.rs:274-277); <= 0 = unset */
 } syl_contain_params;
 
 void syl_contain_params_default(syl_contain_params *p, int k, int pseudotax);

@@ -118,6 +118,9 @@ def lib():
     L.syo_contain_sample.restype = C.c_int64
     L.syo_contain_sample.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.syo_contain_sample_unknown.restype = C.c_int64
+    L.syo_contain_sample_unknown.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     L.syo_poisson_cutoff.restype = C.c_uint32
     L.syo_poisson_cutoff.argtypes = [C.c_uint32]
     L.syo_fastrand_usize.restype = C.c_uint64
@@ -258,7 +261,12 @@ def get_stats(params, genome_kmers, sample, genome_index=0):
     return r if ok else None
 
 
-def contain_sample(params, kmers, kmer_off, tracked, tracked_off, gn_size, sample, nthreads=1):
+class Unknown(C.Structure):
+    """-u with --read-seq-id: (read identity %, the sample's mean read length, the sample's c)"""
+    _fields_ = [("read_seq_id", C.c_double), ("mean_read_length", C.c_double), ("sample_c", C.c_uint64)]
+
+
+def contain_sample(params, kmers, kmer_off, tracked, tracked_off, gn_size, sample, nthreads=1, unknown=None):
     kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
     kmer_off = np.ascontiguousarray(kmer_off, dtype=np.uint64)
     tr = np.ascontiguousarray(tracked, dtype=np.uint64) if tracked is not None else None
@@ -266,8 +274,12 @@ def contain_sample(params, kmers, kmer_off, tracked, tracked_off, gn_size, sampl
     gs = np.ascontiguousarray(gn_size, dtype=np.uint64)
     n = len(kmer_off) - 1
     out = (AniResult * max(n, 1))()
-    m = lib().syo_contain_sample(C.byref(params), _ptr(kmers), _ptr(kmer_off), _ptr(tr), _ptr(tro), _ptr(gs), n,
-                                 sample._h, nthreads, out, max(n, 1))
+    if unknown is not None:
+        m = lib().syo_contain_sample_unknown(C.byref(params), _ptr(kmers), _ptr(kmer_off), _ptr(tr), _ptr(tro), _ptr(gs), n,
+                                             sample._h, nthreads, out, max(n, 1), C.byref(unknown))
+    else:
+        m = lib().syo_contain_sample(C.byref(params), _ptr(kmers), _ptr(kmer_off), _ptr(tr), _ptr(tro), _ptr(gs), n,
+                                     sample._h, nthreads, out, max(n, 1))
     assert m >= 0
     return [out[i] for i in range(m)]
 

@@ -321,10 +321,11 @@ def get_stats(genome_kmers, sample, k=31, min_number_kmers=50.0, min_count_corre
 
 
 def contain_sample(genomes, sample, k=31, pseudotax=False, min_number_kmers=50.0, min_count_correct=3.0,
-                   minimum_ani=None, redundant_ani=99.0, no_ci=False):
+                   minimum_ani=None, redundant_ani=99.0, no_ci=False, unknown=None):
     """Inner body of contain() for one sample (src/contain.rs:284-334), written from the reference
     source only.  genomes: list of dict(kmers=[..], tracked=[..], gn_size=int); sample: dict hash->count.
     Pass-1 results are taken in genome-index order (the reference's order is thread-timing dependent).
+    unknown = (read_seq_id percent, mean_read_length, sample c): -u with --read-seq-id (:274-279, :377-408).
     -> list of dicts (get_stats fields + genome, rel_abund, seq_abund) in output order."""
     min_ani = minimum_ani / 100.0 if minimum_ani is not None else (0.95 if pseudotax else 0.90)  # :746-748
     kw = dict(k=k, min_number_kmers=min_number_kmers, min_count_correct=min_count_correct, min_ani=min_ani, no_ci=no_ci)
@@ -334,6 +335,17 @@ def contain_sample(genomes, sample, k=31, pseudotax=False, min_number_kmers=50.0
         if r is not None:
             r["genome"] = gi
             res.append(r)
+
+    def true_cov(rows):  # estimate_true_cov :377-389
+        if unknown is None:
+            return
+        seq_id, rl, _ = unknown
+        kid = (seq_id / 100.0) ** k
+        mult = rl / (rl - k + 1.0)
+        for r in rows:
+            r["final_est_cov"] = r["final_est_cov"] / kid * mult
+
+    true_cov(res)
     if pseudotax:
         # winner_table (:410-430): first entry wins ties, a later genome needs a strictly larger ANI
         winner = {}
@@ -354,11 +366,19 @@ def contain_sample(genomes, sample, k=31, pseudotax=False, min_number_kmers=50.0
         old = {r["genome"]: r for r in res}
         thr = (redundant_ani / 100.0) ** k
         res = [r for r in res2 if float(old[r["genome"]]["contain"] - r["contain"]) < thr * r["glen"]]
+        true_cov(res)
+        explained = 1.0
+        if unknown is not None:  # estimate_covered_bases :391-408
+            _, rl, sc = unknown
+            mult = rl / (rl - k + 1.0)
+            covered = sum(genomes[r["genome"]]["gn_size"] * r["final_est_cov"] for r in res)
+            tentative = float(sc * sum(sample.values())) * mult
+            explained = 0.0 if tentative == 0.0 else min(covered / tentative, 1.0)
         total_cov = sum(r["final_est_cov"] for r in res)  # :319-326
         total_seq = sum(r["final_est_cov"] * genomes[r["genome"]]["gn_size"] for r in res)
         for r in res:
             r["rel_abund"] = r["final_est_cov"] / total_cov * 100.0
-            r["seq_abund"] = r["final_est_cov"] * genomes[r["genome"]]["gn_size"] / total_seq * 100.0
+            r["seq_abund"] = r["final_est_cov"] * genomes[r["genome"]]["gn_size"] / total_seq * 100.0 * explained
         res.sort(key=lambda r: -r["rel_abund"])  # stable, :329-331
     else:
         res.sort(key=lambda r: -r["final_est_ani"])  # :332-334

@@ -933,10 +933,38 @@ static int sortkey_desc(const void *a, const void *b) {
     return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0); /* stable */
 }
 
+/* -u / --estimate-unknown with an explicit --read-seq-id (src/contain.rs:274-279: kmer_id = (seq_id/100)^k; the
+ * automatic estimate get_kmer_identity :901-951 walks the hash map in iteration order and is out of scope):
+ * estimate_true_cov (:377-389) and estimate_covered_bases (:391-408). */
+static void estimate_true_cov(syo_ani_result *res, size_t n, double kmer_id, double read_length, int k) {
+    const double multiplier = read_length / (read_length - (double)k + 1.);
+    for (size_t i = 0; i < n; i++) res[i].final_est_cov = res[i].final_est_cov / kmer_id * multiplier;
+}
+
+static int64_t contain_sample_impl(const syo_params *p, const uint64_t *kmers, const uint64_t *kmer_off,
+                                   const uint64_t *tracked, const uint64_t *tracked_off,
+                                   const uint64_t *gn_size, uint32_t n_genomes, const syo_sample *sample,
+                                   int nthreads, syo_ani_result *out, size_t cap, const syo_unknown *u);
+
 int64_t syo_contain_sample(const syo_params *p, const uint64_t *kmers, const uint64_t *kmer_off,
                            const uint64_t *tracked, const uint64_t *tracked_off,
                            const uint64_t *gn_size, uint32_t n_genomes, const syo_sample *sample,
                            int nthreads, syo_ani_result *out, size_t cap) {
+    return contain_sample_impl(p, kmers, kmer_off, tracked, tracked_off, gn_size, n_genomes, sample, nthreads, out, cap, NULL);
+}
+
+int64_t syo_contain_sample_unknown(const syo_params *p, const uint64_t *kmers, const uint64_t *kmer_off,
+                                   const uint64_t *tracked, const uint64_t *tracked_off,
+                                   const uint64_t *gn_size, uint32_t n_genomes, const syo_sample *sample,
+                                   int nthreads, syo_ani_result *out, size_t cap, const syo_unknown *u) {
+    return contain_sample_impl(p, kmers, kmer_off, tracked, tracked_off, gn_size, n_genomes, sample, nthreads, out, cap, u);
+}
+
+static int64_t contain_sample_impl(const syo_params *p, const uint64_t *kmers, const uint64_t *kmer_off,
+                                   const uint64_t *tracked, const uint64_t *tracked_off,
+                                   const uint64_t *gn_size, uint32_t n_genomes, const syo_sample *sample,
+                                   int nthreads, syo_ani_result *out, size_t cap, const syo_unknown *u) {
+    const double kmer_id = u ? pow(u->read_seq_id / 100., (double)p->k) : 1.;
     /* pass 1 (:284-292): par_iter over genomes */
     syo_ani_result *r1 = (syo_ani_result *)malloc(((size_t)n_genomes + 1) * sizeof(syo_ani_result));
     uint8_t *ok1 = (uint8_t *)calloc((size_t)n_genomes + 1, 1);
@@ -952,6 +980,7 @@ int64_t syo_contain_sample(const syo_params *p, const uint64_t *kmers, const uin
     syo_ani_result *res = r1;
     size_t nres = n1;
     syo_ani_result *r2 = NULL;
+    if (u) estimate_true_cov(r1, n1, kmer_id, u->mean_read_length, p->k); /* :295 */
     if (p->pseudotax) {
         /* winner_table (:410-430) */
         size_t tot = 0;
@@ -991,6 +1020,19 @@ int64_t syo_contain_sample(const syo_params *p, const uint64_t *kmers, const uin
         }
         free(ok2);
         winmap_free(&w);
+        double bases_explained = 1.;
+        if (u) {
+            estimate_true_cov(r2, n2, kmer_id, u->mean_read_length, p->k); /* :310 */
+            /* estimate_covered_bases :391-408 */
+            const double multiplier = u->mean_read_length / (u->mean_read_length - (double)p->k + 1.);
+            double covered = 0.;
+            for (size_t i = 0; i < n2; i++) covered += (double)gn_size[r2[i].genome] * r2[i].final_est_cov;
+            uint64_t total_counts = 0;
+            for (size_t i = 0; i <= sample->m.capmask; i++)
+                if (sample->m.keys[i] != EMPTY_KEY) total_counts += sample->m.vals[i];
+            const double tentative = (double)(u->sample_c * total_counts) * multiplier;
+            bases_explained = tentative == 0. ? 0. : (covered / tentative < 1. ? covered / tentative : 1.);
+        }
         /* abundances (:319-326) */
         double total_cov = 0., total_seq_cov = 0.;
         for (size_t i = 0; i < n2; i++) {
@@ -999,7 +1041,7 @@ int64_t syo_contain_sample(const syo_params *p, const uint64_t *kmers, const uin
         }
         for (size_t i = 0; i < n2; i++) {
             r2[i].rel_abund = r2[i].final_est_cov / total_cov * 100.;
-            r2[i].seq_abund = r2[i].final_est_cov * (double)gn_size[r2[i].genome] / total_seq_cov * 100. * 1.;
+            r2[i].seq_abund = r2[i].final_est_cov * (double)gn_size[r2[i].genome] / total_seq_cov * 100. * bases_explained;
         }
         res = r2;
         nres = n2;

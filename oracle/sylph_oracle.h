@@ -124,10 +124,16 @@ int syo_get_stats(const syo_params *p, const uint64_t *genome_kmers, size_t n,
  * reference pushes them from rayon workers in timing-dependent order).
  * tracked_off/tracked may be NULL (db sketched with --disable-profiling).
  * out has cap rows; returns number of rows (or -1 if cap too small). */
+/* -u / --estimate-unknown with --read-seq-id (percent): the sample's c and mean read length come from its sketch */
+typedef struct { double read_seq_id; double mean_read_length; uint64_t sample_c; } syo_unknown;
 int64_t syo_contain_sample(const syo_params *p, const uint64_t *kmers, const uint64_t *kmer_off,
                            const uint64_t *tracked, const uint64_t *tracked_off,
                            const uint64_t *gn_size, uint32_t n_genomes, const syo_sample *sample,
                            int nthreads, syo_ani_result *out, size_t cap);
+int64_t syo_contain_sample_unknown(const syo_params *p, const uint64_t *kmers, const uint64_t *kmer_off,
+                                   const uint64_t *tracked, const uint64_t *tracked_off,
+                                   const uint64_t *gn_size, uint32_t n_genomes, const syo_sample *sample,
+                                   int nthreads, syo_ani_result *out, size_t cap, const syo_unknown *u);
 
 /* Largest cov with PoissonCDF(cov; median) < CUTOFF_PVALUE for median 1..29
  * (src/contain.rs:664-675, src/constants.rs:3) computed by direct summation. */

@@ -15,9 +15,9 @@ class Survivor(C.Structure):
 class ContainParams(C.Structure):
     _fields_ = [
         ("k", C.c_int32), ("pseudotax", C.c_int32), ("no_ci", C.c_int32), ("no_adj", C.c_int32),
-        ("mean_coverage", C.c_int32), ("reserved", C.c_int32),
+        ("mean_coverage", C.c_int32), ("estimate_unknown", C.c_int32),
         ("min_number_kmers", C.c_double), ("min_count_correct", C.c_double),
-        ("minimum_ani", C.c_double), ("redundant_ani", C.c_double),
+        ("minimum_ani", C.c_double), ("redundant_ani", C.c_double), ("read_seq_id", C.c_double),
     ]
 
 
@@ -64,6 +64,7 @@ SIGNATURES = {
     "syl_sample_size": (_u64, [_vp]),
     "syl_sample_mean_read_length": (_d, [_vp]),
     "syl_sample_num_dup_removed": (_u64, [_vp]),
+    "syl_sample_set_mean_read_length": (None, [_vp, _d]),
     "syl_sample_download": (_i, [_vp, _vp, _vp, _vp]),
     "syl_sample_device_ptrs": (_i, [_vp, _pp, _pp]),
     "syl_sample_free": (None, [_vp]),

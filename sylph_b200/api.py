@@ -401,6 +401,11 @@ class Sample:
     def mean_read_length(self):
         return float(_lib.lib().syl_sample_mean_read_length(self._h))
 
+    @mean_read_length.setter
+    def mean_read_length(self, v):
+        """for uploaded sketches (.sylsp files carry the value; -u reads it)"""
+        _lib.lib().syl_sample_set_mean_read_length(self._h, float(v))
+
     @property
     def num_dup_removed(self):
         return int(_lib.lib().syl_sample_num_dup_removed(self._h))

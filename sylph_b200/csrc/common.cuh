@@ -122,6 +122,8 @@ struct syl_sample {
     uint64_t c = 200;
     double mean_read_length = 0.;
     uint64_t num_dup_removed = 0;
+    uint64_t sum_counts = 0;   // sum of all counts (computed on first use: -u / estimate_covered_bases)
+    bool sum_counts_valid = false;
 };
 
 // Device-resident batch of GenomeSketch (src/types.rs:163-173) in CSR form

@@ -1119,6 +1119,11 @@ __global__ void k_join2_order(const SampleView *__restrict__ views, uint64_t G, 
 
 }  // namespace syl
 
+namespace syl {
+// what -u needs to know about a sample (src/contain.rs:377-408)
+struct SampleMeta { double mean_read_length; uint64_t c, sum_counts; };
+}
+
 // One in-flight device-driven query / profile (C ABI: syl_profile_job).
 struct syl_profile_job {
     syl_ctx *ctx = nullptr;
@@ -1126,6 +1131,8 @@ struct syl_profile_job {
     syl::StatParams P;       // pass-2 / query parameters
     bool profile = true;
     double redundant_ani = 99.;
+    double read_seq_id = -1.;            // > 0: -u with an explicit read identity
+    std::vector<syl::SampleMeta> metas;  // per sample (only filled for -u)
     uint32_t S = 0, world = 1, rank = 0;
     uint64_t G = 0, R = 0, max_n = 0, tbytes = 0;
     int stage = 0;           // 1 pass 1 enqueued, 2 ranked, 3 pass 2 enqueued
@@ -1139,6 +1146,45 @@ struct syl_profile_job {
 };
 
 namespace syl {
+
+__global__ void k_sum_counts(const uint32_t *__restrict__ count, uint64_t n, unsigned long long *__restrict__ out) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += count[i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// -u: sample meta (sum of the counts is computed on the device once per sample handle)
+static int sample_metas(syl_ctx *ctx, const syl_sample *const *samples, uint32_t n, std::vector<SampleMeta> &out) {
+    cudaStream_t st = ctx->stream;
+    out.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        syl_sample *s = const_cast<syl_sample *>(samples[i]);
+        if (!s->sum_counts_valid) {
+            unsigned long long *d = reinterpret_cast<unsigned long long *>(ctx->d_counters + 19);
+            SYL_CUDA(cudaMemsetAsync(d, 0, 8, st));
+            if (s->n) k_sum_counts<<<ctx->num_sms * 4, 256, 0, st>>>(s->count, s->n, d);
+            SYL_CUDA(cudaMemcpyAsync(ctx->h_counters + 19, d, 8, cudaMemcpyDeviceToHost, st));
+            SYL_CUDA(cudaStreamSynchronize(st));
+            s->sum_counts = ctx->h_counters[19];
+            s->sum_counts_valid = true;
+        }
+        out[i] = {s->mean_read_length, s->c, s->sum_counts};
+    }
+    return SYL_OK;
+}
+
+// estimate_true_cov (src/contain.rs:377-389) for the rows of one call (query: all rows; profile: the kept rows)
+static inline double unknown_multiplier(const SampleMeta &m, int k) { return m.mean_read_length / (m.mean_read_length - (double)k + 1.); }
+
+static int check_unknown_args(const syl_contain_params *p) {
+    if (p->estimate_unknown && !(p->read_seq_id > 0.)) {
+        set_error("-u without --read-seq-id: the automatic read-identity estimate depends on hash-map iteration order (src/contain.rs:901-951)");
+        return SYL_ERR_UNSUPPORTED;
+    }
+    return SYL_OK;
+}
 
 static void job_release(syl_profile_job *j) {
     delete j;  // the scratch blocks go back to the owning ctx's cache (DevBuf::owner)
@@ -1163,6 +1209,8 @@ static int job_begin(syl_ctx *ctx, const syl_db *db, const syl_sample *const *sa
     pp.pseudotax = profile ? 1 : 0;
     j->P = make_params(&pp);
     j->redundant_ani = pp.redundant_ani;
+    JOB_TRY(check_unknown_args(p));
+    if (p->estimate_unknown) { j->read_seq_id = p->read_seq_id; JOB_TRY(sample_metas(ctx, samples, n_samples, j->metas)); }
     j->R = R ? ((R + 255) & ~255ull) : default_rows_per_rank(n_samples, db->n_genomes);
     j->tbytes = table_bytes(j->R);
     const uint64_t NP = (uint64_t)j->S * j->G;
@@ -1302,7 +1350,8 @@ static int job_pass2(syl_profile_job *j) {
 
 // derep_if_reassign_threshold (src/contain.rs:353-375) + abundances (:319-326) + the output order (:329-334)
 // for the pass-2 rows of all shards: row.reserved = pass-1 containment count, row.seq_abund = genome size
-static void profile_finalize(std::vector<syl_ani_row> &r2, uint32_t n_samples, int k, double redundant_ani, std::vector<syl_ani_row> &all) {
+static void profile_finalize(std::vector<syl_ani_row> &r2, uint32_t n_samples, int k, double redundant_ani, std::vector<syl_ani_row> &all,
+                             const std::vector<SampleMeta> *metas = nullptr, double read_seq_id = -1.) {
     std::sort(r2.begin(), r2.end(), [](const syl_ani_row &a, const syl_ani_row &b) {
         return a.sample != b.sample ? a.sample < b.sample : a.genome < b.genome;
     });
@@ -1316,6 +1365,18 @@ static void profile_finalize(std::vector<syl_ani_row> &r2, uint32_t n_samples, i
             const double reass_thresh = threshold * (double)n2.glen;
             if (num_reassign < reass_thresh) kept.push_back(n2);
         }
+        double bases_explained = 1.;
+        if (metas && read_seq_id > 0.) {  // -u: estimate_true_cov (:310) + estimate_covered_bases (:391-408)
+            const SampleMeta &m = (*metas)[smp];
+            const double mult = unknown_multiplier(m, k), kid = std::pow(read_seq_id / 100., (double)k);
+            double covered = 0.;
+            for (syl_ani_row &r : kept) {
+                r.final_est_cov = r.final_est_cov / kid * mult;
+                covered += r.seq_abund * r.final_est_cov;  // seq_abund still holds gn_size
+            }
+            const double tentative = (double)(m.c * m.sum_counts) * mult;
+            bases_explained = tentative == 0. ? 0. : std::min(covered / tentative, 1.);
+        }
         double total_cov = 0., total_seq_cov = 0.;
         for (const syl_ani_row &r : kept) {
             total_cov += r.final_est_cov;
@@ -1324,7 +1385,7 @@ static void profile_finalize(std::vector<syl_ani_row> &r2, uint32_t n_samples, i
         for (syl_ani_row &r : kept) {
             const double gs = r.seq_abund;
             r.rel_abund = r.final_est_cov / total_cov * 100.;
-            r.seq_abund = r.final_est_cov * gs / total_seq_cov * 100. * 1.;
+            r.seq_abund = r.final_est_cov * gs / total_seq_cov * 100. * bases_explained;
             r.reserved = 0.;
         }
         std::stable_sort(kept.begin(), kept.end(),
@@ -1366,11 +1427,16 @@ static int job_finish(syl_profile_job *j, std::vector<syl_ani_row> &out, uint64_
     if (ovf) { set_error("coverage count >= 256: CSR formulation needed"); return SYL_ERR_UNSUPPORTED; }
     if (need > j->R) { *need_R = need; set_error("row table too small"); return SYL_ERR_CAPACITY; }
     if (j->profile) {
-        profile_finalize(rows, j->S, j->P.k, j->redundant_ani, out);
+        profile_finalize(rows, j->S, j->P.k, j->redundant_ani, out, &j->metas, j->read_seq_id);
     } else {
         std::sort(rows.begin(), rows.end(), [](const syl_ani_row &a, const syl_ani_row &b) {
             return a.sample != b.sample ? a.sample < b.sample : a.genome < b.genome;
         });
+        if (j->read_seq_id > 0.)  // estimate_true_cov (:295)
+            for (syl_ani_row &r : rows) {
+                const SampleMeta &m = j->metas[r.sample];
+                r.final_est_cov = r.final_est_cov / std::pow(j->read_seq_id / 100., (double)j->P.k) * unknown_multiplier(m, j->P.k);
+            }
         out.swap(rows);
     }
     return SYL_OK;
@@ -1510,7 +1576,8 @@ void syl_contain_params_default(syl_contain_params *p, int k, int pseudotax) {
     p->no_ci = 0;
     p->no_adj = 0;
     p->mean_coverage = 0;
-    p->reserved = 0;
+    p->estimate_unknown = 0;
+    p->read_seq_id = -1.;
     p->min_number_kmers = 50.;
     p->min_count_correct = 3.;
     p->minimum_ani = -1.;
@@ -1520,6 +1587,7 @@ void syl_contain_params_default(syl_contain_params *p, int k, int pseudotax) {
 int syl_query(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
               const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows) {
     SYL_TRY(check_pair_args(ctx, db, samples, n_samples, p, rows, cap, n_rows));
+    SYL_TRY(check_unknown_args(p));
     *n_rows = 0;
     SYL_CUDA(cudaSetDevice(ctx->device));
     syl::tl_ctx = ctx;
@@ -1540,6 +1608,12 @@ int syl_query(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, 
     SYL_TRY(scratch_init(ctx, db, samples, n_samples, false, S));
     const StatParams P = make_params(p);
     SYL_TRY(contain_pass(ctx, db, P, false, S, out, false, nullptr));
+    if (p->estimate_unknown) {  // estimate_true_cov (src/contain.rs:295)
+        std::vector<SampleMeta> metas;
+        SYL_TRY(sample_metas(ctx, samples, n_samples, metas));
+        for (syl_ani_row &r : out)
+            r.final_est_cov = r.final_est_cov / std::pow(p->read_seq_id / 100., (double)p->k) * unknown_multiplier(metas[r.sample], p->k);
+    }
     *n_rows = out.size();
     if (out.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
     std::copy(out.begin(), out.end(), rows);
@@ -1610,6 +1684,7 @@ void syl_profile_job_free(syl_profile_job *j) { job_release(j); }
 int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples, uint32_t n_samples,
                 const syl_contain_params *p, syl_ani_row *rows, uint64_t cap, uint64_t *n_rows) {
     SYL_TRY(check_pair_args(ctx, db, samples, n_samples, p, rows, cap, n_rows));
+    SYL_TRY(check_unknown_args(p));
     *n_rows = 0;
     if (!db->has_tracked) {  // src/contain.rs:231-234
         set_error("Attempting profiling, but the database was sketched with the --disable-profiling option");
@@ -1647,35 +1722,19 @@ int syl_profile(syl_ctx *ctx, const syl_db *db, const syl_sample *const *samples
     k_mark_survivors<<<nblk(n1, 256), 256, 0, st>>>(S.rows.p, n1, S.G, db->genome_base, S.survivor.p, S.ani1.p);
     ctx->launches++;
     SYL_TRY(contain_pass(ctx, db, P, true, S, r2, false, nullptr));
-    const double threshold = std::pow(pp.redundant_ani / 100., (double)pp.k);
-    size_t i1 = 0, i2 = 0;
-    for (uint32_t smp = 0; smp < n_samples; smp++) {
-        // derep_if_reassign_threshold (src/contain.rs:353-375), per sample, genome order
-        std::vector<syl_ani_row> kept;
-        while (i1 < r1.size() && r1[i1].sample < smp) i1++;
-        size_t j = i1;
-        for (; i2 < r2.size() && r2[i2].sample == smp; i2++) {
-            const syl_ani_row &n2 = r2[i2];
-            while (j < r1.size() && r1[j].sample == smp && r1[j].genome < n2.genome) j++;
-            const syl_ani_row &o = r1[j];
-            const double num_reassign = (double)(o.contain - n2.contain);
-            const double reass_thresh = threshold * (double)n2.glen;
-            if (num_reassign < reass_thresh) kept.push_back(n2);
+    // stash pass 1's containment count and the genome size in the pass-2 rows, then the common host finish
+    // (derep, -u, abundances, order)
+    {
+        size_t j = 0;
+        for (syl_ani_row &n2 : r2) {  // both lists are ordered by (sample, genome); r2's pairs are a subset of r1's
+            while (j < r1.size() && (r1[j].sample < n2.sample || (r1[j].sample == n2.sample && r1[j].genome < n2.genome))) j++;
+            n2.reserved = (double)r1[j].contain;
+            n2.seq_abund = (double)db->h_gn_size[n2.genome - db->genome_base];
         }
-        // abundances (src/contain.rs:319-326), summed in genome order
-        double total_cov = 0., total_seq_cov = 0.;
-        for (const syl_ani_row &r : kept) {
-            total_cov += r.final_est_cov;
-            total_seq_cov += r.final_est_cov * (double)db->h_gn_size[r.genome - db->genome_base];
-        }
-        for (syl_ani_row &r : kept) {
-            r.rel_abund = r.final_est_cov / total_cov * 100.;
-            r.seq_abund = r.final_est_cov * (double)db->h_gn_size[r.genome - db->genome_base] / total_seq_cov * 100. * 1.;
-        }
-        std::stable_sort(kept.begin(), kept.end(),
-                         [](const syl_ani_row &a, const syl_ani_row &b) { return a.rel_abund > b.rel_abund; });
-        all.insert(all.end(), kept.begin(), kept.end());
     }
+    std::vector<SampleMeta> metas;
+    if (pp.estimate_unknown) SYL_TRY(sample_metas(ctx, samples, n_samples, metas));
+    profile_finalize(r2, n_samples, pp.k, pp.redundant_ani, all, pp.estimate_unknown ? &metas : nullptr, pp.estimate_unknown ? pp.read_seq_id : -1.);
     *n_rows = all.size();
     if (all.size() > cap) { set_error("row buffer too small"); return SYL_ERR_CAPACITY; }
     std::copy(all.begin(), all.end(), rows);

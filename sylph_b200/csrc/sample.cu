@@ -1476,6 +1476,7 @@ int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_
 uint64_t syl_sample_size(const syl_sample *s) { return s ? s->n : 0; }
 double syl_sample_mean_read_length(const syl_sample *s) { return s ? s->mean_read_length : 0.; }
 uint64_t syl_sample_num_dup_removed(const syl_sample *s) { return s ? s->num_dup_removed : 0; }
+void syl_sample_set_mean_read_length(syl_sample *s, double v) { if (s) s->mean_read_length = v; }
 
 int syl_sample_download(syl_ctx *ctx, const syl_sample *s, uint64_t *hash, uint32_t *count) {
     if (!ctx || !s) { set_error("NULL argument"); return SYL_ERR_ARG; }

@@ -23,7 +23,7 @@ def test_header_symbols_all_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), "library does not export " + n
         assert n in _lib.SIGNATURES, "python binding misses " + n
-    assert lib.syl_abi_version() == 1
+    assert lib.syl_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -37,6 +37,7 @@ def test_struct_layouts_match_header():
     p = _lib.ContainParams()
     _lib.lib().syl_contain_params_default(C.byref(p), 31, 1)
     assert (p.k, p.pseudotax, p.min_number_kmers, p.min_count_correct, p.minimum_ani, p.redundant_ani) == (31, 1, 50.0, 3.0, -1.0, 99.0)
+    assert (p.estimate_unknown, p.read_seq_id) == (0, -1.0) and C.sizeof(_lib.ContainParams) == 64
 
 
 def test_no_cpu_fallback_without_gpu():

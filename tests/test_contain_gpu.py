@@ -224,3 +224,29 @@ def test_sharded_profile_stages_on_one_gpu(ctx):
         assert len(rows) == len(exp)
         for f in rows.dtype.names:
             assert np.array_equal(rows[f], exp[f]), (rpr, f)
+
+
+@pytest.mark.parametrize("pseudotax", [False, True])
+def test_estimate_unknown_with_read_seq_id(ctx, pseudotax):
+    """-u with an explicit --read-seq-id (src/contain.rs:274-279, 377-408): coverage scaled by read identity and the
+    read-length / k-mer ratio, sequence abundance by the fraction of the sample the profile explains.  The automatic
+    identity estimate is refused (hash-map iteration order)."""
+    import sylph_b200
+    from oracle import oracle as O
+    from sylph_b200.api import contain_params
+    g, smp = synth_db_and_sample(ctx, 80, 100000, 60000, 20, c=20)
+    d, hc = g.download(), smp.download()
+    db = ctx.build_db(g)
+    P = contain_params(pseudotax=pseudotax, estimate_unknown=1, read_seq_id=98.0)
+    rows = ctx.profile(db, [smp], P) if pseudotax else sort_query_rows(ctx.query(db, [smp], P))
+    exp = O.contain_sample(O.default_params(pseudotax=pseudotax), d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"],
+                           O.Sample(*hc), unknown=O.Unknown(98.0, smp.mean_read_length, 20))
+    plain = O.contain_sample(O.default_params(pseudotax=pseudotax), d["kmers"], d["kmer_off"], d["tracked"], d["tracked_off"], d["gn_size"],
+                             O.Sample(*hc))
+    assert len(exp) > 5 and exp[0].final_est_cov > plain[0].final_est_cov
+    compare(rows, exp, pseudotax)
+    if pseudotax:
+        assert sum(float(r["seq_abund"]) for r in rows) < 99.9     # the community covers 20 of 80 genomes; reads carry errors
+    with pytest.raises(sylph_b200.SylphError) as e:
+        ctx.query(db, [smp], contain_params(pseudotax=False, estimate_unknown=1))
+    assert e.value.code == 5                                          # SYL_ERR_UNSUPPORTED

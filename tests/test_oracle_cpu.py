@@ -271,6 +271,21 @@ def test_contain_sample_vs_pyref(pseudotax):
             assert np.allclose(list(r.ci), e["ci"], rtol=0, atol=1e-12)
         if pseudotax:
             assert abs(r.rel_abund - e["rel_abund"]) < 1e-9 and abs(r.seq_abund - e["seq_abund"]) < 1e-9
+    # -u / --estimate-unknown with an explicit --read-seq-id (src/contain.rs:274-279, 377-408): coverage scaled by the
+    # read identity and the k-mer / read length ratio, sequence abundance by the fraction of reads explained
+    unk = (98.5, 142.7, 20000)
+    exp_u = R.contain_sample([dict(kmers=g["kmers"].tolist(), tracked=g["tracked"].tolist(), gn_size=g["gn_size"]) for g in genomes],
+                             sample, pseudotax=pseudotax, unknown=unk)
+    got_u = O.contain_sample(O.default_params(pseudotax=pseudotax), kmers, koff, tracked, toff, gs, O.Sample(sh, sc),
+                             unknown=O.Unknown(*unk))
+    assert [r.genome for r in got_u] == [e["genome"] for e in exp_u] == [r.genome for r in got]
+    for r, e, r0 in zip(got_u, exp_u, got):
+        assert abs(r.final_est_cov - e["final_est_cov"]) < 1e-9 * max(1.0, e["final_est_cov"])
+        assert r.final_est_cov > r0.final_est_cov and r.final_est_ani == r0.final_est_ani
+        if pseudotax:
+            assert abs(r.rel_abund - e["rel_abund"]) < 1e-9 and abs(r.seq_abund - e["seq_abund"]) < 1e-9
+    if pseudotax:
+        assert sum(r.seq_abund for r in got_u) < 99.0 < sum(r.seq_abund for r in got) + 1e-6   # some reads are unexplained
 
 
 @pytest.fixture(scope="module")
