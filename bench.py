@@ -33,6 +33,19 @@ K, C = 31, 200
 GENOME_LEN = 4_000_000
 
 
+def usable_cores():
+    """Host cores this process may really use: the container's CPU quota (cgroup cpu.max) caps os.cpu_count();
+    running the CPU arm with more threads than the quota only gets it throttled."""
+    n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 def sketch_config(args):
     """The `config` object of the sketch workload: identical in our arm and in the reference arm."""
     n_bases = args.reads * READ_LEN
@@ -194,7 +207,7 @@ def cpu_sketch_baseline(host_bases, host_off, n_reads_sample, repeats=1):
     """Oracle (AVX2-intrinsic seeding + OpenMP, dedup sequential like the reference) on a bounded sample."""
     import numpy as np
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     nb = int(host_off[n_reads_sample])
     b = host_bases[:nb]
     o = host_off[:n_reads_sample + 1].astype(np.uint64)
@@ -227,7 +240,7 @@ def run_reference(args):
         return
     from sylph_b200 import synth
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     b, o = synth.reads(args.reads, READ_LEN, device=dev)
     b, o = b.cpu().numpy(), o.cpu().numpy().astype(np.uint64)
@@ -468,7 +481,7 @@ def bench_genomes(args, ctx, rank, world, local):
     if rank == 0 and not args.no_cpu:   # parity + CPU arm on a few genomes of the batch
         from oracle import oracle as O
         from concurrent.futures import ThreadPoolExecutor
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         hb = bases.cpu().numpy()
         idx = list(range(0, nG, max(1, nG // 16)))
 
@@ -603,7 +616,7 @@ def bench_pairs(args, ctx, rank, world, local, reads):
             d = genomes.download()
         if rank == 0:
             from oracle import oracle as O
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             h, c = samples[0].download()
             smp = O.Sample(h, c)
             p = O.default_params(pseudotax=True)

@@ -124,10 +124,12 @@ int default_pack_threads() {
     }
     unsigned hc = std::thread::hardware_concurrency();
     if (!hc) hc = 1;
+    unsigned lw = 1;
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): share the host's cores
-        const int lw = atoi(e);
-        if (lw > 1) hc = std::max(1u, hc / (unsigned)lw);
+        const int v = atoi(e);
+        if (v > 1) lw = (unsigned)v;
     }
+    hc = std::max(1u, hc / lw);
     // a container's CPU quota (cgroup v2 cpu.max / v1 cfs_quota): threads beyond it only get the process throttled
     {
         long long quota = -1, period = 100000;
@@ -140,9 +142,10 @@ int default_pack_threads() {
             fclose(g);
             if (FILE *h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(h, "%lld", &period) != 1) period = 100000; fclose(h); }
         }
-        if (quota > 0 && period > 0) {  // leave one core's worth for the thread that feeds the GPU
+        if (quota > 0 && period > 0) {  // the ranks share the quota; leave one core's worth for the threads that feed the GPUs
             const unsigned q = (unsigned)((quota + period - 1) / period);
-            return (int)std::max(1u, std::min(std::min(hc, 32u), q > 1 ? q - 1 : 1u));
+            const unsigned mine = q > lw ? (q - 1) / lw : 1u;
+            return (int)std::max(1u, std::min(std::min(hc, 32u), mine));
         }
     }
     // the packer is memory-bound well before all cores of a big host are busy (measured on a 2 x 32-core
