@@ -575,16 +575,28 @@ __device__ __forceinline__ uint64_t wyrand_at(uint64_t seed, uint64_t d) {
 constexpr int BOOT_ITERS = 100;
 constexpr int BOOT_THREADS = 256;
 
-// 64 x 64 -> 128-bit product, xor of the two halves (WyRand's output function): four 32 x 32 -> 64
-// multiplies with 64-bit accumulate (IMAD.WIDE), no duplicated partial products.
+// 64 x 64 -> 128-bit product, xor of the two halves (WyRand's output function).  The 128-bit type
+// compiles to four IMAD.WIDE with carry-in/out (11 instructions with the xors); a hand-split into
+// 32-bit halves costs 18 because every 64-bit addend needs an aligned register pair.
 __device__ __forceinline__ uint64_t mum_xor(uint64_t a, uint64_t b) {
-    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
-    const uint64_t p00 = (uint64_t)a0 * b0;
-    const uint64_t m1 = (uint64_t)a0 * b1 + (p00 >> 32);            // < 2^64: (2^32-1)^2 + 2^32 - 1
-    const uint64_t m2 = (uint64_t)a1 * b0 + (uint32_t)m1;
-    const uint64_t hi = (uint64_t)a1 * b1 + (m1 >> 32) + (m2 >> 32);
-    const uint64_t lo = (m2 << 32) | (uint32_t)p00;
-    return lo ^ hi;
+    const unsigned __int128 p = (unsigned __int128)a * b;
+    return (uint64_t)p ^ (uint64_t)(p >> 64);
+}
+
+// ctr += (x >= t) for t >= 1, given nt = 2^64 - t: the carry out of the 64-bit sum x + nt.
+// Three instructions (IADD3 carry-out, IADD3.X, add-with-carry); the C forms compile to 5-6.
+__device__ __forceinline__ void count_ge(uint32_t &ctr, uint64_t x, uint64_t nt) {
+    asm("{\n\t.reg .u32 d;\n\tadd.cc.u32 d, %1, %3;\n\taddc.cc.u32 d, %2, %4;\n\taddc.u32 %0, %0, 0;\n\t}"
+        : "+r"(ctr) : "r"((uint32_t)x), "r"((uint32_t)(x >> 32)), "r"((uint32_t)nt), "r"((uint32_t)(nt >> 32)));
+}
+
+// Smallest 64-bit draw x whose Lemire index floor(x*n / 2^64) reaches c, for 0 <= c < n < 2^32:
+// ceil(c * 2^64 / n) by two 64/32 long-division steps.  c >= n has no such draw (callers mask it).
+__device__ __forceinline__ uint64_t lemire_threshold(uint64_t c, uint64_t n) {
+    if (c >= n) return ~0ull;
+    const uint64_t d1 = c << 32, q1 = d1 / n, r1 = d1 % n;
+    const uint64_t d0 = r1 << 32, q0 = d0 / n, r0 = d0 % n;
+    return (q1 << 32) + q0 + (r0 ? 1 : 0);
 }
 
 // One CTA resamples |full| values for one iteration `it` of one bootstrapped row.
@@ -594,7 +606,7 @@ __device__ __forceinline__ uint64_t mum_xor(uint64_t a, uint64_t b) {
 // majority) cost nothing beyond the RNG.
 __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32_t *__restrict__ hist_in, const StatParams &P,
                                          double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
-                                         uint32_t *__restrict__ reject_flag, uint32_t *Hb, uint64_t *cum) {
+                                         uint32_t *__restrict__ reject_flag, uint32_t *Hb, uint64_t *cum, uint64_t *thr) {
     const uint32_t *H = hist_in + (uint64_t)row * 17;
     if (threadIdx.x < 17) Hb[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
@@ -602,38 +614,55 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
         for (int v = 0; v < 17; v++) { acc += H[v]; cum[v] = acc; }  // cum[v] = #values <= v
     }
     __syncthreads();
-    const uint64_t n = cum[16], z = cum[0];
-    const uint32_t n32 = (uint32_t)n, z32 = (uint32_t)z;  // |full| = |genome_kmers| < 2^32
-    const uint32_t c1 = (uint32_t)cum[1], c2 = (uint32_t)cum[2], c3 = (uint32_t)cum[3];
-    uint32_t n1 = 0, n2 = 0, n3 = 0;
+    if (threadIdx.x < 4) thr[threadIdx.x] = lemire_threshold(cum[threadIdx.x], cum[16]);
+    __syncthreads();
+    const uint64_t n = cum[16];
+    const uint32_t n32 = (uint32_t)n;  // |full| = |genome_kmers| < 2^32
+    // Lemire's index is hi = floor(x*n / 2^64), and hi >= c  <=>  x >= ceil(c * 2^64 / n): the four
+    // common class boundaries are compared on the 64-bit draw itself, so the two 32x32->64 multiplies
+    // of the index are only paid by the rare draws that need it (values >= 4, rejection candidates).
+    const uint64_t t3 = thr[3], nt0 = 0ull - thr[0], nt1 = 0ull - thr[1], nt2 = 0ull - thr[2], nt3 = 0ull - t3;
+    uint32_t ge0 = 0, ge1 = 0, ge2 = 0, ge3 = 0;
+    const bool more_than_3 = cum[3] < n;
     // draw number d = it*n + j + 1; WyRand state s(d) = 7 + d*C0, advanced by BOOT_THREADS*C0 per trip
     uint64_t s = 7ull + ((uint64_t)it * n + threadIdx.x + 1) * 0x2d358dccaa6c78a5ull;
     const uint64_t s_step = (uint64_t)BOOT_THREADS * 0x2d358dccaa6c78a5ull;
     for (uint32_t j = threadIdx.x; j < n32; j += BOOT_THREADS, s += s_step) {
         const uint64_t x = mum_xor(s, s ^ 0x8bb84b93962eacc9ull);
-        // fastrand gen_mod_u64 (Lemire): hi = (x*n) >> 64, lo = (x*n) mod 2^64, with n < 2^32
-        const uint64_t a = (uint64_t)(uint32_t)x * n32;                 // x_lo * n
-        const uint64_t b = (x >> 32) * n32 + (a >> 32);                 // x_hi * n + carry
-        const uint32_t hi = (uint32_t)(b >> 32);
-        if ((uint32_t)b == 0u) {  // necessary for lo < n (prob 2^-32): only then form lo exactly
-            const uint64_t lo = (b << 32) | (uint32_t)a;
+        // fastrand gen_mod_u64 redraws when lo = (x*n) mod 2^64 < (2^64 - n) mod n.  lo < n < 2^32 needs
+        // the low word of x_lo*n to be < n (probability n / 2^32): only then form lo exactly.
+        if ((uint32_t)x * n32 < n32) {
+            const uint64_t lo = x * n;
             if (lo < n && lo < (0ull - n) % n) atomicExch(reject_flag + row, 1u);  // the reference would redraw
         }
         // full_covs[hi] = v with cum[v-1] <= hi < cum[v].  Branch-free for the common values (0: most draws;
         // 1, 2, 3: counted in registers) — lanes of a warp draw different values, a branch per value would
         // serialise them (measured: 60 instructions per draw with the branches, 23 of 32 lanes active).
-        const uint32_t g0 = hi >= z32 ? 1u : 0u, g1 = hi >= c1 ? 1u : 0u, g2 = hi >= c2 ? 1u : 0u, g3 = hi >= c3 ? 1u : 0u;
-        n1 += g0 - g1;
-        n2 += g1 - g2;
-        n3 += g2 - g3;
-        if (g3) {  // a value >= 4: rare for a bootstrapped row (median <= 2)
+        count_ge(ge0, x, nt0);
+        count_ge(ge1, x, nt1);
+        count_ge(ge2, x, nt2);
+        count_ge(ge3, x, nt3);
+        if (more_than_3 && x >= t3) {  // a value >= 4: rare for a bootstrapped row (median <= 2)
+            const uint64_t hi = __umul64hi(x, n);
             uint32_t v = 4;
 #pragma unroll
             for (int step = 8; step >= 1; step >>= 1)
-                if (v + step <= 16 && (uint64_t)hi >= cum[v + step - 1]) v += step;
+                if (v + step <= 16 && hi >= cum[v + step - 1]) v += step;
             atomicAdd(&Hb[v], 1u);
         }
     }
+    // a boundary of 0 has every draw at or above it (the carry form needs t >= 1); a boundary equal to n
+    // has none (its threshold would be 2^64)
+    const uint32_t trips = threadIdx.x < n32 ? (n32 - threadIdx.x + BOOT_THREADS - 1) / BOOT_THREADS : 0u;
+    if (cum[0] == 0) ge0 = trips;
+    if (cum[1] == 0) ge1 = trips;
+    if (cum[2] == 0) ge2 = trips;
+    if (cum[3] == 0) ge3 = trips;
+    if (cum[0] >= n) ge0 = 0;
+    if (cum[1] >= n) ge1 = 0;
+    if (cum[2] >= n) ge2 = 0;
+    if (cum[3] >= n) ge3 = 0;
+    uint32_t n1 = ge0 - ge1, n2 = ge1 - ge2, n3 = ge2 - ge3;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         n1 += __shfl_xor_sync(0xffffffffu, n1, d); n2 += __shfl_xor_sync(0xffffffffu, n2, d); n3 += __shfl_xor_sync(0xffffffffu, n3, d);
@@ -665,7 +694,8 @@ k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
             uint32_t *__restrict__ reject_flag) {
     __shared__ uint32_t Hb[17];
     __shared__ uint64_t cum[17];
-    boot_one(blockIdx.y, blockIdx.x, hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum);
+    __shared__ uint64_t thr[4];
+    boot_one(blockIdx.y, blockIdx.x, hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr);
 }
 
 // persistent form: the number of bootstrapped rows is read from device memory (no host round trip
@@ -676,9 +706,10 @@ k_boot_iter_p(const uint32_t *__restrict__ hist_in, const unsigned long long *__
               uint32_t *__restrict__ reject_flag) {
     __shared__ uint32_t Hb[17];
     __shared__ uint64_t cum[17];
+    __shared__ uint64_t thr[4];
     const uint64_t nb = *d_nboot < boot_cap ? *d_nboot : boot_cap;
     for (uint64_t item = blockIdx.x; item < nb * BOOT_ITERS; item += gridDim.x) {
-        boot_one((uint32_t)(item / BOOT_ITERS), (uint32_t)(item % BOOT_ITERS), hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum);
+        boot_one((uint32_t)(item / BOOT_ITERS), (uint32_t)(item % BOOT_ITERS), hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr);
         __syncthreads();  // Hb / cum are rewritten by the next item
     }
 }

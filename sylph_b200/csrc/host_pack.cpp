@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+
 #include <algorithm>
 
 namespace syl {
@@ -214,6 +216,11 @@ void PackPool::worker() {
 void PackPool::wait_chunk(uint32_t c) {
     std::unique_lock<std::mutex> lk(mu_);
     cv_done_.wait(lk, [&]() { return remaining_[c] == 0; });
+}
+
+bool PackPool::wait_chunk_for(uint32_t c, unsigned usec) {
+    std::unique_lock<std::mutex> lk(mu_);
+    return cv_done_.wait_for(lk, std::chrono::microseconds(usec), [&]() { return remaining_[c] == 0; });
 }
 
 bool PackPool::chunk_done(uint32_t c) {

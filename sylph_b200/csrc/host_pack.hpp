@@ -41,6 +41,7 @@ public:
     void start(const std::vector<PackItem> *items, const std::vector<uint32_t> *chunk_items, int64_t gate);
     void open_gate(int64_t gate);
     void wait_chunk(uint32_t c);
+    bool wait_chunk_for(uint32_t c, unsigned usec);  // true: chunk c is done; false: timed out
     bool chunk_done(uint32_t c);
     // take chunk c away from the workers if none of its items has been started; true: the caller handles it
     bool try_skip_chunk(uint32_t c);

@@ -1213,7 +1213,11 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
             continue;
         }
         if (steal_first) { steal_turn = false; continue; }  // nothing to take from the back right now: go on with packed chunks
-        I.pool->wait_chunk((uint32_t)f);  // the packers are on it (or the only chunks left are theirs)
+        // Front chunk still being packed.  If an ASCII copy is in flight and there are untouched chunks at the back,
+        // whichever finishes first decides the next move (blocking on the packers alone would idle the link for as
+        // long as they take: on a host whose memory system is shared by eight ranks that is most of the call).
+        if (steal_ok && ascii_busy && bk > f) I.pool->wait_chunk_for((uint32_t)f, 40);
+        else I.pool->wait_chunk((uint32_t)f);  // the packers are on it (or the only chunks left are theirs)
     }
     I.pool->open_gate((int64_t)1 << 60);  // all remaining items (skipped chunks included) drain
     I.pool->finish();

@@ -235,3 +235,42 @@ def test_host_packer_is_exact_byte_to_seq():
         b = rng.integers(0, 256, n, dtype=np.uint8)
         assert np.array_equal(pack2(b, 1), ref(b)), n
         assert np.array_equal(pack2(b, 3), ref(b)), n
+
+
+def _lemire_threshold(c, n):
+    """k_boot_iter_p's lemire_threshold: ceil(c * 2^64 / n) by two 64/32 division steps."""
+    if c >= n:
+        return (1 << 64) - 1
+    d1 = c << 32
+    q1, r1 = divmod(d1, n)
+    q0, r0 = divmod(r1 << 32, n)
+    assert q1 < (1 << 32) and q0 < (1 << 32) and d1 < (1 << 64) and (r1 << 32) < (1 << 64)
+    return (q1 << 32) + q0 + (1 if r0 else 0)
+
+
+def test_bootstrap_class_boundaries_on_the_raw_draw():
+    """The bootstrap kernel never forms Lemire's index for the common classes: floor(x*n / 2^64) >= c
+    is decided as x >= ceil(c * 2^64 / n), and that compare is taken from the carry of x + (2^64 - T)."""
+    rng = np.random.default_rng(5)
+    M = 1 << 64
+    for _ in range(400):
+        n = int(rng.integers(1, 1 << 32)) if rng.random() < 0.5 else int(rng.integers(1, 40000))
+        for c in {0, 1, n - 1, n, int(rng.integers(0, n + 1)), int(rng.integers(0, n + 1))}:
+            if c < 0:
+                continue
+            T = _lemire_threshold(c, n)
+            if c < n:
+                assert T == -((-c * M) // n)
+            xs = [0, M - 1, T, max(T - 1, 0), min(T + 1, M - 1)] + [int(v) for v in rng.integers(0, M, 8, dtype=np.uint64)]
+            for x in xs:
+                hi = (x * n) >> 64
+                if c < n:
+                    assert (hi >= c) == (x >= T), (n, c, x)
+                    if T >= 1:
+                        assert ((x + (M - T)) >> 64) == (1 if x >= T else 0)
+                else:
+                    assert hi < c                    # nothing is drawn at or above n: the kernel zeroes this count
+                # fastrand's redraw needs lo < n < 2^32, which needs the low word of x_lo * n to be < n
+                lo = (x * n) % M
+                if lo < n:
+                    assert ((x & 0xFFFFFFFF) * n) & 0xFFFFFFFF < n
