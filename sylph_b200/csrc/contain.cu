@@ -614,7 +614,7 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
         for (int v = 0; v < 17; v++) { acc += H[v]; cum[v] = acc; }  // cum[v] = #values <= v
     }
     __syncthreads();
-    if (threadIdx.x < 4) thr[threadIdx.x] = lemire_threshold(cum[threadIdx.x], cum[16]);
+    if (threadIdx.x < 16) thr[threadIdx.x] = lemire_threshold(cum[threadIdx.x], cum[16]);
     __syncthreads();
     const uint64_t n = cum[16];
     const uint32_t n32 = (uint32_t)n;  // |full| = |genome_kmers| < 2^32
@@ -624,6 +624,8 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
     const uint64_t t3 = thr[3], nt0 = 0ull - thr[0], nt1 = 0ull - thr[1], nt2 = 0ull - thr[2], nt3 = 0ull - t3;
     uint32_t ge0 = 0, ge1 = 0, ge2 = 0, ge3 = 0;
     const bool more_than_3 = cum[3] < n;
+    uint32_t vmax = 4;  // largest value present (cum[vmax] = n): no draw lies at or above boundary vmax
+    while (vmax < 16 && cum[vmax] < n) vmax++;
     // draw number d = it*n + j + 1; WyRand state s(d) = 7 + d*C0, advanced by BOOT_THREADS*C0 per trip
     uint64_t s = 7ull + ((uint64_t)it * n + threadIdx.x + 1) * 0x2d358dccaa6c78a5ull;
     const uint64_t s_step = (uint64_t)BOOT_THREADS * 0x2d358dccaa6c78a5ull;
@@ -642,12 +644,11 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
         count_ge(ge1, x, nt1);
         count_ge(ge2, x, nt2);
         count_ge(ge3, x, nt3);
-        if (more_than_3 && x >= t3) {  // a value >= 4: rare for a bootstrapped row (median <= 2)
-            const uint64_t hi = __umul64hi(x, n);
+        if (more_than_3 && x >= t3) {
+            // a value >= 4 (a few percent of the draws of a row with median 2, but then most WARPS have such a lane):
+            // walk the remaining class boundaries upwards — the mass sits right above 4 — again on the raw draw
             uint32_t v = 4;
-#pragma unroll
-            for (int step = 8; step >= 1; step >>= 1)
-                if (v + step <= 16 && hi >= cum[v + step - 1]) v += step;
+            while (v < vmax && x >= thr[v]) v++;
             atomicAdd(&Hb[v], 1u);
         }
     }
@@ -694,23 +695,30 @@ k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
             uint32_t *__restrict__ reject_flag) {
     __shared__ uint32_t Hb[17];
     __shared__ uint64_t cum[17];
-    __shared__ uint64_t thr[4];
+    __shared__ uint64_t thr[16];
     boot_one(blockIdx.y, blockIdx.x, hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr);
 }
 
 // persistent form: the number of bootstrapped rows is read from device memory (no host round trip
-// between the statistics kernel and the bootstrap); CTAs stride over the (row, iteration) items
+// between the statistics kernel and the bootstrap).  One CTA per resident slot; the (row, iteration)
+// items are handed out through a device counter, because their cost follows |genome_kmers| of the
+// row and a fixed stride leaves the CTAs that drew the large rows running alone at the end.
 __global__ void __launch_bounds__(BOOT_THREADS)
 k_boot_iter_p(const uint32_t *__restrict__ hist_in, const unsigned long long *__restrict__ d_nboot, uint64_t boot_cap, StatParams P,
               double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
-              uint32_t *__restrict__ reject_flag) {
+              uint32_t *__restrict__ reject_flag, uint32_t *__restrict__ work_ctr) {
     __shared__ uint32_t Hb[17];
     __shared__ uint64_t cum[17];
-    __shared__ uint64_t thr[4];
+    __shared__ uint64_t thr[16];
+    __shared__ uint32_t s_item;
     const uint64_t nb = *d_nboot < boot_cap ? *d_nboot : boot_cap;
-    for (uint64_t item = blockIdx.x; item < nb * BOOT_ITERS; item += gridDim.x) {
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(work_ctr, 1u);
+        __syncthreads();
+        const uint64_t item = s_item;
+        if (item >= nb * BOOT_ITERS) break;
         boot_one((uint32_t)(item / BOOT_ITERS), (uint32_t)(item % BOOT_ITERS), hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr);
-        __syncthreads();  // Hb / cum are rewritten by the next item
+        __syncthreads();  // Hb / cum / s_item are rewritten by the next item
     }
 }
 
@@ -1244,6 +1252,7 @@ static int job_begin(syl_ctx *ctx, const syl_db *db, const syl_sample *const *sa
     if (p->estimate_unknown) { j->read_seq_id = p->read_seq_id; JOB_TRY(sample_metas(ctx, samples, n_samples, j->metas)); }
     j->R = R ? ((R + 255) & ~255ull) : default_rows_per_rank(n_samples, db->n_genomes);
     j->tbytes = table_bytes(j->R);
+    if (j->R * BOOT_ITERS >= 0xFFFF0000ull) { set_error("row capacity too large for the bootstrap work counter"); return fail(SYL_ERR_ARG); }
     const uint64_t NP = (uint64_t)j->S * j->G;
     if (NP >= 0x7FFFFFFFull) { set_error("samples x genomes exceeds 2^31 pairs per call; split the sample batch"); return fail(SYL_ERR_ARG); }
     if (NP * COV_BINS * 4 > (8ull << 30)) { set_error("pair histograms exceed 8 GB; split the sample batch"); return fail(SYL_ERR_UNSUPPORTED); }
@@ -1258,7 +1267,7 @@ static int job_begin(syl_ctx *ctx, const syl_db *db, const syl_sample *const *sa
     JOB_TRY(j->tab1.alloc(j->tbytes, st));
     JOB_TRY(j->boot_rows.alloc(j->R, st)); JOB_TRY(j->hist.alloc(j->R * 17, st));
     JOB_TRY(j->res_ani.alloc(j->R * BOOT_ITERS, st)); JOB_TRY(j->res_lambda.alloc(j->R * BOOT_ITERS, st));
-    JOB_TRY(j->res_ok.alloc(j->R * BOOT_ITERS, st)); JOB_TRY(j->reject.alloc(j->R, st));
+    JOB_TRY(j->res_ok.alloc(j->R * BOOT_ITERS, st)); JOB_TRY(j->reject.alloc(j->R + 1, st));  // [R] = the bootstrap's work counter
     if (profile) {
         JOB_TRY(j->lost.alloc(NP, st)); JOB_TRY(j->order.alloc(NP, st)); JOB_TRY(j->contain1.alloc(NP, st));
         JOB_TRY(j->tab2.alloc(j->tbytes, st)); JOB_TRY(j->gn_size.alloc(std::max<uint64_t>(j->G, 1), st));
@@ -1304,11 +1313,11 @@ static int job_bootstrap(syl_profile_job *j, void *tab) {
     cudaStream_t st = ctx->stream;
     if (j->P.no_ci) return SYL_OK;
     ShardTable *t = reinterpret_cast<ShardTable *>(tab);
-    SYL_CUDA(cudaMemsetAsync(j->reject.p, 0, (size_t)j->R * 4, st));
+    SYL_CUDA(cudaMemsetAsync(j->reject.p, 0, (size_t)(j->R + 1) * 4, st));
     KernelTimer kt(ctx, SYL_KERNEL_BOOT);
     static int boot_ctas = 0;  // resident CTAs per SM (a partially filled second wave would double the tail)
     if (!boot_ctas && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&boot_ctas, k_boot_iter_p, BOOT_THREADS, 0) != cudaSuccess) boot_ctas = 4;
-    k_boot_iter_p<<<ctx->num_sms * std::max(boot_ctas, 1), BOOT_THREADS, 0, st>>>(j->hist.p, &t->n_boot, j->R, j->P, j->res_ani.p, j->res_lambda.p, j->res_ok.p, j->reject.p);
+    k_boot_iter_p<<<ctx->num_sms * std::max(boot_ctas, 1), BOOT_THREADS, 0, st>>>(j->hist.p, &t->n_boot, j->R, j->P, j->res_ani.p, j->res_lambda.p, j->res_ok.p, j->reject.p, j->reject.p + j->R);
     k_boot_seq<<<nblk(j->R, 32), 32, 0, st>>>(j->hist.p, (uint32_t)j->R, j->P, j->reject.p, j->res_ani.p, j->res_lambda.p, j->res_ok.p, &t->n_boot);
     k_boot_final<<<(unsigned)j->R, 128, 0, st>>>(j->boot_rows.p, (uint32_t)j->R, j->res_ani.p, j->res_lambda.p, j->res_ok.p, table_rows(tab), &t->n_boot);
     kt.stop();

@@ -291,72 +291,30 @@ static int sketch_genomes_device_sort(syl_ctx *ctx, const uint8_t *d_bases, uint
 // ------------------------------------------------------------------------------------------------
 // Sort-free post-pass.
 //   * k_seed writes every tile's survivors into the tile's own slot (SlotOut), so the output is in
-//     tile = position order already; k_tile_sort_compact orders the <= 512 survivors INSIDE a tile by
+//     tile = position order already; its flush orders the <= 512 survivors INSIDE a tile by
 //     (contig, position) in shared memory and compacts the tiles (scan of the per-tile counts).
 //   * duplicates (a hash seen twice in one genome, src/sketch.rs:594-600): a genome's survivors are now
-//     contiguous; CTA (genome, part) walks them and groups the hashes of ITS share of the hash space
-//     (~6 000 of them) in a shared-memory table — no sort by hash.
+//     contiguous; they are grouped through one L2-resident open-addressing table in which every genome
+//     owns a region of twice its survivor count — no sort by hash, no per-CTA capacity to overflow.
 //   * k_spacing as before; kept / tracked survivors are compacted with block counts + one small scan.
 // One host synchronisation (the totals), like the read-sketch path.
 constexpr uint32_t GEN_SLOT = 512;        // survivors per tile slot (= the seeding kernel's staging capacity)
-constexpr uint32_t GEN_PART_N = 6000;     // expected hashes per (genome, part) CTA
-constexpr uint32_t GEN_SLOTS = 16384;     // table slots per CTA (load factor ~0.37)
-constexpr int GEN_DUP_THREADS = 512;
 
-// tile t: slot -> ordered by (contig, pos) -> compact arrays at toff[t].  A survivor's window start is unique inside
-// its tile, so the order is the rank of its bit in a 32 768-bit map of the tile: set the bits, scan the word
-// popcounts, look the rank up — three barriers instead of the 36 compare-exchange rounds of a bitonic network
-// (which took 0.2 ms per 0.5 Gbp).
+// tile t: slot -> compact arrays at toff[t].  (Round 2 first ordered the slot here, by the rank of each survivor's
+// window start in a 32 768-bit map of the tile; that ranking now runs inside k_seed's flush, where the survivors are
+// still in shared memory, and this kernel is a copy.)
 __global__ void __launch_bounds__(256)
-k_tile_sort_compact(const syl_survivor *__restrict__ slots, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ toff,
-                    const uint64_t *__restrict__ contig_off, uint32_t tile_bases, int k, uint64_t *__restrict__ poskey,
-                    uint64_t *__restrict__ hash) {
-    __shared__ uint32_t bits[1024];   // SEED_TILE = 32768 window starts
-    __shared__ uint32_t pre[1024];    // survivors before word w
-    __shared__ uint32_t wsum[8];
-    const uint32_t t = blockIdx.x, n = tile_cnt[t];
-    if (n == 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < 1024; i += 256) bits[i] = 0u;
-    __syncthreads();
-    const syl_survivor *src = slots + (uint64_t)t * GEN_SLOT;
-    const uint64_t T0 = (uint64_t)t * tile_bases;
-    syl_survivor mine[2];
-    uint32_t pw[2];
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const uint32_t i = tid + 256 * e;
-        if (i < n) {
-            mine[e] = src[i];
-            pw[e] = (uint32_t)(contig_off[mine[e].rec] + mine[e].pos - (uint64_t)(k - 1) - T0);  // window start, tile-relative
-            atomicOr(&bits[pw[e] >> 5], 1u << (pw[e] & 31u));
-        }
-    }
-    __syncthreads();
-    {   // exclusive scan of the 1024 word popcounts: 4 words per thread
-        uint32_t c[4], tot = 0;
-#pragma unroll
-        for (int e = 0; e < 4; e++) { c[e] = __popc(bits[4 * tid + e]); tot += c[e]; }
-        uint32_t inc = tot;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
-        if (lane == 31) wsum[wid] = inc;
-        __syncthreads();
-        uint32_t base = inc - tot;
-        for (int w = 0; w < wid; w++) base += wsum[w];
-#pragma unroll
-        for (int e = 0; e < 4; e++) { pre[4 * tid + e] = base; base += c[e]; }
-    }
-    __syncthreads();
-    const uint32_t out0 = toff[t];
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const uint32_t i = tid + 256 * e;
-        if (i < n) {
-            const uint32_t w = pw[e] >> 5, r = pre[w] + __popc(bits[w] & ((1u << (pw[e] & 31u)) - 1u));
-            poskey[out0 + r] = ((uint64_t)mine[e].rec << 32) | mine[e].pos;
-            hash[out0 + r] = mine[e].hash;
-        }
+k_tile_compact(const syl_survivor *__restrict__ slots, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ toff,
+               uint64_t n_tiles, uint64_t *__restrict__ poskey, uint64_t *__restrict__ hash) {
+    // one warp per tile: the slot is already in position order (k_seed's slotted flush), so this is a copy
+    const uint64_t t = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const uint32_t n = tile_cnt[t], out0 = toff[t];
+    const syl_survivor *src = slots + t * GEN_SLOT;
+    for (uint32_t i = threadIdx.x & 31; i < n; i += 32) {
+        const syl_survivor sv = src[i];
+        poskey[out0 + i] = ((uint64_t)sv.rec << 32) | sv.pos;
+        hash[out0 + i] = sv.hash;
     }
 }
 
@@ -369,66 +327,71 @@ __global__ void k_genome_ranges(const uint64_t *__restrict__ poskey, const uint3
     gs[g] = g == n_genomes ? (uint32_t)N : (uint32_t)lower_bound_u64(poskey, N, genome_off[g] << 32);
 }
 
-__global__ void k_genome_parts(const uint32_t *__restrict__ gs, uint64_t n_genomes, uint32_t *__restrict__ parts) {
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_genomes) parts[g] = (gs[g + 1] - gs[g] + GEN_PART_N - 1) / GEN_PART_N;
-}
+// ---- duplicates (src/sketch.rs:594-600,605: a hash seen twice in one genome drops all its occurrences) ----
+// One open-addressing table for the whole batch in global memory (it stays in the 126 MB L2): genome g owns the
+// slots [2 * gs[g], 2 * gs[g+1]) — load factor 1/2 whatever the genome's size or its share of repeats, so there is
+// no table-overflow case.  A key is the 64-bit hash (< 2^63 for every c >= 2); bit 63 of a stored key is the
+// "seen again" mark, set with an atomic OR by every later occurrence; the empty key is all ones.
+constexpr unsigned long long DUP_EMPTY = 0xFFFFFFFFFFFFFFFFull, DUP_MARK = 1ull << 63;
 
-__device__ __forceinline__ uint32_t gen_part_of(uint64_t h, uint32_t P) {
-    return (uint32_t)((((h >> 8) & 0xFFFFFFull) * P) >> 24);  // hashes are uniform below the threshold: so are these 24 bits
-}
-
-// block b -> (genome g, part p); flags the survivors of g whose hash falls into part p: 0 = the hash occurs
-// >= 2x in the genome (dropped, src/sketch.rs:594-600,605), 3 = undecided (k_spacing decides kept / tracked)
-__global__ void __launch_bounds__(GEN_DUP_THREADS)
-k_genome_dups(const uint64_t *__restrict__ hash, const uint32_t *__restrict__ gs, const uint32_t *__restrict__ pstart, uint64_t n_genomes,
-              uint8_t *__restrict__ flag, uint32_t *__restrict__ overflow) {
-    extern __shared__ __align__(16) uint8_t gd_smem[];
-    unsigned long long *tab = reinterpret_cast<unsigned long long *>(gd_smem);
-    uint8_t *dup = gd_smem + (size_t)GEN_SLOTS * 8;
-    const uint32_t b = blockIdx.x;
-    if (b >= pstart[n_genomes]) return;
-    uint32_t lo = 0, hi = (uint32_t)n_genomes;  // last g with pstart[g] <= b
-    while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (pstart[mid] <= b) lo = mid; else hi = mid; }
-    const uint32_t g = lo, p = b - pstart[g], P = pstart[g + 1] - pstart[g];
-    const uint32_t s0 = gs[g], s1 = gs[g + 1];
-    for (uint32_t i = threadIdx.x; i < GEN_SLOTS; i += GEN_DUP_THREADS) { tab[i] = 0xFFFFFFFFFFFFFFFFull; dup[i] = 0; }
-    __syncthreads();
-    // four independent loads per trip: the loop is bound by the latency of the hash loads (L2), not by the table
-    for (uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 4 * GEN_DUP_THREADS) {
-        unsigned long long hq[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * GEN_DUP_THREADS; hq[q] = i < s1 ? hash[i] : 0xFFFFFFFFFFFFFFFFull; }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const unsigned long long h = hq[q];
-            if (h == 0xFFFFFFFFFFFFFFFFull || gen_part_of(h, P) != p) continue;
-            uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
-            uint32_t probes = 0;
-            for (;; probes++) {
-                if (probes >= GEN_SLOTS) { atomicExch(overflow, 1u); break; }  // table full (pathological skew): generic path
-                const unsigned long long prev = atomicCAS(&tab[sl], 0xFFFFFFFFFFFFFFFFull, h);
-                if (prev == 0xFFFFFFFFFFFFFFFFull) break;
-                if (prev == h) { dup[sl] = 1; break; }
-                sl = (sl + 1) & (GEN_SLOTS - 1);
-            }
-        }
+// genome of survivor i: the last g with gs[g] <= i, searched between the genomes of the block's first and last
+// survivor (s_lo / s_hi, found once per block)
+__device__ __forceinline__ uint32_t dup_genome_of(const uint32_t *__restrict__ gs, uint64_t n_genomes, uint32_t i, uint32_t first, uint32_t last,
+                                                   uint32_t *s_lo, uint32_t *s_hi) {
+    if (threadIdx.x < 2) {
+        const uint32_t x = threadIdx.x ? last : first;
+        uint32_t lo = 0, hi = (uint32_t)n_genomes;
+        while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (gs[mid] <= x) lo = mid; else hi = mid; }
+        *(threadIdx.x ? s_hi : s_lo) = lo;
     }
     __syncthreads();
-    for (uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 4 * GEN_DUP_THREADS) {
-        unsigned long long hq[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * GEN_DUP_THREADS; hq[q] = i < s1 ? hash[i] : 0xFFFFFFFFFFFFFFFFull; }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const unsigned long long h = hq[q];
-            if (h == 0xFFFFFFFFFFFFFFFFull || gen_part_of(h, P) != p) continue;
-            uint32_t sl = (uint32_t)(h ^ (h >> 29)) & (GEN_SLOTS - 1);
-            uint32_t probes = 0;
-            while (tab[sl] != h && probes < GEN_SLOTS) { sl = (sl + 1) & (GEN_SLOTS - 1); probes++; }
-            flag[i0 + q * GEN_DUP_THREADS] = (probes < GEN_SLOTS && dup[sl]) ? 0 : 3;
-        }
+    uint32_t lo = *s_lo, hi = *s_hi + 1;
+    while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (gs[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t dup_slot(unsigned long long h, uint32_t size) {
+    return (uint32_t)((((h >> 6) & 0xFFFFFFFFull) * size) >> 32);  // hashes are uniform below the threshold: so are these 32 bits
+}
+
+__global__ void __launch_bounds__(256)
+k_dups_insert(const uint64_t *__restrict__ hash, const uint32_t *__restrict__ gs, uint64_t n_genomes, const uint32_t *__restrict__ d_n,
+              uint32_t cap, unsigned long long *__restrict__ table) {
+    __shared__ uint32_t s_lo, s_hi;
+    const uint32_t N = min(*d_n, cap), first = blockIdx.x * 256u;
+    if (first >= N) return;
+    const uint32_t i = first + threadIdx.x;
+    const uint32_t g = dup_genome_of(gs, n_genomes, min(i, N - 1), first, min(first + 255u, N - 1), &s_lo, &s_hi);
+    if (i >= N) return;
+    const uint32_t base = gs[g], size = 2u * (gs[g + 1] - base);
+    unsigned long long *T = table + 2ull * base;
+    const unsigned long long h = hash[i];
+    uint32_t sl = dup_slot(h, size);
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&T[sl], DUP_EMPTY, h);
+        if (prev == DUP_EMPTY) break;
+        if ((prev & ~DUP_MARK) == h) { if (!(prev & DUP_MARK)) atomicOr(&T[sl], DUP_MARK); break; }
+        if (++sl == size) sl = 0;
     }
+}
+
+// flag[i] = 0: the hash occurs >= 2x in its genome (dropped), 3: undecided (k_spacing decides kept / tracked)
+__global__ void __launch_bounds__(256)
+k_dups_flag(const uint64_t *__restrict__ hash, const uint32_t *__restrict__ gs, uint64_t n_genomes, const uint32_t *__restrict__ d_n,
+            uint32_t cap, const unsigned long long *__restrict__ table, uint8_t *__restrict__ flag) {
+    __shared__ uint32_t s_lo, s_hi;
+    const uint32_t N = min(*d_n, cap), first = blockIdx.x * 256u;
+    if (first >= N) return;
+    const uint32_t i = first + threadIdx.x;
+    const uint32_t g = dup_genome_of(gs, n_genomes, min(i, N - 1), first, min(first + 255u, N - 1), &s_lo, &s_hi);
+    if (i >= N) return;
+    const uint32_t base = gs[g], size = 2u * (gs[g + 1] - base);
+    const unsigned long long *T = table + 2ull * base;
+    const unsigned long long h = hash[i];
+    uint32_t sl = dup_slot(h, size);
+    unsigned long long k;
+    while (((k = T[sl]) & ~DUP_MARK) != h) { if (++sl == size) sl = 0; }  // every hash was inserted: the walk ends
+    flag[i] = (k & DUP_MARK) ? 0 : 3;
 }
 
 // per block of 1024 survivors: number of kept (flag 1) and tracked (flag 2) ones
@@ -501,12 +464,13 @@ static int sketch_genomes_device_slots(syl_ctx *ctx, const uint8_t *d_bases, uin
     if (n_tiles * GEN_SLOT >= 0xFFFFFFFFull) { set_error("genome batch too large; split the batch"); return SYL_ERR_ARG; }
     const uint64_t cap = std::min<uint64_t>(n_tiles * GEN_SLOT, n_bases / c + n_bases / (4 * c) + 65536);  // compact survivors
     DevBuf<syl_survivor> slots;
-    DevBuf<uint32_t> tile_cnt, toff, gs, parts, pstart, bk, bt, bk_off, bt_off, scan_k, scan_t, t1, t2, flags32;
+    DevBuf<uint32_t> tile_cnt, toff, gs, bk, bt, bk_off, bt_off, scan_k, scan_t, t1, t2, flags32;
     DevBuf<uint64_t> poskey, hash, tmp_k, tmp_t;
+    DevBuf<unsigned long long> dup_table;
     DevBuf<uint8_t> flag;
     SYL_TRY(slots.alloc(n_tiles * GEN_SLOT, st));
     SYL_TRY(tile_cnt.alloc(n_tiles, st)); SYL_TRY(toff.alloc(n_tiles + 1, st));
-    SYL_TRY(flags32.alloc(2, st));  // [0] slot overflow, [1] table overflow
+    SYL_TRY(flags32.alloc(2, st));  // [0] slot overflow, [1] unused
     SYL_CUDA(cudaMemsetAsync(flags32.p, 0, 8, st));
     SYL_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint64_t), st));
     SeedJob job;
@@ -520,16 +484,13 @@ static int sketch_genomes_device_slots(syl_ctx *ctx, const uint8_t *d_bases, uin
     SYL_TRY(scan_u32(ctx, tile_cnt.p, n_tiles, toff.p, t1, t2));   // toff[n_tiles] = N (device)
     const uint32_t *d_n = toff.p + n_tiles;
     SYL_TRY(poskey.alloc(cap, st)); SYL_TRY(hash.alloc(cap, st)); SYL_TRY(flag.alloc(cap, st));
-    k_tile_sort_compact<<<(unsigned)n_tiles, 256, 0, st>>>(slots.p, tile_cnt.p, toff.p, d_contig_off, (uint32_t)seed_cta_tile_bases(), k,
-                                                           poskey.p, hash.p);
-    SYL_TRY(gs.alloc(n_genomes + 1, st)); SYL_TRY(parts.alloc(n_genomes, st)); SYL_TRY(pstart.alloc(n_genomes + 1, st));
+    k_tile_compact<<<nblk(n_tiles, 8), 256, 0, st>>>(slots.p, tile_cnt.p, toff.p, n_tiles, poskey.p, hash.p);
+    SYL_TRY(gs.alloc(n_genomes + 1, st));
     k_genome_ranges<<<nblk(n_genomes + 1, 256), 256, 0, st>>>(poskey.p, d_n, d_genome_off, n_genomes, gs.p);
-    k_genome_parts<<<nblk(n_genomes, 256), 256, 0, st>>>(gs.p, n_genomes, parts.p);
-    SYL_TRY(scan_u32(ctx, parts.p, n_genomes, pstart.p, t1, t2));
-    const size_t dsm = (size_t)GEN_SLOTS * 9;
-    SYL_CUDA(cudaFuncSetAttribute(k_genome_dups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    const uint64_t dup_grid = cap / GEN_PART_N + n_genomes + 1;  // >= sum of ceil(n_g / PART_N)
-    k_genome_dups<<<(unsigned)dup_grid, GEN_DUP_THREADS, dsm, st>>>(hash.p, gs.p, pstart.p, n_genomes, flag.p, flags32.p + 1);
+    SYL_TRY(dup_table.alloc(2 * cap, st));
+    SYL_CUDA(cudaMemsetAsync(dup_table.p, 0xFF, 2 * cap * sizeof(unsigned long long), st));
+    k_dups_insert<<<nblk(cap, 256), 256, 0, st>>>(hash.p, gs.p, n_genomes, d_n, (uint32_t)cap, dup_table.p);
+    k_dups_flag<<<nblk(cap, 256), 256, 0, st>>>(hash.p, gs.p, n_genomes, d_n, (uint32_t)cap, dup_table.p, flag.p);
     // N is only known on the device: size the element-wise grids for the capacity (threads past N return)
     k_spacing<<<nblk(cap, 256), 256, 0, st>>>(poskey.p, cap, min_spacing, flag.p, d_n);
     const uint64_t nb = (cap + 1023) / 1024;

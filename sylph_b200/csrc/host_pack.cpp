@@ -16,6 +16,8 @@ namespace syl {
 
 namespace {
 
+constexpr uint64_t PACK_PREFETCH_DEFAULT = 0;
+
 struct Lut {
     uint8_t t[256];
     Lut() {
@@ -79,6 +81,16 @@ __attribute__((target("avx2"))) void pack2_avx2(const uint8_t *bases, uint64_t n
     if (n % 32) pack2_scalar(bases + 32 * full, n % 32, words + 2 * full);
 }
 
+__attribute__((target("avx512f,avx512bw,avx512vbmi"), always_inline)) inline __m128i pack64_avx512(
+    const uint8_t *src, __m512i tab_lo, __m512i tab_hi, __m512i w41, __m512i w161, __m128i rev) {
+    const __m512i v = _mm512_loadu_si512(src);
+    const __mmask64 hi = _mm512_movepi8_mask(v);                                // bytes >= 0x80 -> code 0
+    const __m512i code = _mm512_maskz_permutex2var_epi8(~hi, tab_lo, v, tab_hi);  // BYTE_TO_SEQ[b & 0x7F]
+    const __m512i p2 = _mm512_maddubs_epi16(code, w41);
+    const __m512i p4 = _mm512_madd_epi16(p2, w161);                             // 16 dwords: 4 bases each, in the low byte
+    return _mm_shuffle_epi8(_mm512_cvtepi32_epi8(p4), rev);                     // word = B0<<24 | B1<<16 | B2<<8 | B3
+}
+
 // 64 bases -> 4 words with AVX-512 VBMI: the low 7 bits of a byte index a 128-entry BYTE_TO_SEQ table held in two
 // registers (VPERMI2B); bytes >= 0x80 are masked to 0.
 __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack2_avx512(const uint8_t *bases, uint64_t n, uint32_t *words) {
@@ -89,15 +101,27 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack2_avx512(const u
     const __m512i w161 = _mm512_set1_epi32(0x00010010);  // words (16, 1): p0*16 + p1
     const __m128i rev = _mm_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12);
     const uint64_t full = n / 64;
-    for (uint64_t i = 0; i < full; i++) {
-        const __m512i v = _mm512_loadu_si512(bases + 64 * i);
-        const __mmask64 hi = _mm512_movepi8_mask(v);                                // bytes >= 0x80 -> code 0
-        const __m512i code = _mm512_maskz_permutex2var_epi8(~hi, tab_lo, v, tab_hi);  // BYTE_TO_SEQ[b & 0x7F]
-        const __m512i p2 = _mm512_maddubs_epi16(code, w41);
-        const __m512i p4 = _mm512_madd_epi16(p2, w161);                             // 16 dwords: 4 bases each, in the low byte
-        const __m128i b = _mm512_cvtepi32_epi8(p4);                                 // B0 .. B15
-        _mm_storeu_si128(reinterpret_cast<__m128i *>(words + 4 * i), _mm_shuffle_epi8(b, rev));  // word = B0<<24 | B1<<16 | B2<<8 | B3
+    // software prefetch distance in bytes (0 = off): the hardware streamer stops at every 4 KB page of the (pinned,
+    // small-page) source buffer; SYL_PACK_PREFETCH overrides
+    static const uint64_t pf = []() -> uint64_t { const char *e = getenv("SYL_PACK_PREFETCH"); return e ? (uint64_t)atoll(e) : PACK_PREFETCH_DEFAULT; }();
+#define pack64(src) pack64_avx512((src), tab_lo, tab_hi, w41, w161, rev)
+    uint64_t i = 0;
+    for (; i + 4 <= full; i += 4) {  // 256 bases -> one 64-byte store
+        const uint8_t *src = bases + 64 * i;
+        if (pf) {
+            _mm_prefetch(reinterpret_cast<const char *>(src + pf), _MM_HINT_T0);
+            _mm_prefetch(reinterpret_cast<const char *>(src + pf + 64), _MM_HINT_T0);
+            _mm_prefetch(reinterpret_cast<const char *>(src + pf + 128), _MM_HINT_T0);
+            _mm_prefetch(reinterpret_cast<const char *>(src + pf + 192), _MM_HINT_T0);
+        }
+        __m512i o = _mm512_castsi128_si512(pack64(src));
+        o = _mm512_inserti32x4(o, pack64(src + 64), 1);
+        o = _mm512_inserti32x4(o, pack64(src + 128), 2);
+        o = _mm512_inserti32x4(o, pack64(src + 192), 3);
+        _mm512_storeu_si512(words + 4 * i, o);
     }
+    for (; i < full; i++) _mm_storeu_si128(reinterpret_cast<__m128i *>(words + 4 * i), pack64(bases + 64 * i));
+#undef pack64
     if (n % 64) pack2_scalar(bases + 64 * full, n % 64, words + 4 * full);
 }
 

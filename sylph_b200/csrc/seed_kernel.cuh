@@ -53,6 +53,12 @@ struct SeedMeta {
     uint16_t run_rec[SEED_MAXRUNS];    // run -> record slot + 1 (filled by a max-scan over run starts)
 };
 static_assert(sizeof(SeedMeta) <= SEED_ASC_BYTES, "meta must fit in the dead ASCII region");
+static_assert(SEED_TILE <= 65536, "tile-relative window starts are kept as u16");
+// survivors (16 B) fill only the lower half of the 32-byte staging entries; the upper half keeps each
+// staged survivor's tile-relative window start
+__device__ __forceinline__ uint16_t *seed_stage_pos(SeedMeta &M) {
+    return reinterpret_cast<uint16_t *>(reinterpret_cast<syl_survivor *>(M.stage) + SEED_STAGE);
+}
 
 // Multipliers 2^(32-s) for the three xor-shift distances, passed as kernel parameters so that
 // ptxas cannot strength-reduce "mul.hi by a power of two" back into an ALU-pipe shift.
@@ -157,6 +163,7 @@ __device__ __forceinline__ void seed_resolve(const SeedSmem &S, SeedMeta &M, uin
         sv.pos = (uint32_t)((long long)pw - M.rel[j] + (K - 1));
         if (idx < (unsigned)SEED_STAGE) {
             reinterpret_cast<syl_survivor *>(M.stage)[idx] = sv;
+            seed_stage_pos(M)[idx] = (uint16_t)pw;  // tile-relative window start: the slotted flush ranks by it
         } else {
             const unsigned long long gi = atomicAdd(g_count, 1ull);
             if (gi < cap) reinterpret_cast<syl_survivor *>(out)[gi] = sv;
@@ -456,8 +463,36 @@ k_seed(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint64_t *__re
             slot.tile_cnt[blockIdx.x] = nst;
             if (total > lim) atomicExch(slot.overflow, 1u);
         }
+        // The slot is written in POSITION order (the genome post-pass then needs no sort at all): bitmap of the
+        // staged window starts in the dead stream words, rank = survivors before the word + bits below.
+        constexpr int NW = SEED_TILE / 32, PER = NW / SEED_THREADS;
+        static_assert(NW % SEED_THREADS == 0 && NW <= SEED_CW_WORDS, "bitmap layout");
+        uint32_t *bits = S.fw, *pre = S.cw;
+        const uint16_t *sp = seed_stage_pos(M);
+        for (int i = tid; i < NW; i += SEED_THREADS) bits[i] = 0u;
+        __syncthreads();
+        for (unsigned int i = tid; i < nst; i += SEED_THREADS) atomicOr(&bits[sp[i] >> 5], 1u << (sp[i] & 31u));
+        __syncthreads();
+        {
+            uint32_t cnt[PER], tot = 0;
+#pragma unroll
+            for (int e = 0; e < PER; e++) { cnt[e] = __popc(bits[PER * tid + e]); tot += cnt[e]; }
+            uint32_t inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += v; }
+            if ((tid & 31) == 31) M.warp_tot[tid >> 5] = (int)inc;
+            __syncthreads();
+            uint32_t base = inc - tot;
+            for (int w = 0; w < (tid >> 5); w++) base += (uint32_t)M.warp_tot[w];
+#pragma unroll
+            for (int e = 0; e < PER; e++) { pre[PER * tid + e] = base; base += cnt[e]; }
+        }
+        __syncthreads();
         syl_survivor *dst = reinterpret_cast<syl_survivor *>(out) + (uint64_t)blockIdx.x * slot.cap;
-        for (unsigned int i = tid; i < nst; i += SEED_THREADS) dst[i] = reinterpret_cast<const syl_survivor *>(M.stage)[i];
+        for (unsigned int i = tid; i < nst; i += SEED_THREADS) {
+            const uint32_t p = sp[i], w = p >> 5;
+            dst[pre[w] + __popc(bits[w] & ((1u << (p & 31u)) - 1u))] = reinterpret_cast<const syl_survivor *>(M.stage)[i];
+        }
         return;
     }
     const unsigned int staged = min(M.stage_count, (unsigned)SEED_STAGE);
