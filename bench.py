@@ -523,7 +523,11 @@ def rows_equal_oracle(rows, exp, tol=1e-6):
     return True, None
 
 
-PAIR_KERNELS = {"join": "k_join_hist<pass 1>", "join2": "k_join2_hits", "stats": "k_stats_hist", "boot": "k_boot_iter"}
+PAIR_KERNELS = {"join": "k_join_hist<pass 1> (+ k_range_bounds)", "join2": "k_join2_order (+ k_local_best)", "stats": "k_stats_hist", "boot": "k_boot_iter_p"}
+PAIR_LIMITER = {"join": "DRAM: random sectors of the db index (ncu: 0.32 GB per sample at 4.9 TB/s)",
+                "join2": "DRAM / latency: genome ids of the recorded equal ranges",
+                "stats": "latency (one warp per touched pair)",
+                "boot": "integer issue: ~42 instructions per 32 bootstrap draws, issue slots 69 % busy, no DRAM traffic"}
 
 
 def bench_pairs(args, ctx, rank, world, local, reads):
@@ -592,19 +596,26 @@ def bench_pairs(args, ctx, rank, world, local, reads):
                               "collectives": ("all_gather(pass-1 row tables) + all_reduce MIN(winner order per sample key) + "
                                               "all_gather(pass-2 row tables), NCCL, no host sync in between") if world > 1 else "none"},
            "e2e_note": "syl_profile returns rows in host memory: the D2H of the result rows is inside the timed region"}
-    # live roofline of the step's dominant kernel: CUDA events recorded inside the library around every launch
+    # live roofline: CUDA events recorded inside the library around every launch.  SURVEY §8(d)'s byte model (8 B x |G| per
+    # pair: the reference streams every genome sketch past every sample) describes the STEP, not one kernel — the largest
+    # kernel at one sample is the bootstrap, which touches 17 counters per row — so the bytes are taken over the device
+    # time of all the step's kernels; the dominant kernel and its share are named next to it.
     peak, peak_src = measured_peak_hbm()
     dom = max(per_step, key=lambda kname: per_step[kname])
-    alg_bytes = 8.0 * db_keys + 64.0 * G * n_samples  # SURVEY §8(d): 8 B x |G| per pair (db streamed once for all samples) + 64 B per row
-    ach = alg_bytes / (per_step[dom] * 1e-3) / 1e9 if per_step[dom] else None
+    alg_bytes = 8.0 * db_keys + 64.0 * G * n_samples  # 8 B x |G| per pair (db streamed once for all samples) + 64 B per row
+    kern_ms = sum(per_step.values())
+    ach = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms else None
     out["kernels_ms_per_step"] = per_step
-    out["roofline"] = {"kernel": PAIR_KERNELS[dom], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+    out["roofline"] = {"kernel": "profile step kernels (%s); largest: %s" % (" + ".join(PAIR_KERNELS[k_] for k_ in per_step), PAIR_KERNELS[dom]),
+                       "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                        "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
-                       "kernel_ms": per_step[dom], "kernel_share_of_step": per_step[dom] / (ms / args.steps),
+                       "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / (ms / args.steps),
+                       "dominant_kernel": {"name": PAIR_KERNELS[dom], "ms": per_step[dom], "share_of_step": per_step[dom] / (ms / args.steps),
+                                           "limiter": PAIR_LIMITER.get(dom)},
                        "algorithmic_bytes_per_launch": alg_bytes,
-                       "note": "SURVEY §8(d) byte model of a genome-streaming probe loop (8 B x |G| per pair); this implementation "
-                               "probes a sorted db index with the sample keys and never streams the db, so this is an equivalent "
-                               "bandwidth that is not bounded by HBM (DESIGN.md 4.4)"}
+                       "note": "SURVEY §8(d) byte model of a genome-streaming probe loop; this implementation probes a sorted db "
+                               "index with the sample keys and never streams the db, so this is an EQUIVALENT bandwidth (DESIGN.md "
+                               "4.4); ncu --set full of the kernels: profiles/r02_contain_kernels_ncu_full_selected.csv"}
     # ---- parity: sample 0's rows against the CPU oracle on the WHOLE db (N>1: shards gathered on every rank)
     if not args.no_cpu:
         if world > 1:

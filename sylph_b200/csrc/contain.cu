@@ -378,6 +378,44 @@ k_stats(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off, cons
 // caller falls back to the CSR formulation for this pass.
 constexpr uint32_t COV_BINS = 256;
 
+// ---- thread -> (sample, key) mapping of the join kernels ---------------------------------------------------------
+// Plain form (rb == nullptr): grid (key blocks, samples), one key per thread.  With several samples that order walks
+// the db index once PER SAMPLE (the blocks of sample s+1 start when sample s is through), and the index is far larger
+// than L2: 16 samples cost 16x the DRAM traffic of one.  Tiled form: the hash space is cut into R ranges of equal
+// db-bucket count and the block index runs sample-fastest over (range, sample), so the blocks resident at any time
+// probe the SAME stretch of the index for all samples and that stretch comes from DRAM once.  rb[s * (R+1) + r] =
+// index of sample s's first key in range r (k_range_bounds); a block loops over its range's keys (~100).
+struct KeyMap { const uint32_t *rb; uint32_t R, S; };
+
+template <class F>
+__device__ __forceinline__ void for_each_key(const KeyMap km, const SampleView *__restrict__ views, F body) {
+    if (!km.rb) {
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < views[blockIdx.y].n) body((uint32_t)blockIdx.y, i);
+        return;
+    }
+    const uint32_t s = blockIdx.x % km.S, r = blockIdx.x / km.S;
+    const uint32_t *b = km.rb + (uint64_t)s * (km.R + 1) + r;
+    const uint32_t lo = b[0], hi = b[1];
+    for (uint64_t i = (uint64_t)lo + threadIdx.x; i < hi; i += blockDim.x) body(s, i);
+}
+
+__global__ void k_range_bounds(const SampleView *__restrict__ views, uint32_t S, uint32_t R, uint64_t bpr, uint64_t M, uint64_t NB,
+                               uint32_t *__restrict__ rb) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)S * (R + 1)) return;
+    const uint32_t s = (uint32_t)(t / (R + 1)), r = (uint32_t)(t % (R + 1));
+    const SampleView sv = views[s];
+    const uint64_t want = (uint64_t)r * bpr;  // first key whose bucket is >= want (buckets are monotone in the key)
+    uint64_t lo = 0, hi = sv.n;
+    if (r == R) lo = sv.n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (bucket_of(sv.hash[mid], M, NB) < want) lo = mid + 1; else hi = mid;
+    }
+    rb[t] = (uint32_t)lo;
+}
+
 // The genome ids of one k-mer's equal range [lo, e) -> hit counters / count histograms of one sample.
 // PASS2: the k-mer belongs to the pass-1 survivor with the best pass-1 ANI (lowest genome on ties,
 // tracked k-mers take part in the decision); other survivors lose it (src/contain.rs:410-430, :641-646).
@@ -433,14 +471,15 @@ __global__ void k_join_hist(const SampleView *__restrict__ views, uint64_t G,
                             const uint32_t *__restrict__ bstart, uint64_t M, uint64_t NB, uint64_t maxkey,
                             const uint8_t *__restrict__ survivor, const double *__restrict__ ani1,
                             uint8_t *__restrict__ touched, uint32_t *__restrict__ lost, uint32_t *__restrict__ chist,
-                            unsigned long long *__restrict__ ovf, uint2 *__restrict__ hits, uint64_t hits_stride) {
-    const SampleView sv = views[blockIdx.y];
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sv.n) return;
-    const uint64_t row = (uint64_t)blockIdx.y * G;
-    if (PASS2) { survivor += row; ani1 += row; lost += row; }
-    touched += row;
-    chist += row * COV_BINS;
+                            unsigned long long *__restrict__ ovf, uint2 *__restrict__ hits, uint64_t hits_stride, const KeyMap km) {
+  for_each_key(km, views, [&](const uint32_t smp, const uint64_t i) {
+    const SampleView sv = views[smp];
+    const uint64_t row = (uint64_t)smp * G;
+    const uint8_t *survivor_r = PASS2 ? survivor + row : survivor;
+    const double *ani1_r = PASS2 ? ani1 + row : ani1;
+    uint32_t *lost_r = PASS2 ? lost + row : lost;
+    uint8_t *touched_r = touched + row;
+    uint32_t *chist_r = chist + row * COV_BINS;
     const uint64_t key = sv.hash[i];
     const uint32_t c = sv.count[i];
     if (key > maxkey || c == 0) return;  // count 0: src/contain.rs:634-636
@@ -475,8 +514,9 @@ __global__ void k_join_hist(const SampleView *__restrict__ views, uint64_t G,
         e += adv;
         if (adv < 4) break;
     }
-    if (hits) hits[(uint64_t)blockIdx.y * hits_stride + i] = make_uint2(lo, e - lo);  // equal range in the db, for pass 2
-    join_range<PASS2>(gid, lo, e, c, survivor, ani1, touched, lost, chist, ovf);
+    if (hits) hits[(uint64_t)smp * hits_stride + i] = make_uint2(lo, e - lo);  // equal range in the db, for pass 2
+    join_range<PASS2>(gid, lo, e, c, survivor_r, ani1_r, touched_r, lost_r, chist_r, ovf);
+  });
 }
 
 // Pass 2 over the equal ranges recorded by pass 1: no directory / key look-ups, only the genome ids.
@@ -703,7 +743,7 @@ k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
 // between the statistics kernel and the bootstrap).  One CTA per resident slot; the (row, iteration)
 // items are handed out through a device counter, because their cost follows |genome_kmers| of the
 // row and a fixed stride leaves the CTAs that drew the large rows running alone at the end.
-__global__ void __launch_bounds__(BOOT_THREADS)
+__global__ void __launch_bounds__(BOOT_THREADS, 6)
 k_boot_iter_p(const uint32_t *__restrict__ hist_in, const unsigned long long *__restrict__ d_nboot, uint64_t boot_cap, StatParams P,
               double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
               uint32_t *__restrict__ reject_flag, uint32_t *__restrict__ work_ctr) {
@@ -915,13 +955,13 @@ static int contain_pass(syl_ctx *ctx, const syl_db *db, const StatParams &P, boo
             KernelTimer kt(ctx, pass2 ? SYL_KERNEL_JOIN2 : SYL_KERNEL_JOIN);
             if (!pass2)
                 k_join_hist<false><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->N, db->bstart, db->M, db->NB, db->maxkey,
-                                                          nullptr, nullptr, S.touched.p, nullptr, S.chist.p, d_ovf, S.hits.p, S.max_n);
+                                                          nullptr, nullptr, S.touched.p, nullptr, S.chist.p, d_ovf, S.hits.p, S.max_n, KeyMap{nullptr, 0, 0});
             else if (S.hits_valid)
                 k_join2_hits<<<jgrid, 128, 0, st>>>(S.views.p, G, db->gid, S.hits.p, S.max_n, S.survivor.p, S.ani1.p, S.touched.p,
                                                     S.lost.p, S.chist.p, d_ovf);
             else
                 k_join_hist<true><<<jgrid, 128, 0, st>>>(S.views.p, G, db->keys, db->gid, db->N, db->bstart, db->M, db->NB, db->maxkey,
-                                                         S.survivor.p, S.ani1.p, S.touched.p, S.lost.p, S.chist.p, d_ovf, nullptr, 0);
+                                                         S.survivor.p, S.ani1.p, S.touched.p, S.lost.p, S.chist.p, d_ovf, nullptr, 0, KeyMap{nullptr, 0, 0});
             if (!pass2) S.hits_valid = S.hits.p != nullptr;
             ctx->launches++;
         }
@@ -1096,15 +1136,14 @@ k_rank_rows(const uint8_t *__restrict__ tabs, uint64_t tbytes, uint32_t world, u
 // tracked k-mers both count, src/contain.rs:416-426)
 __global__ void k_local_best(const SampleView *__restrict__ views, uint64_t G, const uint32_t *__restrict__ gid,
                              const uint2 *__restrict__ hits, uint64_t hits_stride, const uint32_t *__restrict__ order_tbl,
-                             uint32_t *__restrict__ wbest) {
-    const SampleView sv = views[blockIdx.y];
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sv.n) return;
-    const uint2 h = hits[(uint64_t)blockIdx.y * hits_stride + i];
+                             uint32_t *__restrict__ wbest, const KeyMap km) {
+  for_each_key(km, views, [&](const uint32_t smp, const uint64_t i) {
+    const uint2 h = hits[(uint64_t)smp * hits_stride + i];
     uint32_t best = ORD_NONE;
-    const uint32_t *ord = order_tbl + (uint64_t)blockIdx.y * G;
+    const uint32_t *ord = order_tbl + (uint64_t)smp * G;
     for (uint32_t j = h.x; j < h.x + h.y; j++) best = min(best, ord[gid[j] >> 1]);
-    wbest[(uint64_t)blockIdx.y * hits_stride + i] = best;
+    wbest[(uint64_t)smp * hits_stride + i] = best;
+  });
 }
 
 // pass 2 over the equal ranges recorded by pass 1.  FUSED: the winner (smallest order in the range) is
@@ -1113,15 +1152,13 @@ template <bool FUSED>
 __global__ void k_join2_order(const SampleView *__restrict__ views, uint64_t G, const uint32_t *__restrict__ gid,
                               const uint2 *__restrict__ hits, uint64_t hits_stride, const uint32_t *__restrict__ order_tbl,
                               const uint32_t *__restrict__ wbest, uint8_t *__restrict__ touched, uint32_t *__restrict__ lost,
-                              uint32_t *__restrict__ chist, unsigned long long *__restrict__ ovf) {
-    const SampleView sv = views[blockIdx.y];
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sv.n) return;
-    const uint2 h = hits[(uint64_t)blockIdx.y * hits_stride + i];
+                              uint32_t *__restrict__ chist, unsigned long long *__restrict__ ovf, const KeyMap km) {
+  for_each_key(km, views, [&](const uint32_t smp, const uint64_t i) {
+    const uint2 h = hits[(uint64_t)smp * hits_stride + i];
     if (h.y == 0) return;
-    const uint64_t row = (uint64_t)blockIdx.y * G;
+    const uint64_t row = (uint64_t)smp * G;
     const uint32_t *ord = order_tbl + row;
-    const uint32_t lo = h.x, e = h.x + h.y, c = sv.count[i];
+    const uint32_t lo = h.x, e = h.x + h.y, c = views[smp].count[i];
     uint32_t winner;
     if (FUSED) {
         winner = ORD_NONE;
@@ -1133,7 +1170,7 @@ __global__ void k_join2_order(const SampleView *__restrict__ views, uint64_t G, 
             for (int q = 0; q < 4; q++) if (j + q < e) winner = min(winner, ord[gq[q] >> 1]);
         }
     } else {
-        winner = wbest[(uint64_t)blockIdx.y * hits_stride + i];
+        winner = wbest[(uint64_t)smp * hits_stride + i];
     }
     if (winner == ORD_NONE) return;  // no survivor holds this k-mer
     for (uint32_t j = lo; j < e; j += 4) {
@@ -1154,6 +1191,7 @@ __global__ void k_join2_order(const SampleView *__restrict__ views, uint64_t G, 
             else atomicAdd(ovf, 1ull);
         }
     }
+  });
 }
 
 }  // namespace syl
@@ -1177,7 +1215,9 @@ struct syl_profile_job {
     int stage = 0;           // 1 pass 1 enqueued, 2 ranked, 3 pass 2 enqueued
     syl::DevBuf<syl::SampleView> views;
     syl::DevBuf<uint8_t> touched, tab1, gat1, tab2, gat2, res_ok;
-    syl::DevBuf<uint32_t> chist, lost, order, contain1, wbest, boot_rows, hist, reject;
+    syl::DevBuf<uint32_t> chist, lost, order, contain1, wbest, boot_rows, hist, reject, range_bounds;
+    syl::KeyMap km{nullptr, 0, 0};   // tiled (range, sample) mapping of the join kernels when there are several samples
+    dim3 jgrid;
     syl::DevBuf<uint2> hits;
     syl::DevBuf<double> res_ani, res_lambda;
     syl::DevBuf<uint64_t> gn_size;
@@ -1282,11 +1322,26 @@ static int job_begin(syl_ctx *ctx, const syl_db *db, const syl_sample *const *sa
     JOB_CUDA(cudaMemsetAsync(j->hits.p, 0, HN * sizeof(uint2), st));
     JOB_CUDA(cudaMemsetAsync(j->tab1.p, 0, sizeof(ShardTable), st));
     ShardTable *t1 = reinterpret_cast<ShardTable *>(j->tab1.p);
-    const dim3 jgrid(nblk(std::max<uint64_t>(j->max_n, 1), 128), (unsigned)j->S);
+    j->jgrid = dim3(nblk(std::max<uint64_t>(j->max_n, 1), 128), (unsigned)j->S);
+    static const bool tile_env_off = getenv("SYL_JOIN_PLAIN") != nullptr;
+    if (j->S > 1 && j->max_n && db->N && !tile_env_off) {
+        // ~100 keys of the largest sample per (range, sample) block; ranges are equal numbers of db buckets
+        const uint64_t R = std::min<uint64_t>(std::max<uint64_t>(j->max_n / 100, 1), std::max<uint64_t>(db->NB, 1));
+        const uint64_t bpr = (db->NB + R - 1) / R;
+        if (R * j->S < 0x7FFFFFFFull) {
+            JOB_TRY(j->range_bounds.alloc((uint64_t)j->S * (R + 1), st));
+            KernelTimer kt(ctx, SYL_KERNEL_JOIN);
+            k_range_bounds<<<nblk((uint64_t)j->S * (R + 1), 256), 256, 0, st>>>(j->views.p, j->S, (uint32_t)R, bpr, db->M, db->NB, j->range_bounds.p);
+            ctx->launches++;
+            j->km = KeyMap{j->range_bounds.p, (uint32_t)R, j->S};
+            j->jgrid = dim3((unsigned)(R * j->S), 1);
+        }
+    }
+    const dim3 jgrid = j->jgrid;
     if (j->max_n && db->N) {
         KernelTimer kt(ctx, SYL_KERNEL_JOIN);
         k_join_hist<false><<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->keys, db->gid, db->N, db->bstart, db->M, db->NB, db->maxkey,
-                                                  nullptr, nullptr, j->touched.p, nullptr, j->chist.p, &t1->ovf, j->hits.p, j->max_n);
+                                                  nullptr, nullptr, j->touched.p, nullptr, j->chist.p, &t1->ovf, j->hits.p, j->max_n, j->km);
         ctx->launches++;
     }
     StatParams P1 = j->P;
@@ -1337,9 +1392,8 @@ static int job_rank(syl_profile_job *j) {
     k_rank_rows<<<nblk((uint64_t)j->world * j->R, 256), 256, 0, st>>>(tabs, j->tbytes, j->world, (uint32_t)j->R, j->rank, j->G, db->genome_base, j->order.p);
     ctx->launches++;
     if (j->world > 1) {
-        const dim3 jgrid(nblk(std::max<uint64_t>(j->max_n, 1), 128), (unsigned)j->S);
         KernelTimer kt(ctx, SYL_KERNEL_JOIN2);
-        k_local_best<<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->gid, j->hits.p, j->max_n, j->order.p, j->wbest.p);
+        k_local_best<<<j->jgrid, 128, 0, st>>>(j->views.p, j->G, db->gid, j->hits.p, j->max_n, j->order.p, j->wbest.p, j->km);
         ctx->launches++;
     }
     SYL_CUDA(cudaGetLastError());
@@ -1358,15 +1412,15 @@ static int job_pass2(syl_profile_job *j) {
     SYL_CUDA(cudaMemsetAsync(j->lost.p, 0, NP * 4, st));
     SYL_CUDA(cudaMemsetAsync(j->chist.p, 0, NP * COV_BINS * 4, st));
     SYL_CUDA(cudaMemsetAsync(j->tab2.p, 0, sizeof(ShardTable), st));
-    const dim3 jgrid(nblk(std::max<uint64_t>(j->max_n, 1), 128), (unsigned)j->S);
+    const dim3 jgrid = j->jgrid;
     if (j->max_n && db->N) {
         KernelTimer kt(ctx, SYL_KERNEL_JOIN2);
         if (j->world > 1)
             k_join2_order<false><<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->gid, j->hits.p, j->max_n, j->order.p, j->wbest.p, j->touched.p,
-                                                        j->lost.p, j->chist.p, &t2->ovf);
+                                                        j->lost.p, j->chist.p, &t2->ovf, j->km);
         else
             k_join2_order<true><<<jgrid, 128, 0, st>>>(j->views.p, j->G, db->gid, j->hits.p, j->max_n, j->order.p, nullptr, j->touched.p,
-                                                       j->lost.p, j->chist.p, &t2->ovf);
+                                                       j->lost.p, j->chist.p, &t2->ovf, j->km);
         ctx->launches++;
     }
     StatExtra X;

@@ -136,6 +136,33 @@ def test_params_variants_and_multi_sample(ctx):
             compare(sub, oracle_rows(d, s.download(), False, **kw), False)
 
 
+@pytest.mark.parametrize("pseudotax", [False, True])
+def test_several_samples_of_unequal_size_one_call(ctx, pseudotax):
+    """Several samples in one call take the tiled (hash range, sample) mapping of the join kernels: samples of
+    very different sizes (one of them empty, one a handful of reads) == the oracle, sample by sample."""
+    from sylph_b200 import synth
+    from sylph_b200.api import contain_params
+    g, s_big = synth_db_and_sample(ctx, 200, 120000, 150000, 120, c=20)
+    _, s_mid = synth_db_and_sample(ctx, 1, 120000, 30000, 40, c=20, read_seed=0x5EED0011)
+    rb, ro = synth.reads(50, n_comm=5, genome_len=120000, seed=0x5EED0012)
+    s_tiny = ctx.sketch_sequences(rb.numpy(), ro.numpy().astype(np.uint64), c=20)
+    s_empty = ctx.sketch_sequences(np.zeros(0, np.uint8), np.zeros(1, np.uint64), c=20)
+    d = g.download()
+    db = ctx.build_db(g)
+    samples = [s_mid, s_empty, s_big, s_tiny, s_mid]
+    P = contain_params(pseudotax=pseudotax)
+    rows = ctx.profile(db, samples, P) if pseudotax else ctx.query(db, samples, P)
+    n_rows = 0
+    for si, smp in enumerate(samples):
+        sub = rows[rows["sample"] == si]
+        if not pseudotax:
+            sub = sort_query_rows(sub)
+        exp = oracle_rows(d, smp.download(), pseudotax)
+        compare(sub, exp, pseudotax)
+        n_rows += len(exp)
+    assert n_rows == len(rows) and n_rows > 40
+
+
 def test_uploaded_sketches_and_zero_counts(ctx):
     """Sketches that come from files: unsorted sample pairs, a zero count (skipped, src/contain.rs:634)."""
     rng = np.random.default_rng(4)
