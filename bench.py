@@ -394,15 +394,17 @@ def bench_sketch(args, ctx, rank, world, local):
     ctx.enable_timing(False)
     e2e_value = total_bases * e2e_steps / (wall_ms * 1e-3)
     from sylph_b200 import _lib
-    ingest = os.environ.get("SYL_HOST_INGEST", "packed2")
-    if ingest == "ascii":
-        h2d = int(n_bases + 8 * (n_reads + 1))
-        what = "ASCII bases + u64 record offsets copied as they are"
-    else:  # 2-bit words + u32 chunk-relative offsets (one extra offset per 32 Mbase chunk)
-        h2d = int((n_bases + 15) // 16 * 4 + 4 * (n_reads + 1 + n_bases // (32 << 20) + 1))
-        what = ("host ASCII -> 2-bit words by %d packer threads into pinned staging (inside the timed region), "
-                "u32 chunk-relative record offsets" % _lib.lib().syl_pack_threads())
-    e2e = {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d,
+    # bytes as the library copied them in the last timed step (rank 0), and how the chunks crossed the link
+    h2d, ch_packed, ch_ascii = ctx.ingest_stats()
+    if ch_packed == 0:
+        what = "ASCII bases + u64 record offsets copied as they are (%d chunks)" % ch_ascii
+        if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 4 and "SYL_HOST_INGEST" not in os.environ:
+            what += "; the library does not pack when more than 4 ranks share a host (its memory system, not PCIe, is then the narrow resource)"
+    else:
+        what = ("host ASCII -> 2-bit words by %d packer threads into pinned staging (inside the timed region), u32 chunk-relative "
+                "record offsets: %d chunks packed; %d chunks shipped as ASCII because the link was idle while the packers lagged"
+                % (_lib.lib().syl_pack_threads(), ch_packed, ch_ascii))
+    e2e = {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(12 * e2e_state["n"]), "steps": e2e_steps, "ms_per_step": wall_ms / e2e_steps,
            "timing": "wall clock bracketed by device syncs, max over ranks", "per_step_ms": e2e_state["t"],
            "seed_kernel_ms_per_step": e2e_seed_ms, "ingest": what,

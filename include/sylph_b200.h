@@ -154,6 +154,9 @@ int syl_sketch_read_pairs(syl_ctx *ctx, int mem, const uint8_t *bases1, uint64_t
 int syl_pack2(const uint8_t *bases, uint64_t n_bases, uint32_t *words, int n_threads);
 /* Worker threads the host-memory path of syl_sketch_reads packs with (for bench.py's e2e record). */
 int syl_pack_threads(void);
+/* What the last syl_sketch_reads(SYL_MEM_HOST, ASCII) call of this ctx moved: host-to-device bytes (bases + record
+ * offsets, as copied) and how many of its chunks crossed the link as 2-bit words / as ASCII. */
+int syl_ctx_ingest_stats(const syl_ctx *ctx, uint64_t *h2d_bytes, uint64_t *chunks_packed, uint64_t *chunks_ascii);
 /* Wrap an existing sketch (e.g. a deserialised .sylsp).  Pairs need not be sorted; hashes must
  * be distinct. */
 int syl_sample_upload(syl_ctx *ctx, int mem, const uint64_t *hash, const uint32_t *count,

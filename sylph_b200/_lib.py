@@ -60,6 +60,7 @@ SIGNATURES = {
     "syl_sketch_read_pairs": (_i, [_vp, _i, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _i, _u64, _i, _i, _pp]),
     "syl_pack2": (_i, [_vp, _u64, _vp, _i]),
     "syl_pack_threads": (_i, []),
+    "syl_ctx_ingest_stats": (_i, [_vp, _vp, _vp, _vp]),
     "syl_sample_upload": (_i, [_vp, _i, _vp, _vp, _u64, _i, _u64, _pp]),
     "syl_sample_size": (_u64, [_vp]),
     "syl_sample_mean_read_length": (_d, [_vp]),

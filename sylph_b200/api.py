@@ -94,6 +94,12 @@ class Context:
 
     KERNELS = {"seed": 0, "group_dedup": 1, "join": 2, "join2": 3, "stats": 4, "boot": 5, "genome_post": 6, "pack": 7}
 
+    def ingest_stats(self):
+        """-> (h2d_bytes, chunks_packed, chunks_ascii) of the last host-memory sketch_sequences call."""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _lib.check(_lib.lib().syl_ctx_ingest_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def kernel_time(self, which, reset=True):
         """-> (total_ms, launches) of kernel class `which` (name in Context.KERNELS) since the last reset."""
         ms, n = C.c_double(0), C.c_uint64(0)

@@ -62,6 +62,7 @@ struct syl_ctx {
     double kernel_ms[SYL_KERNEL_COUNT] = {};
     uint64_t kernel_launches[SYL_KERNEL_COUNT] = {};
     uint64_t seed_bases = 0;
+    uint64_t ingest_h2d_bytes = 0, ingest_chunks_packed = 0, ingest_chunks_ascii = 0;  // last host-memory read sketch
     void *ingest = nullptr;  // HostIngest (sample.cu): packer pool + pinned staging ring of the host-memory read path
     // double-buffered H2D staging for host-memory ASCII inputs (SYL_HOST_INGEST=ascii; lazily allocated, reused across calls)
     cudaStream_t copy_stream = nullptr;

@@ -1175,6 +1175,7 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
                 cudaMemcpyAsync(I.d_off32[slot], I.h_off[slot], no * 4, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
                 rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
             }
+            ctx->ingest_h2d_bytes += nw * 4 + no * 4;
             cudaEventRecord(I.ev_copied[slot], cs);
             cudaStreamWaitEvent(st, I.ev_copied[slot], 0);
             k_off32_to_64<<<nblk(no, 256), 256, 0, st>>>(I.d_off32[slot], no, I.d_off64[slot]);
@@ -1202,6 +1203,7 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
                 cudaMemcpyAsync(I.d_aoff[slot], rec_off + c.r0, (nr + 1) * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
                 rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
             }
+            ctx->ingest_h2d_bytes += c.nb + (nr + 1) * 8;
             cudaEventRecord(I.ev_a_copied[slot], cs);
             cudaStreamWaitEvent(st, I.ev_a_copied[slot], 0);
             rc = b.add(I.d_asc[slot], nullptr, c.nb, I.d_aoff[slot], c.base, nr, c.r0);
@@ -1221,6 +1223,8 @@ static int feed_host_packed(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases
     }
     I.pool->open_gate((int64_t)1 << 60);  // all remaining items (skipped chunks included) drain
     I.pool->finish();
+    ctx->ingest_chunks_ascii += n_ascii;
+    ctx->ingest_chunks_packed += n_packed;
     static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
     if (dbg) fprintf(stderr, "[host ingest] %zu chunks: %llu shipped as ASCII, %zu packed by %d threads\n", chunks.size(),
                      (unsigned long long)n_ascii, chunks.size() - (size_t)n_ascii, I.pool->threads());
@@ -1279,6 +1283,8 @@ static int feed_host_ascii(syl_ctx *ctx, SampleBuilder &b, const uint8_t *bases,
                 cudaMemcpyAsync(ctx->stage_o[slot], rec_off + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) {
                 rc = SYL_ERR_CUDA; set_error("H2D copy failed"); break;
             }
+            ctx->ingest_h2d_bytes += nb + (nr + 1) * 8;
+            ctx->ingest_chunks_ascii++;
             cudaEventRecord(ctx->ev_copied[slot], cs);
             next = {nb, nr, base, slot, true};
             r0 = r1;
@@ -1306,8 +1312,15 @@ static int sketch_reads_impl(syl_ctx *ctx, int mem, const uint8_t *bases, const 
     SYL_CUDA(cudaSetDevice(ctx->device));
     syl::tl_ctx = ctx;
     cudaStream_t st = ctx->stream;
-    const char *hi_env = getenv("SYL_HOST_INGEST");  // read per call: the tests switch it at run time
-    const bool host_ascii = hi_env && std::string(hi_env) == "ascii";
+    // Host ASCII input: packed by the worker pool (fewer PCIe bytes) or shipped as it is.  Packing costs host memory
+    // traffic (1.5 B per base: the packers read the ASCII, write the words, the copy engine reads them; ASCII costs 1 B
+    // per base), so it pays while PCIe is the narrow resource — 1 to 4 processes per host — and loses once the ranks of
+    // a host saturate its memory system instead (measured with 8 ranks on one host: 20.2 ms per 1 Gbp step shipping
+    // ASCII, 32.7 ms packing; with 1 and 2 ranks packing wins, 10.2 vs 19.9 and 16.4 vs 19.9 ms).
+    // SYL_HOST_INGEST = ascii | packed | packed-only overrides (read per call: the tests switch it at run time).
+    const char *hi_env = getenv("SYL_HOST_INGEST");
+    static const int local_ranks = []() { const char *e = getenv("LOCAL_WORLD_SIZE"); return e ? atoi(e) : 1; }();
+    const bool host_ascii = hi_env ? std::string(hi_env) == "ascii" : local_ranks > 4;
     static const bool dbg = getenv("SYL_DEBUG_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     uint64_t cap_override = 0;
@@ -1315,6 +1328,7 @@ static int sketch_reads_impl(syl_ctx *ctx, int mem, const uint8_t *bases, const 
         SampleBuilder b{ctx, k, c, no_dedup, sem};
         b.expect_bases = n_bases;
         b.expect_reads = n_reads;
+        if (mem == SYL_MEM_HOST) ctx->ingest_h2d_bytes = ctx->ingest_chunks_packed = ctx->ingest_chunks_ascii = 0;
         SYL_TRY(b.begin(cap_override));
         const double t0 = now();
         int rc = SYL_OK;
@@ -1328,6 +1342,7 @@ static int sketch_reads_impl(syl_ctx *ctx, int mem, const uint8_t *bases, const 
             SYL_TRY(ho.alloc(n_reads + 1, st));
             if (nw) SYL_CUDA(cudaMemcpyAsync(hp.p, packed, nw * 4, cudaMemcpyHostToDevice, st));
             SYL_CUDA(cudaMemcpyAsync(ho.p, rec_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+            ctx->ingest_h2d_bytes += nw * 4 + (n_reads + 1) * 8;
             rc = b.add(nullptr, hp.p, n_bases, ho.p, 0, n_reads, 0);
         } else if (n_reads && n_bases) {
             rc = host_ascii ? feed_host_ascii(ctx, b, bases, rec_off, n_reads) : feed_host_packed(ctx, b, bases, rec_off, n_reads);
@@ -1418,6 +1433,14 @@ int syl_sketch_read_pairs(syl_ctx *ctx, int mem, const uint8_t *bases1, uint64_t
 }
 
 int syl_pack_threads(void) { return default_pack_threads(); }
+
+int syl_ctx_ingest_stats(const syl_ctx *ctx, uint64_t *h2d_bytes, uint64_t *chunks_packed, uint64_t *chunks_ascii) {
+    if (!ctx) { set_error("NULL argument"); return SYL_ERR_ARG; }
+    if (h2d_bytes) *h2d_bytes = ctx->ingest_h2d_bytes;
+    if (chunks_packed) *chunks_packed = ctx->ingest_chunks_packed;
+    if (chunks_ascii) *chunks_ascii = ctx->ingest_chunks_ascii;
+    return SYL_OK;
+}
 
 int syl_pack2(const uint8_t *bases, uint64_t n_bases, uint32_t *words, int n_threads) {
     if ((!bases && n_bases) || (!words && n_bases)) { set_error("NULL argument"); return SYL_ERR_ARG; }
