@@ -68,7 +68,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sketch", choices=["sketch", "profile", "genomes"])
-    ap.add_argument("--batch-genomes", type=int, default=125, help="genomes (4 Mbp each) per syl_sketch_genomes call of --workload genomes")
+    ap.add_argument("--batch-genomes", type=int, default=250, help="genomes (4 Mbp each) per syl_sketch_genomes call of --workload genomes")
     ap.add_argument("--reads", type=int, default=6_666_667, help="reads per GPU (150 bp each)")
     ap.add_argument("--genomes", type=int, default=None,
                     help="genomes per GPU for the containment metric (default 10000; 12500 for the 16-sample config-4 shape)")

@@ -646,7 +646,7 @@ __device__ __forceinline__ uint64_t lemire_threshold(uint64_t c, uint64_t n) {
 // majority) cost nothing beyond the RNG.
 __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32_t *__restrict__ hist_in, const StatParams &P,
                                          double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
-                                         uint32_t *__restrict__ reject_flag, uint32_t *Hb, uint64_t *cum, uint64_t *thr) {
+                                         uint32_t *__restrict__ reject_flag, uint32_t *Hb, uint64_t *cum, uint64_t *thr, uint64_t *nthr) {
     const uint32_t *H = hist_in + (uint64_t)row * 17;
     if (threadIdx.x < 17) Hb[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
@@ -654,7 +654,11 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
         for (int v = 0; v < 17; v++) { acc += H[v]; cum[v] = acc; }  // cum[v] = #values <= v
     }
     __syncthreads();
-    if (threadIdx.x < 16) thr[threadIdx.x] = lemire_threshold(cum[threadIdx.x], cum[16]);
+    if (threadIdx.x < 16) {
+        const uint64_t t = lemire_threshold(cum[threadIdx.x], cum[16]);
+        thr[threadIdx.x] = t;
+        nthr[threadIdx.x] = 0ull - t;
+    }
     __syncthreads();
     const uint64_t n = cum[16];
     const uint32_t n32 = (uint32_t)n;  // |full| = |genome_kmers| < 2^32
@@ -662,9 +666,12 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
     // common class boundaries are compared on the 64-bit draw itself, so the two 32x32->64 multiplies
     // of the index are only paid by the rare draws that need it (values >= 4, rejection candidates).
     const uint64_t t3 = thr[3], nt0 = 0ull - thr[0], nt1 = 0ull - thr[1], nt2 = 0ull - thr[2], nt3 = 0ull - t3;
-    uint32_t ge0 = 0, ge1 = 0, ge2 = 0, ge3 = 0;
-    const bool more_than_3 = cum[3] < n;
-    uint32_t vmax = 4;  // largest value present (cum[vmax] = n): no draw lies at or above boundary vmax
+    uint32_t ge[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ge[v] = draws with a value > v (x >= thr[v])
+    const bool more_than_3 = cum[3] < n, more_than_7 = cum[7] < n;
+    // no value above 3: the branch below is never wanted; an all-ones boundary does that without a second test in the
+    // loop (a draw of exactly 2^64-1 would still enter, harmlessly: every count it touches is zeroed after the loop)
+    const uint64_t t3_eff = more_than_3 ? t3 : ~0ull;
+    uint32_t vmax = 8;  // largest value present (cum[vmax] = n): no draw lies at or above boundary vmax
     while (vmax < 16 && cum[vmax] < n) vmax++;
     // draw number d = it*n + j + 1; WyRand state s(d) = 7 + d*C0, advanced by BOOT_THREADS*C0 per trip
     uint64_t s = 7ull + ((uint64_t)it * n + threadIdx.x + 1) * 0x2d358dccaa6c78a5ull;
@@ -672,46 +679,52 @@ __device__ __forceinline__ void boot_one(uint32_t row, uint32_t it, const uint32
     for (uint32_t j = threadIdx.x; j < n32; j += BOOT_THREADS, s += s_step) {
         const uint64_t x = mum_xor(s, s ^ 0x8bb84b93962eacc9ull);
         // fastrand gen_mod_u64 redraws when lo = (x*n) mod 2^64 < (2^64 - n) mod n.  lo < n < 2^32 needs
-        // the low word of x_lo*n to be < n (probability n / 2^32): only then form lo exactly.
+        // the low word of x_lo*n to be < n (probability n / 2^32): only then is lo formed.  The empty volatile asm
+        // pins that to the branch (otherwise the full product is hoisted into the loop: 9 instructions per draw, not 3).
         if ((uint32_t)x * n32 < n32) {
-            const uint64_t lo = x * n;
+            uint64_t xr = x;
+            asm volatile("" : "+l"(xr));
+            const uint64_t lo = xr * n;
             if (lo < n && lo < (0ull - n) % n) atomicExch(reject_flag + row, 1u);  // the reference would redraw
         }
         // full_covs[hi] = v with cum[v-1] <= hi < cum[v].  Branch-free for the common values (0: most draws;
         // 1, 2, 3: counted in registers) — lanes of a warp draw different values, a branch per value would
         // serialise them (measured: 60 instructions per draw with the branches, 23 of 32 lanes active).
-        count_ge(ge0, x, nt0);
-        count_ge(ge1, x, nt1);
-        count_ge(ge2, x, nt2);
-        count_ge(ge3, x, nt3);
-        if (more_than_3 && x >= t3) {
-            // a value >= 4 (a few percent of the draws of a row with median 2, but then most WARPS have such a lane):
-            // walk the remaining class boundaries upwards — the mass sits right above 4 — again on the raw draw
-            uint32_t v = 4;
-            while (v < vmax && x >= thr[v]) v++;
-            atomicAdd(&Hb[v], 1u);
+        count_ge(ge[0], x, nt0);
+        count_ge(ge[1], x, nt1);
+        count_ge(ge[2], x, nt2);
+        count_ge(ge[3], x, nt3);
+        if (x >= t3_eff) {
+            // a value >= 4: a few percent of the draws of a row with median 2, but then a third of the WARPS have
+            // such a lane.  Values 4..7 are counted like 0..3 (negated boundaries from shared memory); beyond 7
+            // the remaining boundaries are walked upwards (rare).
+            count_ge(ge[4], x, nthr[4]);
+            count_ge(ge[5], x, nthr[5]);
+            count_ge(ge[6], x, nthr[6]);
+            if (more_than_7 && x >= thr[7]) {
+                ge[7]++;
+                uint32_t v = 8;
+                while (v < vmax && x >= thr[v]) v++;
+                atomicAdd(&Hb[v], 1u);
+            }
         }
     }
     // a boundary of 0 has every draw at or above it (the carry form needs t >= 1); a boundary equal to n
     // has none (its threshold would be 2^64)
     const uint32_t trips = threadIdx.x < n32 ? (n32 - threadIdx.x + BOOT_THREADS - 1) / BOOT_THREADS : 0u;
-    if (cum[0] == 0) ge0 = trips;
-    if (cum[1] == 0) ge1 = trips;
-    if (cum[2] == 0) ge2 = trips;
-    if (cum[3] == 0) ge3 = trips;
-    if (cum[0] >= n) ge0 = 0;
-    if (cum[1] >= n) ge1 = 0;
-    if (cum[2] >= n) ge2 = 0;
-    if (cum[3] >= n) ge3 = 0;
-    uint32_t n1 = ge0 - ge1, n2 = ge1 - ge2, n3 = ge2 - ge3;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        n1 += __shfl_xor_sync(0xffffffffu, n1, d); n2 += __shfl_xor_sync(0xffffffffu, n2, d); n3 += __shfl_xor_sync(0xffffffffu, n3, d);
+    for (int v = 0; v < 8; v++) {
+        if (cum[v] == 0) ge[v] = trips;
+        if (cum[v] >= n) ge[v] = 0;
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (n1) atomicAdd(&Hb[1], n1);
-        if (n2) atomicAdd(&Hb[2], n2);
-        if (n3) atomicAdd(&Hb[3], n3);
+    // values 1..7 of this thread: ge[v-1] - ge[v]; warp sums go to the shared histogram
+#pragma unroll
+    for (int v = 1; v <= 7; v++) {
+        uint32_t c = ge[v - 1] - ge[v];
+        if (v >= 4 && !more_than_3) c = 0;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&Hb[v], c);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -735,21 +748,21 @@ k_boot_iter(const uint32_t *__restrict__ hist_in, StatParams P,
             uint32_t *__restrict__ reject_flag) {
     __shared__ uint32_t Hb[17];
     __shared__ uint64_t cum[17];
-    __shared__ uint64_t thr[16];
-    boot_one(blockIdx.y, blockIdx.x, hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr);
+    __shared__ uint64_t thr[16], nthr[16];
+    boot_one(blockIdx.y, blockIdx.x, hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr, nthr);
 }
 
 // persistent form: the number of bootstrapped rows is read from device memory (no host round trip
 // between the statistics kernel and the bootstrap).  One CTA per resident slot; the (row, iteration)
 // items are handed out through a device counter, because their cost follows |genome_kmers| of the
 // row and a fixed stride leaves the CTAs that drew the large rows running alone at the end.
-__global__ void __launch_bounds__(BOOT_THREADS, 6)
+__global__ void __launch_bounds__(BOOT_THREADS)  // forcing 6 CTAs/SM (40 registers) measured 9 % slower
 k_boot_iter_p(const uint32_t *__restrict__ hist_in, const unsigned long long *__restrict__ d_nboot, uint64_t boot_cap, StatParams P,
               double *__restrict__ res_ani, double *__restrict__ res_lambda, uint8_t *__restrict__ res_ok,
               uint32_t *__restrict__ reject_flag, uint32_t *__restrict__ work_ctr) {
     __shared__ uint32_t Hb[17];
     __shared__ uint64_t cum[17];
-    __shared__ uint64_t thr[16];
+    __shared__ uint64_t thr[16], nthr[16];
     __shared__ uint32_t s_item;
     const uint64_t nb = *d_nboot < boot_cap ? *d_nboot : boot_cap;
     for (;;) {
@@ -757,7 +770,7 @@ k_boot_iter_p(const uint32_t *__restrict__ hist_in, const unsigned long long *__
         __syncthreads();
         const uint64_t item = s_item;
         if (item >= nb * BOOT_ITERS) break;
-        boot_one((uint32_t)(item / BOOT_ITERS), (uint32_t)(item % BOOT_ITERS), hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr);
+        boot_one((uint32_t)(item / BOOT_ITERS), (uint32_t)(item % BOOT_ITERS), hist_in, P, res_ani, res_lambda, res_ok, reject_flag, Hb, cum, thr, nthr);
         __syncthreads();  // Hb / cum / s_item are rewritten by the next item
     }
 }
