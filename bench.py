@@ -529,7 +529,7 @@ PAIR_KERNELS = {"join": "k_join_hist<pass 1> (+ k_range_bounds)", "join2": "k_jo
 PAIR_LIMITER = {"join": "DRAM: random sectors of the db index (ncu: 0.32 GB per sample at 4.9 TB/s)",
                 "join2": "DRAM / latency: genome ids of the recorded equal ranges",
                 "stats": "latency (one warp per touched pair)",
-                "boot": "integer issue: ~42 instructions per 32 bootstrap draws, issue slots 69 % busy, no DRAM traffic"}
+                "boot": "integer issue: 39 instructions per 32 bootstrap draws on the main path (11 of them the 128-bit multiply), ~50 all-in; issue slots ~70 % busy, no DRAM traffic"}
 
 
 def bench_pairs(args, ctx, rank, world, local, reads):
