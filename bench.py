@@ -82,57 +82,96 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons of THIS rank's GPU during the timed region (B200_PROFILING.md's clocks line).
+    In-process NVML from a background thread (20 samples/s: two driver calls of a few microseconds each) — a polling
+    `nvidia-smi -lms` process that watches all N GPUs takes driver locks on every one of them per sample, and a
+    sample that lands inside a 40 ms timed region costs the slowest rank milliseconds (seen as 1.9 vs 2.4 ms per
+    step at N = 8).  Falls back to nvidia-smi when NVML cannot be loaded."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        """index: one GPU index, a list of them (one nvidia-smi process samples them all; the median /
-        union is reported), or None = no sampling in this process."""
-        self.rows, self.proc = [], None
-        self.index = None if index is None else ",".join(str(i) for i in (index if isinstance(index, (list, tuple)) else [index]))
+        """index: the GPU index of this process (None = no sampling)."""
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag, self.how = index, [], None, None, False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id torch reports
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+            dom = getattr(torch.cuda.get_device_properties(self.index), "pci_domain_id", 0)
+            dev = torch.cuda.get_device_properties(self.index).pci_device_id
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(self.index))
+        return pynvml, h
 
     def start(self):
         if self.index is None:
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + self.Q,
+            self.nvml, self.h = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.how = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi -lms 100"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.rows.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)), int(reasons(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                mask = sum(bit for (name, bit), v in zip(self.BITS, r[2:6]) if v.lower().startswith("active"))
+                self.rows.append((float(r[0]), mask))
+                self.mx = float(r[1])
+            except Exception:
+                pass
 
     def stop(self):
         if self.index is None:
             return {}
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+        elif self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.proc.wait(timeout=2)
             except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                self.proc.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[1]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": getattr(self, "mx", None),
+                "reasons": sorted(name for name, bit in self.BITS if mask & bit), "samples": len(sm), "sampler": self.how}
 
 
 def measured_peak_hbm():
@@ -307,8 +346,8 @@ def bench_sketch(args, ctx, rank, world, local):
     # clocks are sampled from before the warm-up to the end of the timed region: nvidia-smi needs ~100 ms to
     # start and its first query can stall the GPU, so neither may fall inside the (tens of ms) timed region;
     # the warm-up keeps the same load running for >= 0.5 s so that the samples are taken under load
-    # N > 1: rank 0's single nvidia-smi process samples all N GPUs (N polling processes perturb the launch path)
-    clocks = ClockSampler(local if world == 1 else (list(range(world)) if rank == 0 else None))
+    # every rank samples its own GPU (in-process NVML); rank 0 reports the slowest GPU and the union of the reasons
+    clocks = ClockSampler(local)
     clocks.start()
     # ... and until the device has settled: a freshly started process on an idle GPU shows sporadic
     # 30-500 ms stalls in its first seconds (clock ramp / driver housekeeping, also seen with no sampler);
@@ -332,6 +371,15 @@ def bench_sketch(args, ctx, rank, world, local):
     l0 = ctx.launches
     ms, _ = timed(step_resident, args.steps, world)
     clk = clocks.stop()
+    if world > 1:
+        import torch.distributed as dist
+        allc = [None] * world
+        dist.all_gather_object(allc, clk)
+        ok = [c for c in allc if c and c.get("sm_mhz") is not None]
+        if ok:
+            clk = {"sm_mhz": min(c["sm_mhz"] for c in ok), "sm_max_mhz": max(c["sm_max_mhz"] or 0 for c in ok),
+                   "reasons": sorted(set(sum((c["reasons"] for c in ok), []))), "samples": sum(c["samples"] for c in ok),
+                   "sampler": ok[0].get("sampler"), "gpus_sampled": len(ok)}
     clk["warmup_steps_run"] = n_w
     launches = ctx.launches - l0
     kms, klaunch, kbases = ctx.seed_kernel_time(reset=True)
