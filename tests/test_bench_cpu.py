@@ -44,14 +44,14 @@ def test_both_arms_share_the_config_object():
     assert bench.profile_config(A, 1)["samples"] == 1 and bench.profile_config(A, 8)["samples"] == 16
 
 
-def test_clock_sampler_degrades_without_nvidia_smi():
+def test_clock_sampler_degrades_without_a_gpu():
     sys.path.insert(0, REPO)
     import bench
-    c = bench.ClockSampler([0, 1])
-    assert c.index == "0,1"
+    c = bench.ClockSampler(0)   # no NVML device and no nvidia-smi in this container: both fallbacks are taken
     c.start()
     out = c.stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert out["sm_mhz"] is None or out["sm_mhz"] > 0
     off = bench.ClockSampler(None)
     off.start()
     assert off.stop() == {}
