@@ -414,6 +414,7 @@ static int cmd_fastx_stats(const Args &a) {
 
 int main(int argc, char **argv) {
     Args a = parse(argc, argv);
+    host::inflate_threads() = std::max(1, a.threads);  // BGZF members of one file are inflated by this many threads
     if (a.cmd == "fastx-stats") return cmd_fastx_stats(a);
     syl_ctx *ctx = nullptr;
     check(syl_ctx_create(a.device, nullptr, &ctx), "syl_ctx_create");

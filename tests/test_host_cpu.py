@@ -97,6 +97,60 @@ def test_fastx_parser_matches_needletail_semantics(tmp_path):
     assert read_fastx(str(fa))[0] == (b"c1 first contig", b"ACGTNNacgtTTTT") and read_fastx(str(fa))[1] == (b"c2", b"")
 
 
+def _bgzf(data, block=40000):
+    """bgzip's container: gzip members of <= 64 KiB, each with its compressed size in a 'BC' extra field, + the EOF block."""
+    import zlib
+    out = bytearray()
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + [b""]
+    for ch in chunks:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(ch) + co.flush()
+        bsize = len(body) + 25   # 12 header + 6 extra + body + 8 trailer - 1
+        out += struct.pack("<BBBBIBBH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6) + b"BC" + struct.pack("<HH", 2, bsize)
+        out += body + struct.pack("<II", zlib.crc32(ch) & 0xFFFFFFFF, len(ch))
+    return bytes(out)
+
+
+def test_bgzf_members_inflated_in_parallel_give_the_same_records(tmp_path):
+    """A bgzip-compressed FASTQ goes through the block-parallel inflater (any -t > 1); plain gzip, the uncompressed
+    file and -t 1 (zlib's gzread on the same BGZF bytes) must all give the same records.  A damaged block makes the
+    file invalid instead of silently shortening it."""
+    import gzip
+    exe = os.path.join(REPO, "host", "sylph-b200")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.check_call(["make", "-C", os.path.join(REPO, "host"), "-s"], env=env)
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(6000):
+        L = int(rng.integers(0, 300))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=L))
+        recs.append(b"@r%d some description\n" % i + seq + b"\n+\n" + b"I" * L + b"\n")
+    data = b"".join(recs)
+    assert len(data) > 1_000_000            # dozens of BGZF blocks, records straddle block borders
+    plain, gz, bg = tmp_path / "r.fq", tmp_path / "r.fq.gz", tmp_path / "r.bgzf.fq.gz"
+    plain.write_bytes(data)
+    with gzip.open(gz, "wb") as f:
+        f.write(data)
+    bg.write_bytes(_bgzf(data))
+    assert gzip.decompress(bg.read_bytes()) == data   # the container is valid multi-member gzip
+
+    def stats(path, t):
+        out = subprocess.run([exe, "fastx-stats", "-t", str(t), str(path)], stdout=subprocess.PIPE, text=True, check=True).stdout
+        return out.strip().split("\t")[1:]
+
+    want = stats(plain, 1)
+    assert int(want[0]) == 6000
+    for t in (1, 2, 8):
+        assert stats(bg, t) == want and stats(gz, t) == want, t
+    bad = bytearray(bg.read_bytes())
+    bad[len(bad) // 2] ^= 0x55
+    (tmp_path / "bad.fq.gz").write_bytes(bytes(bad))
+    r = subprocess.run([exe, "fastx-stats", "-t", "4", str(tmp_path / "bad.fq.gz")], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("INVALID")
+
+
 def test_pack_pool_scheduling_never_deadlocks(tmp_path):
     """The worker pool behind the host-memory read path (gate on the pinned staging ring, chunks taken over by the
     caller from the back, forced alternation): a scheduler stress test without a GPU — a host-side deadlock would
