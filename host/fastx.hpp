@@ -197,7 +197,50 @@ class LineReader {
             pos_ = len_;
         }
     }
+    // first byte of the next line without consuming it; -1 at EOF
+    int peek() {
+        if (pos_ == len_ && !refill()) return -1;
+        return (unsigned char)buf_[pos_];
+    }
+    // consume the next line, appending its bytes (without the terminator) to dst: no intermediate string.  false at EOF
+    bool append_line(std::vector<uint8_t> &dst) {
+        bool got = false;
+        for (;;) {
+            if (pos_ == len_ && !refill()) break;
+            got = true;
+            const char *b = buf_ + pos_;
+            const char *nl = (const char *)memchr(b, '\n', len_ - pos_);
+            const size_t n = nl ? (size_t)(nl - b) : len_ - pos_;
+            dst.insert(dst.end(), (const uint8_t *)b, (const uint8_t *)b + n);
+            pos_ += n + (nl ? 1 : 0);
+            if (nl) { if (n_line_ + n > 0 && !dst.empty() && dst.back() == '\r') dst.pop_back(); n_line_ = 0; return true; }
+            n_line_ += n;
+        }
+        if (got && n_line_ > 0 && !dst.empty() && dst.back() == '\r') dst.pop_back();
+        n_line_ = 0;
+        return got;
+    }
+    // consume the next line without keeping it; false at EOF
+    bool skip_line() {
+        bool got = false;
+        for (;;) {
+            if (pos_ == len_ && !refill()) return got;
+            got = true;
+            const char *b = buf_ + pos_;
+            const char *nl = (const char *)memchr(b, '\n', len_ - pos_);
+            if (nl) { pos_ += (size_t)(nl - b) + 1; return true; }
+            pos_ = len_;
+        }
+    }
   private:
+    bool refill() {
+        const int n = bgzf_ ? bgzf_->read(buf_, sizeof buf_) : gzread(f_, buf_, sizeof buf_);
+        if (n <= 0) { if (n < 0) err_ = true; return false; }
+        len_ = (size_t)n;
+        pos_ = 0;
+        return true;
+    }
+    size_t n_line_ = 0;  // bytes of the current line appended by earlier buffer fills (append_line)
     gzFile f_ = nullptr;
     std::unique_ptr<BgzfSource> bgzf_;
     char buf_[1 << 16];
@@ -222,9 +265,9 @@ inline bool read_fastx(const std::string &path, FlatRecords &out, bool want_ids,
             if (want_ids) out.ids.push_back(line.substr(1));
             first = false;
             more = false;
-            while (lr.next(line)) {
-                if (!line.empty() && line[0] == '>') { more = true; break; }
-                out.bases.insert(out.bases.end(), line.begin(), line.end());
+            for (int c0; (c0 = lr.peek()) >= 0;) {   // sequence lines go straight into the flat buffer
+                if (c0 == '>') { more = lr.next(line); break; }
+                lr.append_line(out.bases);
             }
             out.offsets.push_back(out.bases.size());
         }
@@ -236,11 +279,10 @@ inline bool read_fastx(const std::string &path, FlatRecords &out, bool want_ids,
             if (first && first_id) *first_id = line.substr(1);
             if (want_ids) out.ids.push_back(line.substr(1));
             first = false;
-            std::string seq, plus, qual;
             // a record without its sequence, '+' or quality line is an invalid file (needletail reports an
-            // error for the record; sylph then drops the file, src/sketch.rs:909-915)
-            if (!lr.next(seq) || !lr.next(plus) || plus.empty() || plus[0] != '+' || !lr.next(qual)) return false;
-            out.bases.insert(out.bases.end(), seq.begin(), seq.end());
+            // error for the record; sylph then drops the file, src/sketch.rs:909-915).  The sequence goes straight
+            // into the flat buffer; the '+' and quality lines are skipped without being copied.
+            if (!lr.append_line(out.bases) || lr.peek() != '+' || !lr.skip_line() || !lr.skip_line()) return false;
             out.offsets.push_back(out.bases.size());
             do { if (!lr.next(line)) return !lr.failed(); } while (line.empty());
         }
