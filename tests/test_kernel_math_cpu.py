@@ -274,3 +274,38 @@ def test_bootstrap_class_boundaries_on_the_raw_draw():
                 lo = (x * n) % M
                 if lo < n:
                     assert ((x & 0xFFFFFFFF) * n) & 0xFFFFFFFF < n
+
+
+def test_tiled_join_ranges_partition_every_sample():
+    """for_each_key's tiled mapping (contain.cu): rb[s][r] = first key of sample s whose db bucket is >= r * bpr, found by
+    binary search on the sample's sorted hashes.  The R cells of a sample must be disjoint, cover all its keys, and put a
+    key into the cell of its own bucket — whatever the sample size, including empty samples and R > number of buckets."""
+    rng = np.random.default_rng(17)
+    M64 = (1 << 64) - 1
+    for trial in range(60):
+        NB = int(rng.integers(1, 5000))
+        M = int(rng.integers(1, 1 << 40))                       # bucket = min(mulhi(key, M), NB - 1), monotone in the key
+        max_n = int(rng.integers(1, 4000))
+        R = min(max(max_n // 100, 1), max(NB, 1)) if trial % 3 else int(rng.integers(1, 2 * NB + 2))
+        bpr = (NB + R - 1) // R
+
+        def bucket(k):
+            return min((k * M) >> 64, NB - 1)
+
+        for n in (0, 1, max_n, int(rng.integers(0, max_n + 1))):
+            keys = np.sort(rng.integers(0, M64, size=n, dtype=np.uint64)).tolist()
+            rb = []
+            for r in range(R + 1):
+                want = r * bpr
+                lo, hi = (n, n) if r == R else (0, n)
+                while lo < hi:
+                    mid = (lo + hi) >> 1
+                    if bucket(keys[mid]) < want:
+                        lo = mid + 1
+                    else:
+                        hi = mid
+                rb.append(lo)
+            assert rb[0] == 0 and rb[R] == n and all(a <= b for a, b in zip(rb, rb[1:]))
+            for r in range(R):
+                for i in range(rb[r], rb[r + 1]):
+                    assert r * bpr <= bucket(keys[i]) < (r + 1) * bpr
