@@ -88,3 +88,112 @@ def test_gloo_gather_and_merge(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+class _FakeJob:
+    """Stand-in for api.ProfileJob on CPU tensors: records the order of the stages and checks, stage by stage, that the
+    collective before it delivered every rank's contribution (what the library's kernels rely on)."""
+
+    def __init__(self, ctx, rows_per_rank):
+        import torch
+        self.ctx, self.R = ctx, rows_per_rank if rows_per_rank else 4
+        w, r = ctx.world, ctx.rank
+        self.b = dict(table1=torch.full((8,), 10 + r, dtype=torch.uint8), gathered1=torch.zeros(8 * w, dtype=torch.uint8),
+                      winner=torch.full((5,), 1000, dtype=torch.int32), table2=torch.zeros(8, dtype=torch.uint8),
+                      gathered2=torch.zeros(8 * w, dtype=torch.uint8))
+        ctx.log.append("begin(R=%d)" % self.R)
+
+    def buffers(self):
+        return self.b
+
+    def rank(self):
+        w, r = self.ctx.world, self.ctx.rank
+        assert self.b["gathered1"].view(w, 8)[:, 0].tolist() == [10 + i for i in range(w)]   # every rank's pass-1 table
+        self.b["winner"][:] = 1000
+        self.b["winner"][r % 5] = 7 + r          # this shard's best order for "its" keys
+        self.ctx.log.append("rank")
+
+    def pass2(self):
+        w = self.ctx.world
+        want = [1000] * 5
+        for i in range(w):
+            want[i % 5] = min(want[i % 5], 7 + i)
+        assert self.b["winner"].tolist() == want                                             # MIN over the shards
+        self.b["table2"][:] = 50 + self.ctx.rank
+        self.ctx.log.append("pass2")
+
+    def finish(self):
+        from sylph_b200 import _lib
+        from sylph_b200.api import ANI_ROW_DTYPE
+        w = self.ctx.world
+        assert self.b["gathered2"].view(w, 8)[:, 0].tolist() == [50 + i for i in range(w)]   # every rank's pass-2 table
+        self.ctx.log.append("finish")
+        if self.ctx.mode == "unsupported":
+            return None, _lib.SYL_ERR_UNSUPPORTED, 0
+        if self.R < 300:                                   # same verdict on every rank (the headers were gathered)
+            return None, _lib.SYL_ERR_CAPACITY, 300
+        rows = np.zeros(w, dtype=ANI_ROW_DTYPE)
+        rows["genome"] = np.arange(w)
+        return rows, _lib.SYL_OK, 0
+
+    def free(self):
+        self.ctx.log.append("free")
+
+
+class _FakeCtx:
+    def __init__(self, rank, world, mode):
+        self.rank, self.world, self.mode, self.log, self._stream = rank, world, mode, [], 0
+
+    def profile_shard_begin(self, db, samples, params, world, rank, rows_per_rank):
+        assert (world, rank) == (self.world, self.rank)
+        return _FakeJob(self, rows_per_rank)
+
+    def sync(self):
+        pass
+
+
+def _worker_profile(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sylph_b200 import dist as D
+    try:
+        # 1. an undersized row table: every rank retries once with the size the gathered headers ask for
+        ctx = _FakeCtx(rank, world, "ok")
+        rows = D.profile_sharded(ctx, None, None, [], 0, params=object())
+        assert len(rows) == world
+        stage = ["rank", "pass2", "finish", "free"]
+        assert ctx.log == ["begin(R=4)"] + stage + ["begin(R=556)"] + stage, ctx.log
+        # 2. the >= 256-count case: every rank falls back to the gathered-survivor formulation
+        ctx = _FakeCtx(rank, world, "unsupported")
+        called = []
+        orig = D.profile_sharded_gather
+        D.profile_sharded_gather = lambda *a, **k: called.append(1) or "fallback"
+        try:
+            assert D.profile_sharded(ctx, None, None, [], 0, params=object()) == "fallback" and called == [1]
+        finally:
+            D.profile_sharded_gather = orig
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_profile_sharded_control_flow(world):
+    """The three collectives of the sharded profile sit between the library's stages in the right order, move every
+    rank's table / the minimum of the winner orders, and all ranks take the same retry / fallback decision."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_profile, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
